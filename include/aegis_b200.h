@@ -1,0 +1,264 @@
+/* aegis_b200.h -- C ABI of the B200-native Aegis audio-analysis hot path (libaegis_b200.so).
+ *
+ * The reference (avabag01-ai/spectrogram-midi, "Aegis Engine") has no FFI: its hot path is a set
+ * of Python calls into librosa/numpy.  Each entry point below names the reference call site(s) it
+ * replaces (paths relative to the reference checkout).  The Python host layer
+ * (spectrogram-midi_b200/) binds these with ctypes and mirrors the reference's call signatures;
+ * INTEGRATION.md shows the binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its comment says "host"; the library never
+ *    allocates, frees or synchronises: outputs and workspaces are caller-provided, work is
+ *    enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*).
+ *  - return value 0 = enqueued; non-zero = error, text via aegis_last_error() (thread local).
+ *    Nothing is thrown across the ABI.
+ *  - n_fft == frame_length == 2048 everywhere (the reference never uses another size,
+ *    aegis_engine.py:17); 4 <= hop <= 512 and hop % 4 == 0.
+ *  - frame t of a clip covers samples [t*hop - pad, t*hop - pad + 2048) with zeros outside
+ *    [0, n_samples): pad = 1024 is librosa's center=True / pad_mode='constant'.
+ */
+#ifndef AEGIS_B200_H
+#define AEGIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AEGIS_N_FFT 2048
+#define AEGIS_N_BINS 1025
+#define AEGIS_ABI_VERSION 1
+
+int aegis_abi_version(void);
+const char* aegis_last_error(void);
+/* Number of SMs of the current device (host query helper for grid sizing in benches). */
+int aegis_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  fused frame-gather + Hann window + FP32 FFT -> |X|, mel power, frame RMS
+ * replaces: librosa.feature.melspectrogram -> librosa.stft   (aegis_engine.py:25,
+ *           aegis_engine_financial.py:46-50) and librosa.feature.rms (aegis_engine.py:70,
+ *           aegis_engine_financial.py:154).
+ * Any of mag / mel / rms may be NULL (skipped).  mel_max (if mel != NULL) receives the per-clip
+ * maximum of the mel power via atomicMax and must be zero-filled by the caller beforehand.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* y;            /* [n_clips][clip_stride] audio, float32 */
+    int64_t clip_stride;       /* samples between clip starts */
+    int64_t n_samples;         /* valid samples per clip */
+    int32_t n_clips;
+    int32_t hop;
+    int32_t pad;               /* virtual zero samples before sample 0 (1024 = center) */
+    int32_t n_frames;          /* T */
+    const float* window;       /* [2048] analysis window */
+    const float* twiddle;      /* [2048][2] (cos, -sin)(2 pi k / 2048) */
+    float* mag;                /* [n_clips][1025][mag_row_stride]  |X| or NULL */
+    int64_t mag_clip_stride;
+    int32_t mag_row_stride;    /* >= T; == T gives librosa's dense [1025, T] */
+    int32_t n_mels;
+    float* mel;                /* [n_clips][n_mels][mel_row_stride] mel power or NULL */
+    int64_t mel_clip_stride;
+    int32_t mel_row_stride;
+    int32_t _reserved0;
+    const int32_t* mel_start;  /* [n_mels] first FFT bin of each triangle */
+    const int32_t* mel_len;    /* [n_mels] */
+    const int32_t* mel_off;    /* [n_mels] offset into mel_w */
+    const float* mel_w;        /* packed non-zero triangle weights */
+    float* mel_max;            /* [n_clips] or NULL */
+    float* rms;                /* [n_clips][rms_clip_stride] or NULL */
+    int64_t rms_clip_stride;
+} aegis_stft_params;
+
+int aegis_stft_fused(const aegis_stft_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4a mel power -> dB (ref = clip max, top_db 80), rake-noise mask, spectral-flux onset envelope
+ * replaces: librosa.power_to_db(S, ref=np.max) (aegis_engine.py:26),
+ *           detect_rake_patterns (aegis_engine_core/vision.py:3-38),
+ *           librosa.onset.onset_strength (no reference call site; BASELINE north_star).
+ * s_db / rake_mask / onset_env may each be NULL.  env_minmax[2*clip+{0,1}] receives min / max of
+ * the envelope (caller pre-fills with +inf / 0).  With input_is_db = 1 the kernel applies the rake
+ * test to a caller-supplied dB image (the signature of detect_rake_patterns(S_dB, ...)).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* mel;          /* [n_clips][n_mels][mel_row_stride] mel power */
+    int64_t mel_clip_stride;
+    int32_t mel_row_stride;
+    int32_t n_mels;
+    int32_t n_clips;
+    int32_t n_frames;
+    const float* mel_max;      /* [n_clips] max mel power of each clip */
+    float* s_db;               /* [n_clips][n_mels][sdb_row_stride] or NULL */
+    int64_t sdb_clip_stride;
+    int32_t sdb_row_stride;
+    int32_t rake_min_frames;   /* int(10 / ms_per_frame) */
+    int32_t rake_max_frames;   /* int(30 / ms_per_frame) */
+    int32_t onset_pad;         /* lag + n_fft/(2*hop) = 3 for the defaults */
+    double rake_ratio;         /* broadband_threshold_ratio */
+    uint8_t* rake_mask;        /* [n_clips][n_frames] or NULL */
+    float* onset_env;          /* [n_clips][n_frames] or NULL */
+    float* env_minmax;         /* [n_clips][2] or NULL */
+    const float* ref_power;    /* [n_clips] reference power for the dB output; NULL = mel_max (ref=np.max) */
+    int32_t input_is_db;       /* 1: `mel` already holds dB values (rake mask only; mel_max unused) */
+    int32_t _reserved0;
+} aegis_melpost_params;
+
+int aegis_mel_post(const aegis_melpost_params* p, void* stream);
+
+/* K4b greedy peak picking on the normalised onset envelope (librosa.util.peak_pick semantics).
+ * peaks[clip][t] = 1 at onset frames; n_peaks[clip] = count. */
+typedef struct {
+    const float* onset_env;    /* [n_clips][n_frames] */
+    const float* env_minmax;   /* [n_clips][2] */
+    int32_t n_clips;
+    int32_t n_frames;
+    int32_t pre_max, post_max, pre_avg, post_avg, wait;
+    int32_t normalize;
+    double delta;
+    uint8_t* cand;             /* workspace [n_clips][n_frames] */
+    uint8_t* peaks;            /* [n_clips][n_frames] */
+    int32_t* n_peaks;          /* [n_clips] */
+} aegis_peaks_params;
+
+int aegis_onset_peaks(const aegis_peaks_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  batched YIN: FFT difference function -> CMND -> parabolic interpolation -> trough /
+ *     beta-threshold / Boltzmann-prior candidate probabilities -> sparse pitch-bin observations
+ * replaces: librosa.pyin stages 1-9 (call sites aegis_engine.py:63,67,190,216;
+ *           aegis_engine_core/worker.py:9-15; aegis_engine_financial.py:63-69).
+ * Per frame: cand_count[f] candidates (bin ascending, unique), voiced_prob[f] (float64).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* y;
+    int64_t clip_stride;
+    int64_t n_samples;
+    int32_t n_clips;
+    int32_t hop;
+    int32_t pad;
+    int32_t n_frames;
+    const float* twiddle;      /* [2048][2] */
+    double sr;
+    double fmin;
+    int32_t min_period;
+    int32_t max_period;
+    int32_t n_pitch_bins;
+    int32_t bins_per_semitone;
+    int32_t n_thresholds;      /* 100 */
+    int32_t max_cand;          /* capacity per frame of cand_bin / cand_prob */
+    const double* thresholds;  /* [n_thresholds] upper edges */
+    const double* beta_probs;  /* [n_thresholds] */
+    const double* beta_cumsum; /* [n_thresholds + 1] */
+    const double* boltz_fact;  /* [max_troughs + 1] */
+    const double* boltz_exp;   /* [max_troughs + 1] */
+    double no_trough_prob;
+    uint16_t* cand_bin;        /* [n_clips * n_frames][max_cand] */
+    double* cand_prob;         /* [n_clips * n_frames][max_cand] (librosa keeps the CMND in float64) */
+    int32_t* cand_count;       /* [n_clips * n_frames] */
+    double* voiced_prob;       /* [n_clips * n_frames] */
+    int32_t* overflow;         /* [1]: set non-zero if any frame had more than max_cand candidates */
+} aegis_yin_params;
+
+int aegis_yin_candidates(const aegis_yin_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  pitch/voicing HMM Viterbi decode (2*n_pitch_bins states, banded transitions, exact
+ *     out-of-band log(tiny) competitors, float64, first-index tie-breaking)
+ * replaces: librosa.sequence.viterbi inside librosa.pyin (same call sites as K2).
+ * One chain per clip.  backptr is workspace: [n_clips][n_frames][2*n_pitch_bins] uint16.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_clips;
+    int32_t n_frames;
+    int32_t n_pitch_bins;
+    int32_t half_width;
+    int32_t n_variants;
+    int32_t n_interior_variants;
+    int32_t max_cand;
+    int32_t _reserved0;
+    const uint16_t* cand_bin;
+    const double* cand_prob;
+    const int32_t* cand_count;
+    const double* voiced_prob;
+    const double* lt_variants; /* [n_variants][2][2*half_width+1] log transition bands */
+    const int32_t* row_variant;/* [n_pitch_bins] */
+    const double* freqs;       /* [n_pitch_bins] */
+    double log_tiny;
+    double log_init_unvoiced;
+    double fill_value;         /* f0 for unvoiced frames (NaN for librosa's default) */
+    uint16_t* backptr;         /* workspace */
+    double* final_value;       /* workspace [n_clips][2*n_pitch_bins] */
+    uint16_t* states;          /* [n_clips][n_frames] */
+    double* f0;                /* [n_clips][n_frames] */
+    uint8_t* voiced_flag;      /* [n_clips][n_frames] */
+} aegis_viterbi_params;
+
+int aegis_viterbi(const aegis_viterbi_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  batched float64 trend filters on f0 series (NaN = unvoiced)
+ * replaces: FinancialNoiseFilters.{savitzky_golay,kalman_filter,holt_winters} and
+ *           multi_filter_consensus (aegis_engine_core_v2/financial_filters.py:25-141,256-298);
+ *           FinancialPitchAnalyzer.{simple_moving_average,exponential_moving_average,
+ *           bollinger_bands,macd} (aegis_engine_core_v2/financial_analysis.py:45-146,203-226).
+ * All series are [n_series][n] float64, row stride = n.  Any output may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const double* x;
+    int32_t n_series;
+    int32_t n;
+    const double* savgol_coeffs; /* [savgol_window] correlation weights */
+    int32_t savgol_window;
+    int32_t sma_window;
+    int32_t ema_span;
+    int32_t boll_window;
+    int32_t macd_fast, macd_slow, macd_signal;
+    int32_t _reserved0;
+    double kalman_q, kalman_r;
+    double holt_alpha, holt_beta;
+    double boll_num_std;
+    double* compact;           /* workspace [n_series][n] */
+    double* scratch;           /* workspace [n_series][n] */
+    double* savgol;
+    double* kalman;
+    double* holt;
+    double* consensus;
+    double* consensus_conf;
+    double* sma;
+    double* ema;
+    double* boll_ma;
+    double* boll_upper;
+    double* boll_lower;
+    double* macd_line;
+    double* macd_sig;
+    double* macd_hist;
+} aegis_trend_params;
+
+int aegis_trend_filters(const aegis_trend_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Corpus synthesis on device (Karplus-Strong plucks + noise rakes, generate_test_signal.py:5-53)
+ * One event per note/rake; events of a clip do not overlap.  out must be zero-filled.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    float* out;                /* [n_clips][clip_stride] */
+    int64_t clip_stride;
+    int32_t n_events;
+    int32_t _reserved0;
+    const int32_t* ev_clip;    /* [n_events] */
+    const int32_t* ev_start;   /* [n_events] first sample */
+    const int32_t* ev_len;     /* [n_events] samples */
+    const int32_t* ev_period;  /* [n_events] KS delay length; 0 = noise rake */
+    const float* ev_amp;       /* [n_events] */
+    const uint32_t* ev_seed;   /* [n_events] */
+    float decay;
+    float _reserved1;
+} aegis_synth_params;
+
+int aegis_synth_ks(const aegis_synth_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AEGIS_B200_H */

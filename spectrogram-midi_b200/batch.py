@@ -1,0 +1,151 @@
+"""Batched perception on one GPU: the whole Aegis analysis front end for many clips at once.
+
+This is the data-parallel form of ``AegisEngine.audio_to_midi`` (aegis_engine.py:41-75): every
+clip is independent (all ``ref=np.max`` are per clip), so a batch is just a leading dimension and
+multi-GPU work is a partition of clip indices (``shard_range``) with no data-path collective.
+Inputs and outputs are CUDA tensors; ``to_host`` converts a result to the reference's dict of
+numpy arrays.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import core, tables
+
+E2 = tables.note_to_hz("E2")
+C6 = tables.note_to_hz("C6")
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> range:
+    """Contiguous, balanced partition of ``n_items`` clip indices (first ``n % world`` ranks get one more)."""
+    base, extra = divmod(n_items, world_size)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def spectral_features(y: torch.Tensor, *, sr: float, hop_length: int = 512, rake_sensitivity: float = 0.6,
+                      with_mag: bool = False, with_sdb: bool = False, with_rake: bool = True,
+                      with_onsets: bool = True, with_rms: bool = True, mag_out: Optional[torch.Tensor] = None) -> dict:
+    """STFT |X| / mel dB / rake mask / RMS / onset envelope + onset frames for a batch (BASELINE cfg2)."""
+    feat = core.stft_features(y, sr=sr, hop_length=hop_length, want_mag=with_mag, want_mel=True,
+                              want_rms=with_rms, mag_out=mag_out)
+    post = core.mel_post(feat["mel"], feat["mel_max"], sr=sr, hop_length=hop_length, rake_ratio=rake_sensitivity,
+                         want_sdb=with_sdb, want_rake=with_rake, want_onset=with_onsets)
+    out = {"n_frames": feat["n_frames"]}
+    if with_mag:
+        out["mag"] = feat["mag"]
+    if with_rms:
+        out["rms"] = feat["rms"]
+    if with_sdb:
+        out["S_dB"] = post["S_dB"]
+    if with_rake:
+        out["rake_mask"] = post["rake_mask"]
+    if with_onsets:
+        out["onset_env"] = post["onset_env"]
+        pk = core.onset_peaks(post["onset_env"], post["env_minmax"], sr=sr, hop_length=hop_length)
+        out["onset_peaks"], out["n_onsets"] = pk["peaks"], pk["n_peaks"]
+    return out
+
+
+def analyze_batch(y: torch.Tensor, *, sr: float, hop_length: int = 512, rake_sensitivity: float = 0.6,
+                  fmin: float = E2, fmax: float = C6, with_sdb: bool = False, with_onsets: bool = False,
+                  with_trend: bool = False, nan_to_num: bool = True, clips_per_launch: Optional[int] = None) -> dict:
+    """Full perception phase for a batch: keys of aegis_engine.py:72-75 (+ optional extras).
+
+    ``f0`` follows v1 (`np.nan_to_num`, aegis_engine.py:69) unless ``nan_to_num=False`` (v2 keeps NaN,
+    aegis_engine_financial.py:122).  ``with_trend`` adds ``multi_filter_consensus`` on the NaN-masked f0
+    (midi_logic_financial.py:158-161).
+    """
+    spec = spectral_features(y, sr=sr, hop_length=hop_length, rake_sensitivity=rake_sensitivity,
+                             with_sdb=with_sdb, with_onsets=with_onsets)
+    pit = core.pyin_batch(y, sr=sr, fmin=fmin, fmax=fmax, hop_length=hop_length, clips_per_launch=clips_per_launch)
+    f0_nan = pit["f0"]
+    out = {
+        "rake_mask": spec["rake_mask"], "voiced_flag": pit["voiced_flag"], "voiced_probs": pit["voiced_prob"],
+        "rms": spec["rms"], "f0": torch.nan_to_num(f0_nan, nan=0.0) if nan_to_num else f0_nan,
+        "states": pit["states"], "n_frames": spec["n_frames"],
+    }
+    for k in ("S_dB", "onset_env", "onset_peaks", "n_onsets"):
+        if k in spec:
+            out[k] = spec[k]
+    if with_trend:
+        tr = core.trend_filters(f0_nan, want=("consensus", "consensus_conf"))
+        out["trend"], out["trend_conf"] = tr["consensus"], tr["consensus_conf"]
+    return out
+
+
+def to_host(result: dict, clip: int, y: Optional[np.ndarray] = None) -> dict:
+    """One clip of a batch result as the reference's perception dict (numpy, aegis_engine.py:72-75)."""
+    host = {
+        "rake_mask": result["rake_mask"][clip].cpu().numpy().astype(bool),
+        "f0": result["f0"][clip].cpu().numpy(),
+        "voiced_flag": result["voiced_flag"][clip].cpu().numpy().astype(bool),
+        "voiced_probs": result["voiced_probs"][clip].cpu().numpy(),
+        "rms": result["rms"][clip].cpu().numpy(),
+    }
+    if y is not None:
+        host["y"] = y
+    for k in ("S_dB", "onset_env", "trend", "trend_conf"):
+        if k in result:
+            host[k] = result[k][clip].cpu().numpy()
+    if "onset_peaks" in result:
+        host["onset_frames"] = np.flatnonzero(result["onset_peaks"][clip].cpu().numpy())
+    return host
+
+
+class HostPipeline:
+    """Host-buffer plugin call for batches: pinned host audio in, host results out.
+
+    The batch is cut into chunks of ``chunk_clips`` clips; chunk i+1 is copied host->device on a copy
+    stream while chunk i runs through the kernels (double-buffered device input), and the small
+    per-frame results (RMS, onset envelope, onset flags) are copied back as each chunk finishes.
+    |X| is produced in HBM per chunk (it is the input of the onset path) and not copied to the host.
+    """
+
+    def __init__(self, n_clips: int, n_samples: int, *, sr: float, hop_length: int = 512, device=None, chunk_clips: int = 128):
+        self.sr, self.hop = sr, hop_length
+        self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.n_clips, self.n_samples = n_clips, n_samples
+        self.chunk = min(chunk_clips, n_clips)
+        self.T = core.frame_count(n_samples, hop_length)
+        self.inbuf = [torch.empty((self.chunk, n_samples), dtype=torch.float32, device=self.dev) for _ in range(2)]
+        self.mag = torch.empty((self.chunk, core.N_BINS, self.T), dtype=torch.float32, device=self.dev)
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.in_ready = [torch.cuda.Event() for _ in range(2)]
+        self.in_free = [torch.cuda.Event() for _ in range(2)]
+        self.rms = torch.empty((n_clips, self.T), dtype=torch.float32, pin_memory=True)
+        self.env = torch.empty((n_clips, self.T), dtype=torch.float32, pin_memory=True)
+        self.peaks = torch.empty((n_clips, self.T), dtype=torch.uint8, pin_memory=True)
+        self.h2d_bytes = n_clips * n_samples * 4
+        self.d2h_bytes = n_clips * self.T * (4 + 4 + 1)
+
+    def run(self, y_host: torch.Tensor) -> dict:
+        if y_host.is_cuda or y_host.shape != (self.n_clips, self.n_samples):
+            raise ValueError("expected a host tensor [n_clips, n_samples]")
+        main = torch.cuda.current_stream(self.dev)
+        starts = list(range(0, self.n_clips, self.chunk))
+        for b in range(2):
+            self.in_free[b].record(main)
+        for i, c0 in enumerate(starts):
+            b = i & 1
+            n = min(self.chunk, self.n_clips - c0)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.in_free[b])
+                self.inbuf[b][:n].copy_(y_host[c0 : c0 + n], non_blocking=True)
+                self.in_ready[b].record(self.copy_stream)
+            main.wait_event(self.in_ready[b])
+            yb = self.inbuf[b][:n]
+            feat = core.stft_features(yb, sr=self.sr, hop_length=self.hop, want_mag=True, want_mel=True, want_rms=True,
+                                      mag_out=self.mag[:n])
+            post = core.mel_post(feat["mel"], feat["mel_max"], sr=self.sr, hop_length=self.hop, want_sdb=False,
+                                 want_rake=False, want_onset=True)
+            pk = core.onset_peaks(post["onset_env"], post["env_minmax"], sr=self.sr, hop_length=self.hop)
+            self.in_free[b].record(main)
+            self.rms[c0 : c0 + n].copy_(feat["rms"], non_blocking=True)
+            self.env[c0 : c0 + n].copy_(post["onset_env"], non_blocking=True)
+            self.peaks[c0 : c0 + n].copy_(pk["peaks"], non_blocking=True)
+        main.synchronize()
+        return {"rms": self.rms, "onset_env": self.env, "onset_peaks": self.peaks}

@@ -1,0 +1,348 @@
+"""Device-level batched operators: torch CUDA tensors in, torch CUDA tensors out.
+
+torch is plumbing only (device memory, streams); every numeric step is a hand-written sm_100a
+kernel in libaegis_b200.so reached through the C ABI.  Inputs are batches of equally long clips
+``y[n_clips, n_samples]`` (float32, contiguous rows).  No function here has a CPU path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import tables
+
+N_FFT = tables.N_FFT
+N_BINS = tables.N_BINS
+
+_table_cache: dict = {}
+
+
+def _dev_tensor(key, device, make):
+    k = (key, str(device))
+    t = _table_cache.get(k)
+    if t is None:
+        t = torch.from_numpy(np.ascontiguousarray(make())).to(device)
+        _table_cache[k] = t
+    return t
+
+
+def _audio_ptr(y: torch.Tensor) -> int:
+    """Device pointer of the audio; an empty tensor has none, so hand the kernels a dummy word."""
+    if y.numel():
+        return y.data_ptr()
+    return _dev_tensor("dummy", y.device, lambda: np.zeros(4, np.float32)).data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _check_audio(y: torch.Tensor) -> torch.Tensor:
+    if not isinstance(y, torch.Tensor) or not y.is_cuda:
+        raise nat.AegisNativeError("expected a CUDA tensor: the Aegis B200 path has no CPU implementation")
+    if y.dim() == 1:
+        y = y[None]
+    if y.dtype != torch.float32:
+        y = y.float()
+    if y.stride(-1) != 1:
+        y = y.contiguous()
+    return y
+
+
+def frame_count(n_samples: int, hop_length: int, center: bool = True) -> int:
+    if center:
+        return 1 + n_samples // hop_length
+    return 1 + (n_samples - N_FFT) // hop_length if n_samples >= N_FFT else 0
+
+
+def _check_fft(n_fft: int, hop_length: int):
+    if n_fft != N_FFT:
+        raise NotImplementedError(f"n_fft/frame_length={n_fft}: the B200 kernels are built for 2048 (aegis_engine.py:17)")
+    if hop_length < 4 or hop_length > 512 or hop_length % 4:
+        raise NotImplementedError(f"hop_length={hop_length}: supported 4..512, multiple of 4")
+
+
+# ----------------------------------------------------------------------------------------------
+# K1
+# ----------------------------------------------------------------------------------------------
+def stft_features(y: torch.Tensor, *, sr: Optional[float] = None, hop_length: int = 512, n_fft: int = N_FFT,
+                  center: bool = True, n_mels: int = 128, want_mag: bool = True, want_mel: bool = False,
+                  want_rms: bool = False, mag_out: Optional[torch.Tensor] = None) -> dict:
+    """Fused STFT magnitude / mel power / RMS of a batch of clips.
+
+    Returns a dict with the requested keys: ``mag`` [n_clips, 1025, T], ``mel`` [n_clips, n_mels, T],
+    ``mel_max`` [n_clips], ``rms`` [n_clips, T] (all float32, librosa layouts).
+    """
+    _check_fft(n_fft, hop_length)
+    y = _check_audio(y)
+    dev = y.device
+    n_clips, n_samples = y.shape
+    T = frame_count(n_samples, hop_length, center)
+    out: dict = {"n_frames": T}
+    P = nat.StftParams()
+    P.y, P.clip_stride, P.n_samples, P.n_clips = _audio_ptr(y), y.stride(0), n_samples, n_clips
+    P.hop, P.pad, P.n_frames = hop_length, (N_FFT // 2 if center else 0), T
+    P.window = _dev_tensor("hann32", dev, lambda: tables.hann_window().astype(np.float32)).data_ptr()
+    P.twiddle = _dev_tensor("twiddle", dev, tables.fft_twiddles).data_ptr()
+    if want_mag:
+        mag = mag_out if mag_out is not None else torch.empty((n_clips, N_BINS, T), dtype=torch.float32, device=dev)
+        if mag.shape != (n_clips, N_BINS, T) or mag.dtype != torch.float32 or mag.stride(2) != 1 and T > 1:
+            raise ValueError("mag_out must be float32 [n_clips, 1025, T] with unit stride along T")
+        P.mag, P.mag_clip_stride, P.mag_row_stride = mag.data_ptr(), mag.stride(0), mag.stride(1)
+        out["mag"] = mag
+    if want_mel:
+        if sr is None:
+            raise ValueError("sr is required for the mel projection")
+        sm = tables.sparse_mel(float(sr), N_FFT, n_mels)
+        key = ("mel", float(sr), n_mels)
+        P.mel_start = _dev_tensor(key + ("s",), dev, lambda: sm.start).data_ptr()
+        P.mel_len = _dev_tensor(key + ("l",), dev, lambda: sm.length).data_ptr()
+        P.mel_off = _dev_tensor(key + ("o",), dev, lambda: sm.offset).data_ptr()
+        P.mel_w = _dev_tensor(key + ("w",), dev, lambda: sm.weights).data_ptr()
+        mel = torch.empty((n_clips, n_mels, T), dtype=torch.float32, device=dev)
+        mel_max = torch.zeros((n_clips,), dtype=torch.float32, device=dev)
+        P.n_mels = n_mels
+        P.mel, P.mel_clip_stride, P.mel_row_stride = mel.data_ptr(), mel.stride(0), mel.stride(1)
+        P.mel_max = mel_max.data_ptr()
+        out["mel"], out["mel_max"] = mel, mel_max
+    if want_rms:
+        rms = torch.empty((n_clips, T), dtype=torch.float32, device=dev)
+        P.rms, P.rms_clip_stride = rms.data_ptr(), rms.stride(0)
+        out["rms"] = rms
+    nat.call("aegis_stft_fused", P, _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# K4
+# ----------------------------------------------------------------------------------------------
+def mel_post(mel: torch.Tensor, mel_max: Optional[torch.Tensor], *, sr: float, hop_length: int = 512,
+             rake_ratio: float = 0.6, want_sdb: bool = True, want_rake: bool = True,
+             want_onset: bool = False, n_fft: int = N_FFT, center: bool = True, lag: int = 1,
+             ref_power: Optional[torch.Tensor] = None, input_is_db: bool = False) -> dict:
+    """dB conversion (ref = clip max unless ``ref_power``, top_db 80), rake mask, onset envelope.
+
+    With ``input_is_db`` the first argument already is a dB image [n_clips, n_mels, T] and only the
+    rake mask is produced (the call shape of ``detect_rake_patterns``).
+    """
+    if lag != 1:
+        raise NotImplementedError("onset lag != 1")
+    if mel.dtype != torch.float32 or mel.stride(2) != 1:
+        mel = mel.float().contiguous()
+    n_clips, n_mels, T = mel.shape
+    dev = mel.device
+    P = nat.MelPostParams()
+    P.mel, P.mel_clip_stride, P.mel_row_stride = mel.data_ptr(), mel.stride(0), mel.stride(1)
+    P.n_mels, P.n_clips, P.n_frames = n_mels, n_clips, T
+    P.mel_max = None if mel_max is None else mel_max.data_ptr()
+    P.ref_power = None if ref_power is None else ref_power.data_ptr()
+    P.input_is_db = int(bool(input_is_db))
+    if input_is_db:
+        want_sdb = want_onset = False
+    lo, hi = tables.rake_frame_limits(hop_length, sr)
+    P.rake_min_frames, P.rake_max_frames, P.rake_ratio = lo, hi, float(rake_ratio)
+    P.onset_pad = lag + (n_fft // (2 * hop_length) if center else 0)
+    out: dict = {}
+    if want_sdb:
+        s_db = torch.empty_like(mel)
+        P.s_db, P.sdb_clip_stride, P.sdb_row_stride = s_db.data_ptr(), s_db.stride(0), s_db.stride(1)
+        out["S_dB"] = s_db
+    if want_rake:
+        mask = torch.empty((n_clips, T), dtype=torch.uint8, device=dev)
+        P.rake_mask = mask.data_ptr()
+        out["rake_mask"] = mask
+    if want_onset:
+        # every index is written except possibly none when T < pad; start from zeros to be safe
+        env = torch.zeros((n_clips, T), dtype=torch.float32, device=dev)
+        mm = torch.empty((n_clips, 2), dtype=torch.float32, device=dev)
+        mm[:, 0] = float("inf")
+        mm[:, 1] = 0.0
+        P.onset_env, P.env_minmax = env.data_ptr(), mm.data_ptr()
+        out["onset_env"], out["env_minmax"] = env, mm
+    nat.call("aegis_mel_post", P, _stream())
+    return out
+
+
+def onset_peaks(onset_env: torch.Tensor, env_minmax: torch.Tensor, *, sr: float, hop_length: int = 512,
+                normalize: bool = True, **overrides) -> dict:
+    """``librosa.onset.onset_detect`` peak picking; returns ``peaks`` uint8 [n_clips, T], ``n_peaks``."""
+    n_clips, T = onset_env.shape
+    dev = onset_env.device
+    prm = tables.onset_peak_params(sr, hop_length)
+    prm.update(overrides)
+    P = nat.PeaksParams()
+    P.onset_env, P.env_minmax, P.n_clips, P.n_frames = onset_env.data_ptr(), env_minmax.data_ptr(), n_clips, T
+    P.pre_max, P.post_max, P.pre_avg, P.post_avg = int(prm["pre_max"]), int(prm["post_max"]), int(prm["pre_avg"]), int(prm["post_avg"])
+    P.wait, P.normalize, P.delta = int(prm["wait"]), int(bool(normalize)), float(prm["delta"])
+    cand = torch.empty((n_clips, T), dtype=torch.uint8, device=dev)
+    peaks = torch.empty((n_clips, T), dtype=torch.uint8, device=dev)
+    n_peaks = torch.empty((n_clips,), dtype=torch.int32, device=dev)
+    P.cand, P.peaks, P.n_peaks = cand.data_ptr(), peaks.data_ptr(), n_peaks.data_ptr()
+    nat.call("aegis_onset_peaks", P, _stream())
+    return {"peaks": peaks, "n_peaks": n_peaks}
+
+
+# ----------------------------------------------------------------------------------------------
+# K2 + K3
+# ----------------------------------------------------------------------------------------------
+def yin_candidates(y: torch.Tensor, cfg: tables.PyinConfig, *, center: bool = True,
+                   max_cand: Optional[int] = None) -> dict:
+    """Sparse pYIN observations per frame (bins ascending, unique) + voiced probability."""
+    _check_fft(cfg.frame_length, cfg.hop_length)
+    y = _check_audio(y)
+    dev = y.device
+    n_clips, n_samples = y.shape
+    T = frame_count(n_samples, cfg.hop_length, center)
+    if max_cand is None:
+        max_cand = cfg.max_troughs
+    n_fr = n_clips * T
+    key = ("pyin", cfg.sr, cfg.hop_length, cfg.fmin, cfg.fmax, cfg.n_thresholds)
+    P = nat.YinParams()
+    P.y, P.clip_stride, P.n_samples, P.n_clips = _audio_ptr(y), y.stride(0), n_samples, n_clips
+    P.hop, P.pad, P.n_frames = cfg.hop_length, (cfg.frame_length // 2 if center else 0), T
+    P.twiddle = _dev_tensor("twiddle", dev, tables.fft_twiddles).data_ptr()
+    P.sr, P.fmin = cfg.sr, cfg.fmin
+    P.min_period, P.max_period = cfg.min_period, cfg.max_period
+    P.n_pitch_bins, P.bins_per_semitone = cfg.n_pitch_bins, cfg.bins_per_semitone
+    P.n_thresholds, P.max_cand = cfg.n_thresholds, max_cand
+    P.thresholds = _dev_tensor(key + ("th",), dev, lambda: cfg.thresholds).data_ptr()
+    P.beta_probs = _dev_tensor(key + ("bp",), dev, lambda: cfg.beta_probs).data_ptr()
+    P.beta_cumsum = _dev_tensor(key + ("bc",), dev, lambda: cfg.beta_cumsum).data_ptr()
+    P.boltz_fact = _dev_tensor(key + ("bf",), dev, lambda: cfg.boltz_fact).data_ptr()
+    P.boltz_exp = _dev_tensor(key + ("be",), dev, lambda: cfg.boltz_exp).data_ptr()
+    P.no_trough_prob = cfg.no_trough_prob
+    cand_bin = torch.empty((n_fr, max_cand), dtype=torch.int16, device=dev)
+    cand_prob = torch.empty((n_fr, max_cand), dtype=torch.float64, device=dev)
+    cand_count = torch.empty((n_fr,), dtype=torch.int32, device=dev)
+    voiced_prob = torch.empty((n_fr,), dtype=torch.float64, device=dev)
+    overflow = torch.zeros((1,), dtype=torch.int32, device=dev)
+    P.cand_bin, P.cand_prob, P.cand_count = cand_bin.data_ptr(), cand_prob.data_ptr(), cand_count.data_ptr()
+    P.voiced_prob, P.overflow = voiced_prob.data_ptr(), overflow.data_ptr()
+    nat.call("aegis_yin_candidates", P, _stream())
+    return dict(cand_bin=cand_bin, cand_prob=cand_prob, cand_count=cand_count,
+                voiced_prob=voiced_prob.view(n_clips, T), overflow=overflow, n_frames=T, max_cand=max_cand)
+
+
+def viterbi_decode(obs: dict, cfg: tables.PyinConfig, n_clips: int, *, fill_na: Optional[float] = float("nan")) -> dict:
+    """Decode the pitch/voicing HMM for each clip from sparse observations (see ``yin_candidates``)."""
+    T = obs["n_frames"]
+    dev = obs["cand_bin"].device
+    nb = cfg.n_pitch_bins
+    key = ("hmm", cfg.sr, cfg.hop_length, cfg.fmin, cfg.fmax)
+    P = nat.ViterbiParams()
+    P.n_clips, P.n_frames, P.n_pitch_bins, P.half_width = n_clips, T, nb, cfg.half_width
+    P.n_variants, P.n_interior_variants, P.max_cand = cfg.lt_variants.shape[0], cfg.n_interior_variants, obs["max_cand"]
+    P.cand_bin, P.cand_prob = obs["cand_bin"].data_ptr(), obs["cand_prob"].data_ptr()
+    P.cand_count, P.voiced_prob = obs["cand_count"].data_ptr(), obs["voiced_prob"].data_ptr()
+    P.lt_variants = _dev_tensor(key + ("lt",), dev, lambda: cfg.lt_variants).data_ptr()
+    P.row_variant = _dev_tensor(key + ("rv",), dev, lambda: cfg.row_variant).data_ptr()
+    P.freqs = _dev_tensor(key + ("fr",), dev, lambda: cfg.freqs).data_ptr()
+    P.log_tiny, P.log_init_unvoiced = cfg.log_tiny, cfg.log_init_unvoiced
+    P.fill_value = float("nan") if fill_na is None else float(fill_na)
+    backptr = torch.empty((n_clips, max(T, 1), 2 * nb), dtype=torch.int16, device=dev)
+    final_value = torch.empty((n_clips, 2 * nb), dtype=torch.float64, device=dev)
+    states = torch.empty((n_clips, T), dtype=torch.int16, device=dev)
+    f0 = torch.empty((n_clips, T), dtype=torch.float64, device=dev)
+    voiced = torch.empty((n_clips, T), dtype=torch.uint8, device=dev)
+    P.backptr, P.final_value = backptr.data_ptr(), final_value.data_ptr()
+    P.states, P.f0, P.voiced_flag = states.data_ptr(), f0.data_ptr(), voiced.data_ptr()
+    nat.call("aegis_viterbi", P, _stream())
+    if fill_na is None:  # librosa: keep the best-guess pitch on unvoiced frames
+        freqs = _dev_tensor(key + ("fr",), dev, lambda: cfg.freqs)
+        f0 = freqs[(states.to(torch.int64) & 0xFFFF) % nb]
+    return dict(states=states, f0=f0, voiced_flag=voiced)
+
+
+def pyin_batch(y: torch.Tensor, *, sr: float, fmin: float, fmax: float, hop_length: int = 512,
+               frame_length: int = N_FFT, center: bool = True, fill_na: Optional[float] = float("nan"),
+               clips_per_launch: Optional[int] = None, **hmm_kwargs) -> dict:
+    """Batched ``librosa.pyin``: f0 [n_clips, T] float64 (NaN unvoiced), voiced_flag, voiced_prob."""
+    cfg = tables.pyin_config(float(sr), int(hop_length), float(fmin), float(fmax), int(frame_length), **hmm_kwargs)
+    y = _check_audio(y)
+    n_clips = y.shape[0]
+    if clips_per_launch is None:
+        clips_per_launch = n_clips
+    parts = []
+    for c0 in range(0, n_clips, clips_per_launch):
+        yc = y[c0 : c0 + clips_per_launch]
+        obs = yin_candidates(yc, cfg, center=center)
+        dec = viterbi_decode(obs, cfg, yc.shape[0], fill_na=fill_na)
+        dec["voiced_prob"] = obs["voiced_prob"]
+        parts.append(dec)
+    if len(parts) == 1:
+        return parts[0]
+    return {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
+
+
+# ----------------------------------------------------------------------------------------------
+# K5
+# ----------------------------------------------------------------------------------------------
+TREND_OUTPUTS = ("savgol", "kalman", "holt", "consensus", "consensus_conf", "sma", "ema",
+                 "boll_ma", "boll_upper", "boll_lower", "macd_line", "macd_sig", "macd_hist")
+
+
+def trend_filters(x: torch.Tensor, *, want=TREND_OUTPUTS, savgol_window: int = 11, savgol_polyorder: int = 3,
+                  kalman_q: float = 1e-5, kalman_r: float = 1e-1, holt_alpha: float = 0.3, holt_beta: float = 0.1,
+                  sma_window: int = 5, ema_span: int = 5, boll_window: int = 20, boll_num_std: float = 2.0,
+                  macd_fast: int = 12, macd_slow: int = 26, macd_signal: int = 9) -> dict:
+    """Batched float64 trend filters over f0 series [n_series, n] (NaN = unvoiced)."""
+    if not x.is_cuda:
+        raise nat.AegisNativeError("expected a CUDA tensor: the Aegis B200 path has no CPU implementation")
+    if x.dim() == 1:
+        x = x[None]
+    x = x.to(torch.float64).contiguous()
+    n_series, n = x.shape
+    dev = x.device
+    P = nat.TrendParams()
+    P.x, P.n_series, P.n = x.data_ptr(), n_series, n
+    coeffs = _dev_tensor(("savgol", savgol_window, savgol_polyorder), dev,
+                         lambda: tables.savgol_coeffs(savgol_window, savgol_polyorder))
+    P.savgol_coeffs, P.savgol_window = coeffs.data_ptr(), savgol_window
+    P.sma_window, P.ema_span, P.boll_window = sma_window, ema_span, boll_window
+    P.macd_fast, P.macd_slow, P.macd_signal = macd_fast, macd_slow, macd_signal
+    P.kalman_q, P.kalman_r, P.holt_alpha, P.holt_beta, P.boll_num_std = kalman_q, kalman_r, holt_alpha, holt_beta, boll_num_std
+    compact = torch.empty_like(x)
+    scratch = torch.empty_like(x)
+    P.compact, P.scratch = compact.data_ptr(), scratch.data_ptr()
+    out = {}
+    need = set(want)
+    if need & {"consensus", "consensus_conf"}:
+        need |= {"savgol", "kalman", "holt"}
+    if need & {"boll_upper", "boll_lower"}:
+        need |= {"boll_ma"}
+    if need & {"macd_sig", "macd_hist"}:
+        need |= {"macd_line"}
+    for name in TREND_OUTPUTS:
+        if name in need:
+            t = torch.empty_like(x)
+            setattr(P, name, t.data_ptr())
+            out[name] = t
+    nat.call("aegis_trend_filters", P, _stream())
+    return {k: v for k, v in out.items() if k in want}
+
+
+# ----------------------------------------------------------------------------------------------
+# corpus synthesis
+# ----------------------------------------------------------------------------------------------
+def synth_events(n_clips: int, n_samples: int, events: dict, device, decay: float = 0.996) -> torch.Tensor:
+    """Render Karplus-Strong / rake events (see corpus.plan_events) into [n_clips, n_samples] float32."""
+    out = torch.zeros((n_clips, n_samples), dtype=torch.float32, device=device)
+    ev = {k: torch.from_numpy(np.ascontiguousarray(v).view(np.int32) if v.dtype == np.uint32 else np.ascontiguousarray(v)).to(device)
+          for k, v in events.items()}
+    P = nat.SynthParams()
+    P.out, P.clip_stride, P.n_events = out.data_ptr(), out.stride(0), int(ev["clip"].numel())
+    P.ev_clip, P.ev_start, P.ev_len = ev["clip"].data_ptr(), ev["start"].data_ptr(), ev["length"].data_ptr()
+    P.ev_period, P.ev_amp, P.ev_seed = ev["period"].data_ptr(), ev["amp"].data_ptr(), ev["seed"].data_ptr()
+    P.decay = decay
+    if P.n_events:
+        nat.call("aegis_synth_ks", P, _stream())
+    peak = out.abs().amax(dim=1, keepdim=True).clamp_min(1e-20)
+    return out / peak * 0.9

@@ -137,3 +137,39 @@ def clip_batch(n_clips: int, duration: float, sr: int = 22050, first_seed: int =
         with mp.get_context("fork").Pool(workers) as pool:
             clips = pool.map(partial(random_clip, duration=duration, sr=sr), seeds)
     return np.stack(clips)
+
+
+def plan_events(n_clips: int, duration: float, sr: int = 22050, first_seed: int = 0) -> dict:
+    """Event list for the device-side synthesiser (``core.synth_events``): the same clip recipe as
+    ``random_clip`` (KS plucks E2..E5 of 0.2-1.5 s, 0-4 rakes of 25 ms, 0.2 s silences; seed = clip
+    index), planned on the host, rendered by one GPU thread per event."""
+    n_total = int(duration * sr)
+    clip, start, length, period, amp, seed = [], [], [], [], [], []
+    rake_len = int(0.025 * sr)
+    for c in range(n_clips):
+        rng = np.random.default_rng(first_seed + c)
+        n_rakes = int(rng.integers(0, 5))
+        rake_slots = set(rng.integers(2, 30, n_rakes).tolist())
+        pos = int(0.2 * sr)
+        k = 0
+        while pos < n_total:
+            if k in rake_slots:
+                ln = min(rake_len, n_total - pos)
+                clip.append(c); start.append(pos); length.append(ln); period.append(0)
+                amp.append(1.0); seed.append(int(rng.integers(0, 2**32 - 1)))
+                pos += rake_len + int(rng.integers(200, 2000))
+                if pos >= n_total:
+                    break
+            midi = int(rng.integers(40, 77))
+            dur = float(rng.uniform(0.2, 1.5))
+            n_note = int(sr * dur)
+            ln = min(n_note, n_total - pos)
+            clip.append(c); start.append(pos); length.append(ln)
+            period.append(int(sr / float(midi_to_hz(midi))))
+            amp.append(float(rng.uniform(0.3, 1.0))); seed.append(int(rng.integers(0, 2**32 - 1)))
+            pos += n_note
+            if rng.random() < 0.35:
+                pos += int(0.2 * sr)
+            k += 1
+    return dict(clip=np.asarray(clip, np.int32), start=np.asarray(start, np.int32), length=np.asarray(length, np.int32),
+                period=np.asarray(period, np.int32), amp=np.asarray(amp, np.float32), seed=np.asarray(seed, np.uint32))

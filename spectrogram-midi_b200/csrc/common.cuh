@@ -1,0 +1,65 @@
+// Shared host/device helpers for libaegis_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include "../../include/aegis_b200.h"
+
+namespace aegis {
+
+void set_error(const char* fmt, ...);
+
+// returns 0 on success; records the CUDA error text otherwise
+int check_launch(const char* what);
+
+inline int sm_count() {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        if (cached <= 0) cached = 148;
+    }
+    return cached;
+}
+
+#define AEGIS_REQUIRE(cond, ...)          \
+    do {                                  \
+        if (!(cond)) {                    \
+            aegis::set_error(__VA_ARGS__); \
+            return 1;                     \
+        }                                 \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ void named_barrier(int id, int n_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// order-preserving atomics for non-negative floats
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+__device__ __forceinline__ void atomic_min_nonneg(float* addr, float v) {
+    atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+
+}  // namespace aegis

@@ -1,0 +1,209 @@
+// K4: mel power -> dB, rake-noise mask, spectral-flux onset envelope, onset peak picking.
+//
+// Replaces librosa.power_to_db(S, ref=np.max) (aegis_engine.py:26), detect_rake_patterns
+// (aegis_engine_core/vision.py:3-38) and librosa.onset.onset_strength / util.peak_pick (no
+// reference call site; named by BASELINE north_star, defined in SURVEY.md Appendix A.6).
+//
+// One thread per spectrogram column (coalesced across the time axis), CTAs of 256 columns of
+// which the outer 32 on each side are halo (rake run-length gate looks at neighbours).  Every
+// 10*log10 is evaluated once per (mel, column) and serves S_dB, the column test and the flux.
+#include "common.cuh"
+
+namespace aegis {
+
+constexpr int MP_THREADS = 256;
+constexpr int MP_HALO = 32;
+constexpr int MP_OWN = MP_THREADS - 2 * MP_HALO;  // 192
+
+__global__ void __launch_bounds__(MP_THREADS)
+mel_post_kernel(const aegis_melpost_params p) {
+    __shared__ unsigned char flag[MP_THREADS];
+    const int clip = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int T = p.n_frames;
+    const int t = blockIdx.x * MP_OWN - MP_HALO + tid;
+    const bool in_clip = (t >= 0 && t < T);
+    const bool own = in_clip && tid >= MP_HALO && tid < MP_HALO + MP_OWN;
+
+    const float* __restrict__ mel = p.mel + static_cast<long long>(clip) * p.mel_clip_stride;
+    const float amin = 1e-10f;
+    const bool is_db = p.input_is_db != 0;
+    const float max_db = is_db ? 0.f : 10.0f * log10f(fmaxf(amin, __ldg(p.mel_max + clip)));
+    const float ref_db = is_db ? 0.f : (p.ref_power ? 10.0f * log10f(fmaxf(amin, __ldg(p.ref_power + clip))) : max_db);
+    const float db_floor = is_db ? -INFINITY : (max_db - ref_db) - 80.0f;  // max(log_spec) - top_db
+    const float onset_floor = max_db - 80.0f;  // power_to_db(ref=1.0): max(log_spec) - top_db
+
+    // pass A: column maximum (dB is monotone in power, so dB(max) == max(dB))
+    float col_max_db = -80.0f;
+    if (in_clip) {
+        if (is_db) {
+            float cmax = -INFINITY;
+            for (int m = 0; m < p.n_mels; ++m) cmax = fmaxf(cmax, __ldg(mel + static_cast<long long>(m) * p.mel_row_stride + t));
+            col_max_db = cmax;
+        } else {
+            float cmax = 0.f;
+            for (int m = 0; m < p.n_mels; ++m) cmax = fmaxf(cmax, __ldg(mel + static_cast<long long>(m) * p.mel_row_stride + t));
+            col_max_db = fmaxf(10.0f * log10f(fmaxf(amin, cmax)) - ref_db, db_floor);
+        }
+    }
+    // pass B: dB per cell -> optional store, broadband count, positive flux against column t-1
+    int active = 0;
+    float flux = 0.f;
+    const float thr = col_max_db - 20.0f;
+    const bool want_flux = p.onset_env != nullptr && !is_db;
+    float* __restrict__ sdb = p.s_db ? p.s_db + static_cast<long long>(clip) * p.sdb_clip_stride : nullptr;
+    for (int m = 0; m < p.n_mels; ++m) {
+        float L = 0.f;
+        if (in_clip) {
+            const float raw = __ldg(mel + static_cast<long long>(m) * p.mel_row_stride + t);
+            L = is_db ? raw : 10.0f * log10f(fmaxf(amin, raw));
+        }
+        const float db = fmaxf(L - ref_db, db_floor);
+        if (own && sdb) sdb[static_cast<long long>(m) * p.sdb_row_stride + t] = db;
+        active += (db > thr) ? 1 : 0;
+        if (want_flux) {
+            const float D = fmaxf(L, onset_floor);
+            float Dprev = __shfl_up_sync(0xffffffffu, D, 1);
+            if (lane == 0 && in_clip && t >= 1)
+                Dprev = fmaxf(10.0f * log10f(fmaxf(amin, __ldg(mel + static_cast<long long>(m) * p.mel_row_stride + t - 1))), onset_floor);
+            flux += fmaxf(0.0f, D - Dprev);
+        }
+    }
+    bool is_rake = false;
+    if (in_clip && !(col_max_db < -60.0f)) {
+        is_rake = (static_cast<double>(active) / static_cast<double>(p.n_mels)) > p.rake_ratio;
+    }
+    flag[tid] = is_rake ? 1 : 0;
+    __syncthreads();
+
+    if (own && p.rake_mask) {
+        bool keep = false;
+        if (is_rake) {
+            const int maxf = p.rake_max_frames;
+            int left = 0;   // rake columns directly before t
+            while (left <= maxf && tid - left - 1 >= 0 && t - left - 1 >= 0 && flag[tid - left - 1]) ++left;
+            int right = 0;  // rake columns directly after t
+            while (right <= maxf && tid + right + 1 < MP_THREADS && t + right + 1 < T && flag[tid + right + 1]) ++right;
+            const int len = left + right + 1;
+            const bool closed = (t + right + 1) < T;  // a run still open at the last column is never emitted
+            keep = closed && left <= maxf && right <= maxf && len >= p.rake_min_frames && len <= maxf;
+        }
+        p.rake_mask[static_cast<long long>(clip) * T + t] = keep ? 1 : 0;
+    }
+
+    if (want_flux) {
+        float* __restrict__ env = p.onset_env + static_cast<long long>(clip) * T;
+        float vmin = __int_as_float(0x7f800000), vmax = 0.f;
+        if (own) {
+            if (t < p.onset_pad) {  // leading zeros of the padded envelope
+                env[t] = 0.f;
+                vmin = 0.f;
+            }
+            const int e = t + p.onset_pad - 1;  // flux(t) = raw[t-1] lands at raw index + pad
+            if (t >= 1 && e < T) {
+                const float v = flux * (1.0f / static_cast<float>(p.n_mels));
+                env[e] = v;
+                vmin = fminf(vmin, v);
+                vmax = fmaxf(vmax, v);
+            }
+        }
+        if (p.env_minmax) {
+            vmin = warp_min(vmin);
+            vmax = warp_max(vmax);
+            if (lane == 0) {
+                if (vmin < __int_as_float(0x7f800000)) atomic_min_nonneg(p.env_minmax + 2 * clip, vmin);
+                atomic_max_nonneg(p.env_minmax + 2 * clip + 1, vmax);
+            }
+        }
+    }
+}
+
+// candidate test of librosa.util.peak_pick on the normalised envelope, one thread per frame
+__global__ void __launch_bounds__(256)
+peak_candidates_kernel(const aegis_peaks_params p) {
+    const int clip = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = p.n_frames;
+    if (n >= N) return;
+    const float* __restrict__ env = p.onset_env + static_cast<long long>(clip) * N;
+    const float mn = p.env_minmax[2 * clip], mx = p.env_minmax[2 * clip + 1];
+    bool is_cand = false;
+    if (mx > 0.f) {  // an all-zero envelope has no onsets
+        const float shift = p.normalize ? mn : 0.f;
+        const float scale = p.normalize ? ((mx - mn) + 1.17549435e-38f) : 1.f;
+        auto x = [&](int i) -> float {
+            const float v = __ldg(env + i) - shift;
+            return p.normalize ? __fdiv_rn(v, scale) : v;
+        };
+        const float xn = x(n);
+        float wmax = xn;
+        const int lo = max(0, n - p.pre_max), hi = min(n + p.post_max, N);
+        for (int i = lo; i < hi; ++i) wmax = fmaxf(wmax, x(i));
+        if (xn == wmax) {
+            const int alo = max(0, n - p.pre_avg), ahi = min(n + p.post_avg, N);
+            double acc = 0.0;
+            for (int i = alo; i < ahi; ++i) acc += static_cast<double>(x(i));
+            const double avg = acc / static_cast<double>(ahi - alo);
+            is_cand = static_cast<double>(xn) >= avg + p.delta;
+        }
+    }
+    p.cand[static_cast<long long>(clip) * N + n] = is_cand ? 1 : 0;
+}
+
+// greedy left-to-right selection with the `wait` dead time; one warp per clip, lane 0 walks
+__global__ void __launch_bounds__(128)
+peak_select_kernel(const aegis_peaks_params p) {
+    const int clip = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (clip >= p.n_clips) return;
+    const int lane = threadIdx.x & 31;
+    const int N = p.n_frames;
+    const unsigned char* __restrict__ cand = p.cand + static_cast<long long>(clip) * N;
+    unsigned char* __restrict__ peaks = p.peaks + static_cast<long long>(clip) * N;
+    for (int i = lane; i < N; i += 32) peaks[i] = 0;
+    __syncwarp();
+    if (lane == 0) {
+        int count = 0;
+        int n = 0;
+        while (n < N) {
+            if (cand[n]) {
+                peaks[n] = 1;
+                ++count;
+                n += p.wait + 1;
+            } else {
+                ++n;
+            }
+        }
+        p.n_peaks[clip] = count;
+    }
+}
+
+}  // namespace aegis
+
+extern "C" int aegis_mel_post(const aegis_melpost_params* p, void* stream) {
+    using namespace aegis;
+    AEGIS_REQUIRE(p != nullptr && p->mel && (p->mel_max || p->input_is_db), "aegis_mel_post: mel / mel_max must be set");
+    AEGIS_REQUIRE(p->n_mels > 0 && p->n_clips >= 0 && p->n_frames >= 0, "aegis_mel_post: bad sizes");
+    AEGIS_REQUIRE(p->rake_max_frames >= 0 && p->rake_max_frames <= MP_HALO - 2,
+                  "aegis_mel_post: rake_max_frames=%d exceeds the %d-column halo", p->rake_max_frames, MP_HALO - 2);
+    AEGIS_REQUIRE(p->onset_env == nullptr || p->onset_pad >= 1, "aegis_mel_post: onset_pad must be >= 1");
+    if (p->n_clips == 0 || p->n_frames == 0) return 0;
+    dim3 grid((p->n_frames + MP_OWN - 1) / MP_OWN, p->n_clips);
+    mel_post_kernel<<<grid, MP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*p);
+    return check_launch("aegis_mel_post");
+}
+
+extern "C" int aegis_onset_peaks(const aegis_peaks_params* p, void* stream) {
+    using namespace aegis;
+    AEGIS_REQUIRE(p != nullptr && p->onset_env && p->env_minmax && p->cand && p->peaks && p->n_peaks,
+                  "aegis_onset_peaks: null pointer");
+    AEGIS_REQUIRE(p->pre_max >= 0 && p->post_max >= 1 && p->pre_avg >= 0 && p->post_avg >= 1 && p->wait >= 0,
+                  "aegis_onset_peaks: bad window parameters");
+    if (p->n_clips == 0 || p->n_frames == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((p->n_frames + 255) / 256, p->n_clips);
+    peak_candidates_kernel<<<grid, 256, 0, st>>>(*p);
+    if (int rc = check_launch("aegis_onset_peaks(candidates)")) return rc;
+    peak_select_kernel<<<(p->n_clips + 3) / 4, 128, 0, st>>>(*p);
+    return check_launch("aegis_onset_peaks(select)");
+}

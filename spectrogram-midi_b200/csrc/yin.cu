@@ -1,0 +1,340 @@
+// K2: batched probabilistic-YIN front half (librosa.pyin stages 1-9).
+//
+// Replaces the per-frame work of librosa.pyin reached from aegis_engine.py:63,67,190,216,
+// aegis_engine_core/worker.py:9-15 and aegis_engine_financial.py:63-69:
+//   difference function via FFT autocorrelation -> cumulative-mean normalisation -> troughs ->
+//   beta(2,18)-weighted thresholds with a Boltzmann prior over trough rank -> parabolic period
+//   refinement -> 10-cent pitch bins.  Output is the sparse column of the HMM observation matrix.
+//
+// A CTA of 128 threads handles two consecutive frames of one clip (a "pair"), built on the same
+// 2048-point FFT passes as the STFT kernel:
+//   forward FFT of (frame + i*reversed-first-half) gives both spectra librosa multiplies;
+//   the two frames' product spectra are packed as P1 + i*P2 and inverted with ONE transform
+//   (acf of frame 1 in the real part, of frame 2 in the imaginary part).
+// Energy / cumulative sums are prefix scans in double; the trough/threshold/prior stage runs one
+// warp per frame with ballot compaction and shuffle reductions.
+#include <cfloat>
+#include "common.cuh"
+#include "fft2048.cuh"
+
+namespace aegis {
+
+constexpr int YIN_THREADS = 128;
+constexpr int YIN_MAX_HOP = 512;
+constexpr int YIN_MAX_LAGS = 1024;     // lags 0 .. max_period, max_period <= 1023
+constexpr int YIN_MAX_TROUGHS = 512;
+
+struct YinSmem {
+    float samples[FFT_N + YIN_MAX_HOP];
+    cf bufA[BUFA_SIZE];   // bufA+bufB are reused as YinScratchE once the transforms are done
+    cf bufB[BUFB_SIZE];
+    cf Z[FFT_N];          // reused as YinScratchC in the candidate phase
+    cf P1[FFT_N / 2 + 1];
+};
+struct YinScratchE {       // lives in bufA..bufB (33 920 B)
+    double yin[2][YIN_MAX_LAGS];
+    float d[2][YIN_MAX_LAGS];
+    double tot[2][64];
+    double e0[2][2];
+};
+struct YinScratchC {       // lives in Z (16 384 B)
+    double tp[2][YIN_MAX_TROUGHS];
+    unsigned short tk[2][YIN_MAX_TROUGHS];
+    unsigned char tq[2][YIN_MAX_TROUGHS];
+};
+static_assert(sizeof(YinScratchE) <= sizeof(cf) * (BUFA_SIZE + BUFB_SIZE), "scratch E too large");
+static_assert(sizeof(YinScratchC) <= sizeof(cf) * FFT_N, "scratch C too large");
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// forward transform of x[n] = in[n] (natural order, complex) through the three passes; result in out
+__device__ __forceinline__ void fft_from_natural(int lt, const cf* in, const FftTwiddles& tw, cf* bufA, cf* bufB, cf* out) {
+    cf v[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) v[a] = in[lt + 128 * a];
+    fft2048_pass1(lt, v, tw, bufA);
+    __syncthreads();
+    fft2048_pass2(lt, tw, bufA, bufB);
+    __syncthreads();
+    fft2048_pass3(lt, bufB, out);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(YIN_THREADS, 3)
+yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n_pairs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    YinSmem& s = *reinterpret_cast<YinSmem*>(smem_raw);
+    YinScratchE& se = *reinterpret_cast<YinScratchE*>(s.bufA);
+    YinScratchC& sc = *reinterpret_cast<YinScratchC*>(s.Z);
+    const int lt = threadIdx.x, lane = lt & 31, warp = lt >> 5;
+    const int T = p.n_frames, hop = p.hop;
+    const long long N = p.n_samples;
+    const int maxp = p.max_period, minp = p.min_period;
+    const int L = maxp - minp + 1;  // CMND length
+    FftTwiddles tw;
+    fft2048_load_twiddles(lt, reinterpret_cast<const cf*>(p.twiddle), tw);
+
+    for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        const int clip = static_cast<int>(pair / pairs_per_clip);
+        const int t0 = static_cast<int>(pair - static_cast<long long>(clip) * pairs_per_clip) * 2;
+        const float* __restrict__ yc = p.y + static_cast<long long>(clip) * p.clip_stride;
+        const long long g0 = static_cast<long long>(t0) * hop - p.pad;
+        __syncthreads();
+        for (int i = lt; i < FFT_N + hop; i += YIN_THREADS) {
+            const long long gi = g0 + i;
+            s.samples[i] = (gi >= 0 && gi < N) ? __ldg(yc + gi) : 0.f;
+        }
+        __syncthreads();
+
+        // ---- spectra: Z = FFT(frame + i*rev), rev[n] = frame[1024-n] (n < 1024), 0 otherwise
+#pragma unroll 1
+        for (int fr = 0; fr < 2; ++fr) {
+            const float* f = s.samples + fr * hop;
+            {
+                cf v[16];
+#pragma unroll
+                for (int a = 0; a < 16; ++a) {
+                    const int n = lt + 128 * a;
+                    v[a] = cf{f[n], (a < 8) ? f[FFT_N / 2 - n] : 0.f};
+                }
+                fft2048_pass1(lt, v, tw, s.bufA);
+            }
+            __syncthreads();
+            fft2048_pass2(lt, tw, s.bufA, s.bufB);
+            __syncthreads();
+            fft2048_pass3(lt, s.bufB, s.Z);
+            __syncthreads();
+            // P = (2A)(2B) with 2A = Z[k] + conj Z[N-k], 2B = (Z[k] - conj Z[N-k]) / i
+#pragma unroll
+            for (int m = 0; m < 9; ++m) {
+                const int k = lt + 128 * m;
+                if (k <= FFT_N / 2) {
+                    const int kn = (FFT_N - k) & (FFT_N - 1);
+                    const cf zk = s.Z[k], zn = s.Z[kn];
+                    const cf A2 = cf{zk.x + zn.x, zk.y - zn.y};
+                    const cf B2 = cf{zk.y + zn.y, zn.x - zk.x};
+                    const cf P = cmul(A2, B2);
+                    if (fr == 0) {
+                        s.P1[k] = P;
+                    } else {  // conj(Q), Q = P1 + i*P2 extended Hermitian-wise; in place over Z
+                        const cf p1 = s.P1[k];
+                        s.Z[k] = cf{p1.x - P.y, -(p1.y + P.x)};
+                        if (kn != k) s.Z[kn] = cf{p1.x + P.y, p1.y - P.x};
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- one transform inverts both: q[n] = conj(FFT(conj Q)[n]) / N = acf1[n] + i*acf2[n]
+        fft_from_natural(lt, s.Z, tw, s.bufA, s.bufB, s.Z);
+
+        // ---- phase E: energies, difference function, cumulative mean, CMND (64 threads / frame)
+        {
+            const int fr = lt >> 6, u = lt & 63;
+            const float* f = s.samples + fr * hop;
+            double acc = 0.0;
+            for (int j = 1 + u; j <= FFT_N / 2; j += 64) acc += static_cast<double>(f[j] * f[j]);
+            acc = warp_sum_d(acc);
+            if (lane == 0) se.e0[fr][warp & 1] = acc;
+            const int chunk = (maxp + 63) / 64;
+            const int lo = 1 + u * chunk, hi = min(lo + chunk, maxp + 1);
+            double run = 0.0;
+            for (int tau = lo; tau < hi; ++tau)
+                run += static_cast<double>(f[FFT_N / 2 + tau] * f[FFT_N / 2 + tau]) - static_cast<double>(f[tau] * f[tau]);
+            se.tot[fr][u] = run;
+            __syncthreads();
+            const double e0 = se.e0[fr][0] + se.e0[fr][1];
+            double base = e0;
+            for (int v = 0; v < u; ++v) base += se.tot[fr][v];
+            float e0f = static_cast<float>(e0);
+            if (fabsf(e0f) < 1e-6f) e0f = 0.f;
+            run = 0.0;
+            double dsum = 0.0;
+            for (int tau = lo; tau < hi; ++tau) {
+                run += static_cast<double>(f[FFT_N / 2 + tau] * f[FFT_N / 2 + tau]) - static_cast<double>(f[tau] * f[tau]);
+                float e = static_cast<float>(base + run);
+                if (fabsf(e) < 1e-6f) e = 0.f;
+                const cf F = s.Z[FFT_N / 2 + tau];
+                float acf = (fr == 0 ? F.x : -F.y) * (1.0f / (4.0f * FFT_N));
+                if (fabsf(acf) < 1e-6f) acf = 0.f;
+                const float dv = (e0f + e) - 2.0f * acf;
+                se.d[fr][tau] = dv;
+                dsum += static_cast<double>(dv);
+            }
+            __syncthreads();  // tot[] fully consumed
+            se.tot[fr][u] = dsum;
+            __syncthreads();
+            base = 0.0;
+            for (int v = 0; v < u; ++v) base += se.tot[fr][v];
+            run = 0.0;
+            for (int tau = lo; tau < hi; ++tau) {
+                run += static_cast<double>(se.d[fr][tau]);
+                if (tau >= minp) {
+                    const double cm = static_cast<double>(static_cast<float>(base + run)) / static_cast<double>(tau);
+                    se.yin[fr][tau - minp] = static_cast<double>(se.d[fr][tau]) / (cm + DBL_MIN);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase C: one warp per frame (warps 0 and 2)
+        if ((warp & 1) == 0) {
+            const int fr = warp >> 1;
+            const int t = t0 + fr;
+            if (t < T) {
+                const double* yv = se.yin[fr];
+                unsigned short* tk = sc.tk[fr];
+                unsigned char* tq = sc.tq[fr];
+                double* tp = sc.tp[fr];
+                const long long fidx = static_cast<long long>(clip) * T + t;
+                // 1. troughs, compacted in lag order
+                int nt = 0;
+                for (int base = 0; base < L; base += 32) {
+                    const int k = base + lane;
+                    bool tr = false;
+                    if (k < L && L >= 2) {
+                        const double x = yv[k];
+                        if (k == 0) tr = x < yv[1];
+                        else if (k == L - 1) tr = x < yv[k - 1];
+                        else tr = (x < yv[k - 1]) && (x <= yv[k + 1]);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, tr);
+                    if (tr) {
+                        const int pos = nt + __popc(m & ((1u << lane) - 1u));
+                        if (pos < YIN_MAX_TROUGHS) tk[pos] = static_cast<unsigned short>(k);
+                    }
+                    nt += __popc(m);
+                }
+                nt = min(nt, YIN_MAX_TROUGHS);
+                __syncwarp();
+                int count = 0;
+                double vsum = 0.0;
+                if (nt > 0) {
+                    // 2. first threshold index each trough is below; global minimum (first on ties)
+                    const int nth = p.n_thresholds;
+                    double best_h = DBL_MAX;
+                    int best_i = 0x7fffffff;
+                    for (int i = lane; i < nt; i += 32) {
+                        const double h = yv[tk[i]];
+                        int q = (h >= 1.0) ? nth : ((h <= 0.0) ? 0 : static_cast<int>(h * nth));  // guess, then fix
+                        q = max(0, min(q, nth));
+                        while (q > 0 && h < __ldg(p.thresholds + q - 1)) --q;
+                        while (q < nth && !(h < __ldg(p.thresholds + q))) ++q;
+                        tq[i] = static_cast<unsigned char>(q);
+                        tp[i] = 0.0;
+                        if (h < best_h) { best_h = h; best_i = i; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double oh = __shfl_xor_sync(0xffffffffu, best_h, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+                        if (oh < best_h || (oh == best_h && oi < best_i)) { best_h = oh; best_i = oi; }
+                    }
+                    __syncwarp();
+                    // 3. troughs below each threshold (this lane owns thresholds lane, lane+32, ...)
+                    int nj[4] = {0, 0, 0, 0}, pj[4] = {0, 0, 0, 0};
+                    for (int i = 0; i < nt; ++i) {
+                        const int q = tq[i];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) nj[r] += (q <= lane + 32 * r) ? 1 : 0;
+                    }
+                    double fj[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int j = lane + 32 * r;
+                        fj[r] = (j < nth && nj[r] > 0) ? __ldg(p.boltz_fact + nj[r]) : 0.0;
+                    }
+                    // 4. probability of each trough: sum_j prior(rank among troughs below th_j) * beta_j
+                    for (int i = 0; i < nt; ++i) {
+                        const int q = tq[i];
+                        if (q >= nth) continue;  // warp-uniform
+                        double c = 0.0;
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int j = lane + 32 * r;
+                            if (j < nth && q <= j) {
+                                c += (fj[r] * __ldg(p.boltz_exp + pj[r])) * __ldg(p.beta_probs + j);
+                                ++pj[r];
+                            }
+                        }
+                        c = warp_sum_d(c);
+                        if (lane == 0) tp[i] = c;
+                    }
+                    __syncwarp();
+                    // 5. emit in ascending-bin order (= descending lag); equal bins: the larger lag wins
+                    if (lane == 0) {
+                        tp[best_i] += p.no_trough_prob * __ldg(p.beta_cumsum + tq[best_i]);
+                        unsigned short* ob = p.cand_bin + fidx * p.max_cand;
+                        double* op = p.cand_prob + fidx * p.max_cand;
+                        const double scale = 12.0 * p.bins_per_semitone;
+                        int last_bin = -1;
+                        bool over = false;
+                        for (int i = nt - 1; i >= 0; --i) {
+                            const double pr = tp[i];
+                            if (pr == 0.0) continue;
+                            const int k = tk[i];
+                            double shift = 0.0;
+                            if (k > 0 && k < L - 1) {
+                                const double a = yv[k + 1] + yv[k - 1] - 2.0 * yv[k];
+                                const double b = (yv[k + 1] - yv[k - 1]) / 2.0;
+                                if (!(fabs(b) >= fabs(a))) shift = -b / a;
+                            }
+                            const double period = static_cast<double>(minp + k) + shift;
+                            const double f0 = p.sr / period;
+                            double bf = rint(scale * log2(f0 / p.fmin));
+                            bf = fmin(fmax(bf, 0.0), static_cast<double>(p.n_pitch_bins));
+                            const int bin = static_cast<int>(bf);
+                            if (bin >= p.n_pitch_bins) continue;  // lands in the unvoiced rows: overwritten
+                            if (bin == last_bin) continue;        // overwritten by the later (larger-lag) write
+                            last_bin = bin;
+                            if (count < p.max_cand) {
+                                ob[count] = static_cast<unsigned short>(bin);
+                                op[count] = pr;
+                                vsum += pr;
+                                ++count;
+                            } else {
+                                over = true;
+                            }
+                        }
+                        if (over) atomicExch(p.overflow, 1);
+                    }
+                }
+                if (lane == 0) {
+                    p.cand_count[fidx] = count;
+                    p.voiced_prob[fidx] = fmin(fmax(vsum, 0.0), 1.0);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace aegis
+
+extern "C" int aegis_yin_candidates(const aegis_yin_params* p, void* stream) {
+    using namespace aegis;
+    AEGIS_REQUIRE(p != nullptr && p->y && p->twiddle, "aegis_yin_candidates: y / twiddle must be set");
+    AEGIS_REQUIRE(p->hop >= 1 && p->hop <= YIN_MAX_HOP, "aegis_yin_candidates: hop=%d unsupported (1..512)", p->hop);
+    AEGIS_REQUIRE(p->min_period >= 1 && p->max_period > p->min_period && p->max_period <= FFT_N / 2 - 1,
+                  "aegis_yin_candidates: periods [%d, %d] out of range", p->min_period, p->max_period);
+    AEGIS_REQUIRE(p->n_thresholds >= 1 && p->n_thresholds <= 128, "aegis_yin_candidates: n_thresholds must be 1..128");
+    AEGIS_REQUIRE(p->thresholds && p->beta_probs && p->beta_cumsum && p->boltz_fact && p->boltz_exp,
+                  "aegis_yin_candidates: prior tables missing");
+    AEGIS_REQUIRE(p->cand_bin && p->cand_prob && p->cand_count && p->voiced_prob && p->overflow && p->max_cand >= 1,
+                  "aegis_yin_candidates: outputs missing");
+    if (p->n_clips == 0 || p->n_frames == 0) return 0;
+    const int pairs_per_clip = (p->n_frames + 1) / 2;
+    const long long n_pairs = static_cast<long long>(pairs_per_clip) * p->n_clips;
+    cudaError_t e = cudaFuncSetAttribute(yin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(YinSmem)));
+    if (e != cudaSuccess) {
+        set_error("aegis_yin_candidates: cannot reserve %zu B shared memory: %s", sizeof(YinSmem), cudaGetErrorString(e));
+        return 2;
+    }
+    const long long max_grid = static_cast<long long>(sm_count()) * 3;
+    const int grid = static_cast<int>(n_pairs < max_grid ? n_pairs : max_grid);
+    yin_kernel<<<grid, YIN_THREADS, sizeof(YinSmem), static_cast<cudaStream_t>(stream)>>>(*p, pairs_per_clip, n_pairs);
+    return check_launch("aegis_yin_candidates");
+}

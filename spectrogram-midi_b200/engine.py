@@ -1,0 +1,117 @@
+"""Engine facades with the reference's signatures, backed by the B200 kernels.
+
+``AegisEngine`` mirrors ``aegis_engine.py:16-75,183-216`` (perception phase) and
+``AegisFinancialEngine`` mirrors ``aegis_engine_financial.py:36-71``: same constructor arguments,
+method names, keyword names/defaults, returned dict keys and dtypes.  The logic-filter phase
+(``extract_events``: note state machine, MIDI writing) is the reference's unchanged consumer; it is
+delegated to the reference's own ``aegis_engine_core.midi_logic`` when that package is importable.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import batch, core, tables
+from . import librosa_compat as librosa
+from .vision import detect_rake_patterns
+from .worker import _pyin_worker  # noqa: F401  (kept importable from here like aegis_engine.py:14)
+
+
+def _as_audio(source, sr, start_time=0, end_time=None):
+    """A numpy array is taken as audio already at ``sr``; a str/path goes through ``librosa_compat.load``."""
+    if isinstance(source, (str, bytes)) or hasattr(source, "__fspath__"):
+        duration = (end_time - start_time) if end_time else None
+        y, _ = librosa.load(source, sr=sr, offset=start_time, duration=duration)
+        return y
+    y = np.asarray(source, dtype=np.float32)
+    s = int(round(start_time * sr))
+    e = None if not end_time else int(round(end_time * sr))
+    return np.ascontiguousarray(y[s:e])
+
+
+class AegisEngine:
+    def __init__(self, sample_rate=44100, hop_length=512, n_fft=2048):
+        self.sr = sample_rate
+        self.hop_length = hop_length
+        self.n_fft = n_fft
+
+    # -- aegis_engine.py:22-27
+    def load_audio(self, file_path, start_time=0, end_time=None):
+        y = _as_audio(file_path, self.sr, start_time, end_time)
+        if len(y) == 0:
+            return y, np.zeros((128, 0), dtype=np.float32)
+        S = librosa.feature.melspectrogram(y=y, sr=self.sr, n_fft=self.n_fft, hop_length=self.hop_length)
+        S_dB = librosa.power_to_db(S, ref=np.max)
+        return y, S_dB
+
+    # -- aegis_engine.py:38-39
+    def detect_rake_patterns(self, S_dB):
+        return detect_rake_patterns(S_dB, self.hop_length, self.sr, 0.6)
+
+    def _pyin(self, y):
+        return librosa.pyin(y, fmin=librosa.note_to_hz("E2"), fmax=librosa.note_to_hz("C6"), sr=self.sr,
+                            hop_length=self.hop_length)
+
+    # -- aegis_engine.py:41-75
+    def audio_to_midi(self, input_wav, output_mid, **kwargs):
+        """Perception phase.  ``output_mid`` is ignored exactly as in the reference (:41-75 never use it)."""
+        start_time, end_time = kwargs.get("start_time", 0), kwargs.get("end_time", None)
+        rake_sensitivity = kwargs.get("rake_sensitivity", 0.6)
+        y = _as_audio(input_wav, self.sr, start_time, end_time)
+        if len(y) == 0:
+            return None
+        # one upload, every kernel on the device, one download (turbo_mode needs no special casing:
+        # the serial full-clip result is what Turbo Mode approximates)
+        yd = torch.from_numpy(y).to(librosa._device())[None]
+        res = batch.analyze_batch(yd, sr=self.sr, hop_length=self.hop_length, rake_sensitivity=rake_sensitivity)
+        return batch.to_host(res, 0, y=y)
+
+    # -- aegis_engine.py:183-216
+    def _parallel_pitch_tracking(self, y):
+        """Turbo Mode.  The reference splits the clip into ``cpu_count()`` independent chunks (lossy at the
+        seams); here the frame-parallel stages already use every SM, so the exact full-clip result is returned."""
+        return self._pyin(np.asarray(y, dtype=np.float32))
+
+    # -- aegis_engine.py:77-181: unchanged consumer
+    def extract_events(self, raw_data, output_mid, **kwargs):
+        try:
+            from aegis_engine import AegisEngine as _Ref  # the reference checkout, if it is on sys.path
+        except Exception as e:  # pragma: no cover - depends on the user's environment
+            raise RuntimeError(
+                "extract_events is the reference's unchanged logic-filter phase (aegis_engine.py:77-181); "
+                "put the reference checkout on sys.path to use it with these perception outputs") from e
+        ref = _Ref(self.sr, self.hop_length, self.n_fft)
+        return ref.extract_events(raw_data, output_mid, **kwargs)
+
+
+class AegisFinancialEngine:
+    """Perception methods of ``aegis_engine_financial.py:36-71`` (sr defaults to 22 050 there)."""
+
+    def __init__(self, sample_rate=22050, hop_length=512, n_fft=2048):
+        self.sr = sample_rate
+        self.hop_length = hop_length
+        self.n_fft = n_fft
+
+    def load_audio(self, file_path, start_time=0, end_time=None):
+        return AegisEngine(self.sr, self.hop_length, self.n_fft).load_audio(file_path, start_time, end_time)
+
+    def detect_rake_patterns(self, S_dB, sensitivity=0.6):
+        return detect_rake_patterns(S_dB, self.hop_length, self.sr, sensitivity)
+
+    def pitch_tracking(self, y):
+        return librosa.pyin(y, fmin=librosa.note_to_hz("E2"), fmax=librosa.note_to_hz("C6"), sr=self.sr,
+                            hop_length=self.hop_length)
+
+    def perception(self, input_wav, **kwargs):
+        """Arrays ``audio_to_midi_financial`` hands to its note logic (:105-160): rake mask, pYIN with NaN
+        f0, RMS, S_dB, plus the consensus trend of ``analyze_pitch_financial`` (financial_analysis.py:386-391)."""
+        y = _as_audio(input_wav, self.sr, kwargs.get("start_time", 0), kwargs.get("end_time", None))
+        if len(y) == 0:
+            return None
+        yd = torch.from_numpy(y).to(librosa._device())[None]
+        res = batch.analyze_batch(yd, sr=self.sr, hop_length=self.hop_length,
+                                  rake_sensitivity=kwargs.get("rake_sensitivity", 0.6), with_sdb=True,
+                                  with_trend=True, nan_to_num=False)
+        host = batch.to_host(res, 0, y=y)
+        host["sr"], host["hop_length"] = self.sr, self.hop_length  # financial_app_realtime.py:224-233
+        return host

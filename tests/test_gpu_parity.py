@@ -1,0 +1,405 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI via
+the Python host layer, against the CPU oracle and the committed golden vectors.
+
+Tolerances (BASELINE.json north_star): spectrogram rtol 1e-4 (+ atol 1e-5 * frame max),
+RMS rtol 1e-5, f0 within 1 cent on voiced frames; integer outputs (voiced flags, Viterbi states on
+identical observations, rake mask, onset frames, MIDI note events) bit-exact.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import librosa_ref as L  # noqa: E402
+from oracle import reference_files as R  # noqa: E402
+
+import spectrogram_midi_b200 as P  # noqa: E402
+from spectrogram_midi_b200 import corpus, tables  # noqa: E402
+
+E2, C6, E6 = L.note_to_hz("E2"), L.note_to_hz("C6"), L.note_to_hz("E6")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from spectrogram_midi_b200 import _native
+
+    _native.load()  # the native library must be the thing that runs: fail loudly otherwise
+    return torch.device("cuda", 0)
+
+
+def _dev(y, dev):
+    y = np.atleast_2d(np.asarray(y, dtype=np.float32))
+    return torch.from_numpy(np.ascontiguousarray(y)).to(dev)
+
+
+SIGNALS = {
+    "track22050": lambda: (corpus.test_track(22050, 0), 22050),
+    "track44100": lambda: (corpus.test_track(44100, 0), 44100),
+    "bench22050": lambda: (corpus.benchmark_signal(22050, 0), 22050),
+    "clip3": lambda: (corpus.random_clip(3, 6.0, 22050), 22050),
+}
+
+
+def _assert_mag_close(got, ref):
+    tol = 1e-4 * np.abs(ref) + 1e-5 * ref.max(axis=0, keepdims=True) + 1e-30
+    bad = np.abs(got - ref) > tol
+    assert not bad.any(), f"{bad.sum()} of {bad.size} bins outside rtol 1e-4 (+1e-5*frame max); worst {np.abs(got - ref).max()}"
+
+
+# ---------------------------------------------------------------------------------- K1 STFT / mel / RMS
+@pytest.mark.parametrize("name", list(SIGNALS))
+def test_stft_magnitude_matches_oracle(dev, name):
+    y, sr = SIGNALS[name]()
+    out = P.core.stft_features(_dev(y, dev), sr=sr, want_mag=True, want_mel=True, want_rms=True)
+    ref = L.stft_magnitude(y)
+    assert out["mag"].shape == (1,) + ref.shape
+    _assert_mag_close(out["mag"][0].cpu().numpy(), ref)
+    np.testing.assert_allclose(out["rms"][0].cpu().numpy(), L.rms(y)[0], rtol=1e-5, atol=1e-9)
+    mel_ref = L.melspectrogram(y, sr)
+    mel = out["mel"][0].cpu().numpy()
+    np.testing.assert_allclose(mel, mel_ref, rtol=2e-4, atol=2e-6 * mel_ref.max())
+    assert abs(float(out["mel_max"][0]) - mel.max()) == 0.0
+
+
+@pytest.mark.parametrize("n", [0, 1, 511, 512, 2047, 2048, 4097, 12345, 22050])
+def test_stft_edge_lengths(dev, n):
+    rng = np.random.default_rng(n)
+    y = rng.normal(0, 0.3, n).astype(np.float32)
+    if n == 0:
+        out = P.core.stft_features(torch.zeros((1, 0), device=dev), want_mag=True, want_rms=True)
+        assert out["mag"].shape == (1, 1025, 1) and float(out["mag"].abs().max()) == 0.0
+        return
+    out = P.core.stft_features(_dev(y, dev), want_mag=True, want_rms=True)
+    ref = L.stft_magnitude(y)
+    assert out["mag"].shape[1:] == ref.shape
+    _assert_mag_close(out["mag"][0].cpu().numpy(), ref)
+    np.testing.assert_allclose(out["rms"][0].cpu().numpy(), L.rms(y)[0], rtol=1e-5, atol=1e-9)
+
+
+def test_stft_ragged_batch_unaligned_rows_and_silence(dev):
+    # rows of 4099 samples: every second clip starts on a non-16-byte boundary (scalar load path)
+    rng = np.random.default_rng(7)
+    y = rng.normal(0, 0.2, (5, 4099)).astype(np.float32)
+    y[2] = 0.0  # digital silence must give exact zeros
+    out = P.core.stft_features(_dev(y, dev), want_mag=True, want_rms=True)
+    for c in range(5):
+        _assert_mag_close(out["mag"][c].cpu().numpy(), L.stft_magnitude(y[c]))
+    assert float(out["mag"][2].abs().max()) == 0.0 and float(out["rms"][2].abs().max()) == 0.0
+    # a strided view (clip_stride > n_samples) is honoured
+    big = _dev(rng.normal(0, 0.2, (3, 9000)).astype(np.float32), dev)
+    view = big[:, :8192]
+    o2 = P.core.stft_features(view, want_mag=True)
+    for c in range(3):
+        _assert_mag_close(o2["mag"][c].cpu().numpy(), L.stft_magnitude(view[c].cpu().numpy()))
+
+
+def test_stft_hop_and_uncentred(dev):
+    y, sr = SIGNALS["clip3"]()
+    for hop in (128, 256):
+        out = P.core.stft_features(_dev(y, dev), hop_length=hop, want_mag=True)
+        _assert_mag_close(out["mag"][0].cpu().numpy(), L.stft_magnitude(y, hop_length=hop))
+    out = P.core.stft_features(_dev(y, dev), center=False, want_mag=True)
+    _assert_mag_close(out["mag"][0].cpu().numpy(), L.stft_magnitude(y, center=False))
+
+
+def test_stft_size_independent_properties_at_batch_scale(dev):
+    """Homogeneity (x2 is exact in fp32), hop-shift equivariance and batch independence on a
+    64 x 30 s batch of BASELINE cfg2 clips (too large to compare against the oracle bin by bin)."""
+    clips = corpus.clip_batch(4, 30.0, 22050, first_seed=100)
+    y = _dev(np.tile(clips, (16, 1)), dev)
+    y = y * torch.linspace(0.25, 1.0, 64, device=dev)[:, None]
+    a = P.core.stft_features(y, sr=22050, want_mag=True, want_mel=True, want_rms=True)
+    b = P.core.stft_features(y * 2.0, sr=22050, want_mag=True, want_rms=True)
+    assert torch.equal(a["mag"] * 2.0, b["mag"]) and torch.equal(a["rms"] * 2.0, b["rms"])
+    shifted = P.core.stft_features(y[:, 512:].contiguous(), want_mag=True)["mag"]
+    T = shifted.shape[2]
+    assert torch.equal(shifted[:, :, 2:T - 2], a["mag"][:, :, 3:T - 1])  # interior frames move by one hop
+    alone = P.core.stft_features(y[37:38].contiguous(), sr=22050, want_mag=True, want_mel=True)
+    assert torch.equal(alone["mag"][0], a["mag"][37]) and torch.equal(alone["mel"][0], a["mel"][37])
+    _assert_mag_close(a["mag"][5].cpu().numpy(), L.stft_magnitude(y[5].cpu().numpy()))
+    # Parseval on the windowed frames: sum |X|^2 (two-sided) == N * sum (w x)^2
+    w = torch.from_numpy(tables.hann_window().astype(np.float32)).to(dev)
+    fr = torch.nn.functional.pad(y[:2], (1024, 1024)).unfold(1, 2048, 512) * w
+    lhs = (a["mag"][:2] ** 2).sum(1) * 2 - a["mag"][:2, 0] ** 2 - a["mag"][:2, 1024] ** 2
+    rhs = 2048 * (fr ** 2).sum(2)
+    assert torch.allclose(lhs, rhs, rtol=2e-4, atol=1e-3)
+
+
+# ---------------------------------------------------------------------------------- K4 dB / rake / onsets
+def test_rake_mask_kernel_matches_reference_golden(dev, golden):
+    names = sorted({k.split("/")[1] for k in golden if k.startswith("rake/")})
+    fired = 0
+    for n in names:
+        hop, sr, ratio = golden[f"rake/{n}/args"]
+        got = P.vision.detect_rake_patterns(golden[f"rake/{n}/S_dB"], int(hop), int(sr), float(ratio))
+        assert got.dtype == bool
+        np.testing.assert_array_equal(got, golden[f"rake/{n}/mask"], err_msg=n)
+        fired += int(got.sum())
+    assert fired > 0
+
+
+@pytest.mark.parametrize("name", list(SIGNALS))
+def test_db_rake_rms_onsets_match_oracle(dev, name):
+    y, sr = SIGNALS[name]()
+    spec = P.batch.spectral_features(_dev(y, dev), sr=sr, with_sdb=True, with_onsets=True)
+    S_ref = L.load_audio_features(y, sr)
+    S = spec["S_dB"][0].cpu().numpy()
+    assert S.dtype == np.float32 and S.shape == S_ref.shape
+    assert np.abs(S - S_ref).max() < 5e-3 and S.max() == 0.0 and S.min() >= -80.0
+    for ratio in (0.6, 0.5):
+        m = P.batch.spectral_features(_dev(y, dev), sr=sr, rake_sensitivity=ratio, with_onsets=False)["rake_mask"]
+        np.testing.assert_array_equal(m[0].cpu().numpy().astype(bool), R.detect_rake_patterns(S_ref, 512, sr, ratio))
+    env_ref = L.onset_strength(y=y, sr=sr)
+    env = spec["onset_env"][0].cpu().numpy()
+    np.testing.assert_allclose(env, env_ref, atol=2e-3)
+    frames = np.flatnonzero(spec["onset_peaks"][0].cpu().numpy())
+    np.testing.assert_array_equal(frames, L.onset_detect(onset_envelope=env_ref, sr=sr))
+    assert int(spec["n_onsets"][0]) == len(frames)
+    # the peak picker on the oracle's own envelope (isolates K4b from fp32 noise in the envelope)
+    np.testing.assert_array_equal(P.librosa_compat.onset_detect(onset_envelope=env_ref, sr=sr),
+                                  L.onset_detect(onset_envelope=env_ref, sr=sr))
+
+
+def test_compat_signatures_and_dtypes(dev):
+    lib = P.librosa_compat
+    y, sr = SIGNALS["track22050"]()
+    S = lib.feature.melspectrogram(y=y, sr=sr, n_fft=2048, hop_length=512)
+    S_dB = lib.power_to_db(S, ref=np.max)
+    assert S.shape == S_dB.shape == (128, 1 + len(y) // 512) and S_dB.dtype == np.float32
+    np.testing.assert_allclose(lib.power_to_db(S, ref=1.0), L.power_to_db(S), atol=5e-3)
+    r = lib.feature.rms(y=y, hop_length=512)
+    assert r.shape == (1, S.shape[1]) and r.dtype == np.float32
+    f0, vf, vp = lib.pyin(y, fmin=lib.note_to_hz("E2"), fmax=lib.note_to_hz("C6"), sr=sr, hop_length=512)
+    assert f0.dtype == np.float64 and vf.dtype == bool and vp.dtype == np.float64 and len(f0) == S.shape[1]
+    assert np.isnan(f0[~vf]).all() and not np.isnan(f0[vf]).any()
+    f0b, vfb, _ = lib.pyin(y, fmin=E2, fmax=C6, sr=sr, fill_na=None)
+    assert not np.isnan(f0b).any() and np.array_equal(vf, vfb)
+    f0r, vfr, _ = lib.pyin(y, fmin=E2, fmax=C6, sr=sr, pad_mode="reflect")
+    ref = L.pyin(np.pad(y, 1024, mode="reflect"), fmin=E2, fmax=C6, sr=sr, center=False)
+    assert np.array_equal(vfr, ref[1])
+    with pytest.raises(lib.ParameterError):
+        lib.pyin(y, fmin=None, fmax=C6)
+    with pytest.raises(TypeError):
+        lib.util.softmask(np.ones(3), np.ones(3), margin=0.5)  # midi_logic.py:43 relies on this TypeError
+    assert P.worker._pyin_worker((y[:8192], sr, 512))[0].shape == (17,)
+    eng = P.AegisEngine(sample_rate=sr)
+    assert eng.audio_to_midi(np.zeros(0, np.float32), None) is None
+    res = eng.audio_to_midi(y, "ignored.mid")
+    assert sorted(res) == ["f0", "rake_mask", "rms", "voiced_flag", "voiced_probs", "y"]
+    assert res["y"] is not None and not np.isnan(res["f0"]).any() and res["rake_mask"].dtype == bool
+    y2, S2 = eng.load_audio(y)
+    np.testing.assert_array_equal(eng.detect_rake_patterns(S2), res["rake_mask"])
+
+
+# ---------------------------------------------------------------------------------- K2 / K3 pYIN
+def _oracle_pyin(y, sr, fmax=C6):
+    return L.pyin(y, fmin=E2, fmax=fmax, sr=sr, hop_length=512, return_intermediates=True)
+
+
+def _sparse_from_dense(obs, n_bins, max_cand, dev):
+    T = obs.shape[1]
+    cb = np.zeros((T, max_cand), np.int16)
+    cp = np.zeros((T, max_cand), np.float64)
+    cc = np.zeros(T, np.int32)
+    for t in range(T):
+        nz = np.flatnonzero(obs[:n_bins, t])
+        cc[t] = len(nz)
+        cb[t, : len(nz)] = nz
+        cp[t, : len(nz)] = obs[nz, t]
+    vp = np.clip(obs[:n_bins].sum(axis=0), 0, 1)
+    return dict(cand_bin=torch.from_numpy(cb).to(dev), cand_prob=torch.from_numpy(cp).to(dev),
+                cand_count=torch.from_numpy(cc).to(dev), voiced_prob=torch.from_numpy(vp).to(dev)[None],
+                n_frames=T, max_cand=max_cand)
+
+
+@pytest.mark.parametrize("name,fmax", [("track22050", C6), ("track44100", C6), ("clip3", C6), ("clip3", E6), ("bench22050", C6)])
+def test_viterbi_is_bit_exact_on_oracle_observations(dev, name, fmax):
+    y, sr = SIGNALS[name]()
+    f0, vf, vp, it = _oracle_pyin(y, sr, fmax)
+    cfg = tables.pyin_config(float(sr), 512, E2, fmax)
+    assert cfg.n_pitch_bins == it["n_pitch_bins"]
+    obs = _sparse_from_dense(it["observation_probs"], cfg.n_pitch_bins, cfg.max_troughs, dev)
+    dec = P.core.viterbi_decode(obs, cfg, 1)
+    states = dec["states"][0].cpu().numpy().astype(np.uint16)
+    np.testing.assert_array_equal(states, it["states"])
+    np.testing.assert_array_equal(dec["voiced_flag"][0].cpu().numpy().astype(bool), vf)
+    np.testing.assert_array_equal(dec["f0"][0].cpu().numpy(), f0)  # NaN == NaN under assert_array_equal
+
+
+def test_viterbi_adversarial_observations(dev):
+    """Random sparse observations incl. voiced_prob == 1 (unvoiced rows log(tiny)), far jumps that force
+    out-of-band transitions, empty frames and edge bins: states must still equal the dense float64 decoder."""
+    sr = 22050
+    cfg = tables.pyin_config(float(sr), 512, E2, C6)
+    n = cfg.n_pitch_bins
+    trans, _ = L.pyin_transition(n, 10, sr, 512)
+    p_init = np.zeros(2 * n)
+    p_init[n:] = 1 / n
+    rng = np.random.default_rng(11)
+    for trial in range(3):
+        T = 120
+        obs = np.zeros((2 * n, T))
+        for t in range(T):
+            k = int(rng.integers(0, 6))
+            bins = rng.choice(n, size=k, replace=False) if trial else rng.choice([0, 1, 2, n - 1, n - 2, 200, 260], size=min(k, 7), replace=False)
+            pr = rng.random(len(bins))
+            if len(bins) and rng.random() < 0.4:
+                pr = pr / pr.sum()  # voiced_prob == 1 up to rounding, clipped to exactly 1 below
+            else:
+                pr = pr * rng.random() / max(1, len(bins))
+            obs[bins, t] = pr
+        vp = np.clip(obs[:n].sum(axis=0, keepdims=True), 0, 1)
+        obs[n:, :] = (1 - vp) / n
+        ref = L.viterbi(obs, trans, p_init)
+        dec = P.core.viterbi_decode(_sparse_from_dense(obs, n, cfg.max_troughs, dev), cfg, 1)
+        np.testing.assert_array_equal(dec["states"][0].cpu().numpy().astype(np.uint16), ref, err_msg=f"trial {trial}")
+
+
+@pytest.mark.parametrize("name,fmax", [("track22050", C6), ("track44100", C6), ("clip3", C6), ("clip3", E6), ("bench22050", C6)])
+def test_yin_candidates_match_oracle(dev, name, fmax):
+    y, sr = SIGNALS[name]()
+    f0, vf, vp, it = _oracle_pyin(y, sr, fmax)
+    cfg = tables.pyin_config(float(sr), 512, E2, fmax)
+    n = cfg.n_pitch_bins
+    obs = P.core.yin_candidates(_dev(y, dev), cfg)
+    assert int(obs["overflow"][0]) == 0
+    T = obs["n_frames"]
+    cb = obs["cand_bin"].cpu().numpy().astype(np.int64)
+    cp = obs["cand_prob"].cpu().numpy()
+    cc = obs["cand_count"].cpu().numpy()
+    dense = np.zeros((n, T))
+    for t in range(T):
+        assert (np.diff(cb[t, : cc[t]]) > 0).all()  # ascending, unique
+        dense[cb[t, : cc[t]], t] = cp[t, : cc[t]]
+    ref = it["observation_probs"][:n]
+    same_support = ((dense > 0) == (ref > 0)).all(axis=0)
+    # fp32 difference functions differ in the last bits between FFT implementations: a trough sitting on a
+    # threshold edge or a .5 bin boundary may move.  Bound it (measured: a few frames per thousand) ...
+    assert same_support.mean() >= 0.97, f"{(~same_support).sum()} of {T} frames have a different candidate set"
+    ok = same_support
+    np.testing.assert_allclose(dense[:, ok], ref[:, ok], rtol=0, atol=2e-3)
+    frac_tight = (np.abs(dense[:, ok] - ref[:, ok]).max(axis=0) < 1e-6).mean()
+    assert frac_tight >= 0.9
+    np.testing.assert_allclose(obs["voiced_prob"][0].cpu().numpy()[ok], vp[ok], atol=2e-3)
+
+
+@pytest.mark.parametrize("name", ["track22050", "track44100", "bench22050", "clip3"])
+def test_pyin_end_to_end_voicing_exact_f0_within_one_cent(dev, name):
+    y, sr = SIGNALS[name]()
+    f0_ref, vf_ref, vp_ref = L.pyin(y, fmin=E2, fmax=C6, sr=sr, hop_length=512)
+    f0, vf, vp = P.librosa_compat.pyin(y, fmin=E2, fmax=C6, sr=sr, hop_length=512)
+    np.testing.assert_array_equal(vf, vf_ref)          # voiced flags: bit-exact
+    both = vf & vf_ref
+    cents = 1200 * np.abs(np.log2(f0[both] / f0_ref[both]))
+    assert cents.max() <= 1.0, f"{(cents > 1).sum()} voiced frames off by more than one cent (max {cents.max():.2f})"
+    np.testing.assert_allclose(vp, vp_ref, atol=2e-3)
+    midi = np.round(L.hz_to_midi(f0[both])).astype(int)
+    np.testing.assert_array_equal(midi, np.round(L.hz_to_midi(f0_ref[both])).astype(int))  # MIDI note numbers
+
+
+def test_pyin_batch_equals_single_and_handles_silence(dev):
+    clips = corpus.clip_batch(3, 4.0, 22050, first_seed=40)
+    clips[1] = 0.0
+    res = P.core.pyin_batch(_dev(clips, dev), sr=22050, fmin=E2, fmax=C6)
+    assert not bool(res["voiced_flag"][1].any()) and float(res["voiced_prob"][1].abs().max()) == 0.0
+    for c in (0, 2):
+        one = P.core.pyin_batch(_dev(clips[c], dev), sr=22050, fmin=E2, fmax=C6)
+        assert torch.equal(one["states"][0], res["states"][c])
+        assert torch.equal(one["voiced_prob"][0], res["voiced_prob"][c])
+    split = P.core.pyin_batch(_dev(clips, dev), sr=22050, fmin=E2, fmax=C6, clips_per_launch=2)
+    assert torch.equal(split["states"], res["states"])
+
+
+# ---------------------------------------------------------------------------------- K5 trend filters
+EXACT = {"kalman": "kalman", "holt": "holt", "ema5": "ema", "macd": "macd_line", "macd_signal": "macd_sig",
+         "macd_hist": "macd_hist"}
+CLOSE = {"savgol": "savgol", "consensus": "consensus", "consensus_conf": "consensus_conf", "sma5": "sma",
+         "boll_ma": "boll_ma", "boll_up": "boll_upper", "boll_lo": "boll_lower"}
+
+
+def test_trend_filters_match_reference_golden(dev, golden):
+    names = sorted({k.split("/")[1] for k in golden if k.startswith("filt/")})
+    assert len(names) >= 6
+    for n in names:
+        f0 = golden[f"filt/{n}/f0"]
+        out = P.core.trend_filters(torch.from_numpy(f0).to(dev), sma_window=5, ema_span=5, boll_window=10)
+        got = {k: v[0].cpu().numpy() for k, v in out.items()}
+        for gk, ok in EXACT.items():   # scalar recurrences: same IEEE operations in the same order
+            np.testing.assert_array_equal(got[ok], golden[f"filt/{n}/{gk}"], err_msg=f"{n}/{gk}")
+        for gk, ok in CLOSE.items():   # windowed sums: numpy/BLAS summation order is unspecified
+            np.testing.assert_allclose(got[ok], golden[f"filt/{n}/{gk}"], rtol=1e-12, atol=1e-9, err_msg=f"{n}/{gk}")
+        sma10 = P.core.trend_filters(torch.from_numpy(f0).to(dev), want=("sma",), sma_window=10)["sma"][0].cpu().numpy()
+        np.testing.assert_allclose(sma10, golden[f"filt/{n}/sma10"], rtol=1e-12, atol=1e-9)
+
+
+def test_filter_classes_mirror_reference_api(dev, golden):
+    from spectrogram_midi_b200.financial_analysis import FinancialPitchAnalyzer
+    from spectrogram_midi_b200.financial_filters import FinancialNoiseFilters, multi_filter_consensus
+
+    for n in ("gappy", "allnan", "onevalid", "short"):
+        f0 = golden[f"filt/{n}/f0"]
+        np.testing.assert_array_equal(FinancialNoiseFilters.kalman_filter(f0), golden[f"filt/{n}/kalman"])
+        np.testing.assert_array_equal(FinancialNoiseFilters.holt_winters(f0), golden[f"filt/{n}/holt"])
+        np.testing.assert_allclose(FinancialNoiseFilters.savitzky_golay(f0), golden[f"filt/{n}/savgol"], rtol=1e-12, atol=1e-9)
+        c, conf = multi_filter_consensus(f0)
+        np.testing.assert_allclose(c, golden[f"filt/{n}/consensus"], rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(conf, golden[f"filt/{n}/consensus_conf"], rtol=1e-9, atol=1e-9)
+        an = FinancialPitchAnalyzer(sr=22050, hop_length=512)
+        np.testing.assert_allclose(an.bollinger_confidence(f0, 10), golden[f"filt/{n}/an_conf"], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(an.analyze_pitch_numeric(f0)["trend"], golden[f"filt/{n}/an_trend"], rtol=1e-12, atol=1e-9)
+    with pytest.raises(IndexError):
+        FinancialPitchAnalyzer().simple_moving_average(np.ones(4), window=5)  # the reference raises here too
+    c, conf = multi_filter_consensus(golden["filt/gappy/f0"], filters=[])
+    assert (conf == 1).all()
+
+
+# ---------------------------------------------------------------------------------- end to end: note events
+def test_midi_note_events_identical_to_reference(dev, golden):
+    """GPU perception -> the (pinned) restatement of midi_logic.get_midi_events == the events the REAL
+    reference midi_logic produced from the oracle's perception arrays (tests/golden/make_golden.py)."""
+    tech = {None: 0, "vibrato": 1, "bend": 2, "slide": 3, "hammer_on": 4, "pull_off": 5}
+    inputs = {"track22050": (corpus.test_track(22050, 0, 10.0), 22050), "track44100": (corpus.test_track(44100, 0), 44100),
+              "clip7": (corpus.random_clip(7, 12.0, 22050), 22050)}
+    total = 0
+    for name, (y, sr) in inputs.items():
+        res = P.AegisEngine(sample_rate=sr).audio_to_midi(y, None)
+        np.testing.assert_array_equal(res["voiced_flag"], golden[f"midi/{name}/voiced_flag"])
+        np.testing.assert_array_equal(res["rake_mask"], golden[f"midi/{name}/rake_mask"])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ev = R.get_midi_events(res["rake_mask"], res["f0"], res["voiced_flag"], res["voiced_probs"], res["rms"], sr, 512, 0.70)
+        got = np.array([[e["note"], e["start"], e["end"], e["velocity"], int(e["track"] == "main"), tech[e.get("technique")]]
+                        for e in ev], dtype=np.int64).reshape(-1, 6)
+        np.testing.assert_array_equal(got, golden[f"midi/{name}/events"], err_msg=name)
+        total += len(ev)
+    assert total >= 10
+
+
+def test_full_batch_pipeline_with_trend(dev):
+    clips = corpus.clip_batch(6, 5.0, 22050, first_seed=20)
+    res = P.batch.analyze_batch(_dev(clips, dev), sr=22050, with_onsets=True, with_trend=True, with_sdb=True, nan_to_num=False)
+    T = 1 + clips.shape[1] // 512
+    assert res["f0"].shape == (6, T) and res["trend"].shape == (6, T) and res["S_dB"].shape == (6, 128, T)
+    for c in (0, 5):
+        f0_ref, vf_ref, _ = L.pyin(clips[c], fmin=E2, fmax=C6, sr=22050, hop_length=512)
+        assert (res["voiced_flag"][c].cpu().numpy().astype(bool) == vf_ref).mean() > 0.995
+        f0 = res["f0"][c].cpu().numpy()
+        trend_ref, _ = R.multi_filter_consensus(f0)
+        np.testing.assert_allclose(res["trend"][c].cpu().numpy(), trend_ref, rtol=1e-12, atol=1e-9)
+    host = P.batch.to_host(res, 3, y=clips[3])
+    assert set(host) >= {"rake_mask", "f0", "voiced_flag", "voiced_probs", "rms", "y", "onset_frames", "trend"}
+
+
+def test_synth_corpus_kernel(dev):
+    plan = corpus.plan_events(8, 3.0, 22050, first_seed=0)
+    y = P.core.synth_events(8, int(3.0 * 22050), plan, dev)
+    assert y.shape == (8, 66150) and torch.isfinite(y).all()
+    assert torch.allclose(y.abs().amax(dim=1), torch.full((8,), 0.9, device=dev), atol=1e-6)
+    f0, vf, _ = P.librosa_compat.pyin(y[0].cpu().numpy(), fmin=E2, fmax=C6, sr=22050)
+    assert vf.mean() > 0.3  # plucked strings are pitched
