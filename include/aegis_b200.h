@@ -62,9 +62,11 @@ typedef struct {
     int32_t mel_row_stride;
     int32_t _reserved0;
     const int32_t* mel_start;  /* [n_mels] first FFT bin of each triangle */
-    const int32_t* mel_len;    /* [n_mels] */
-    const int32_t* mel_off;    /* [n_mels] offset into mel_w */
-    const float* mel_w;        /* packed non-zero triangle weights */
+    const int32_t* mel_len;    /* [n_mels] number of non-zero weights */
+    const int32_t* mel_off;    /* [n_mels] offset of each triangle in mel_w */
+    const float* mel_w;        /* [mel_nnz] packed non-zero triangle weights (staged in shared memory) */
+    int32_t mel_nnz;           /* <= 2304 */
+    int32_t _reserved1;
     float* mel_max;            /* [n_clips] or NULL */
     float* rms;                /* [n_clips][rms_clip_stride] or NULL */
     int64_t rms_clip_stride;
@@ -158,6 +160,7 @@ typedef struct {
     int32_t* cand_count;       /* [n_clips * n_frames] */
     double* voiced_prob;       /* [n_clips * n_frames] */
     int32_t* overflow;         /* [1]: set non-zero if any frame had more than max_cand candidates */
+    double* cmnd_out;          /* optional [n_clips * n_frames][max_period - min_period + 1] CMND curves, or NULL */
 } aegis_yin_params;
 
 int aegis_yin_candidates(const aegis_yin_params* p, void* stream);

@@ -88,9 +88,9 @@ def frame_count(n_samples: int, hop_length: int = 512, n_fft: int = 2048, center
     return 1 + (n_samples - n_fft) // hop_length
 
 
-def frame_signal(y, frame_length=2048, hop_length=512, center=True):
+def frame_signal(y, frame_length=2048, hop_length=512, center=True, dtype=np.float32):
     """[frame_length, T] float32 view-like array of (zero centre-padded) frames."""
-    y = np.asarray(y, dtype=np.float32)
+    y = np.asarray(y, dtype=dtype)
     if center:
         y = np.pad(y, frame_length // 2, mode="constant")
     T = 1 + (len(y) - frame_length) // hop_length
@@ -404,14 +404,20 @@ def pyin(
     fill_na=np.nan,
     center=True,
     return_intermediates=False,
+    frames_dtype=np.float32,
 ):
-    """librosa.pyin (>= 0.10, pad_mode='constant').  Returns (f0, voiced_flag, voiced_prob)."""
+    """librosa.pyin (>= 0.10, pad_mode='constant').  Returns (f0, voiced_flag, voiced_prob).
+
+    ``frames_dtype=np.float64`` evaluates the same algorithm in exact-ish arithmetic (librosa itself
+    runs the difference function in float32); the tests use it to measure how much of any
+    disagreement is the reference's own rounding noise.
+    """
     if win_length is None:
         win_length = frame_length // 2
     if hop_length is None:
         hop_length = frame_length // 4
     y = np.asarray(y, dtype=np.float32)
-    y_frames = frame_signal(y, frame_length, hop_length, center)
+    y_frames = frame_signal(y, frame_length, hop_length, center, dtype=frames_dtype)
     min_period, max_period = pyin_periods(sr, fmin, fmax, frame_length, win_length)
     yin_frames = cmnd(y_frames, frame_length, win_length, min_period, max_period)
     parabolic_shifts = parabolic_interpolation(yin_frames)

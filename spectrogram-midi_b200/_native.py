@@ -28,7 +28,7 @@ class StftParams(C.Structure):
         ("pad", i32), ("n_frames", i32), ("window", _ptr), ("twiddle", _ptr),
         ("mag", _ptr), ("mag_clip_stride", i64), ("mag_row_stride", i32), ("n_mels", i32),
         ("mel", _ptr), ("mel_clip_stride", i64), ("mel_row_stride", i32), ("_reserved0", i32),
-        ("mel_start", _ptr), ("mel_len", _ptr), ("mel_off", _ptr), ("mel_w", _ptr),
+        ("mel_start", _ptr), ("mel_len", _ptr), ("mel_off", _ptr), ("mel_w", _ptr), ("mel_nnz", i32), ("_reserved1", i32),
         ("mel_max", _ptr), ("rms", _ptr), ("rms_clip_stride", i64),
     ]
 
@@ -61,7 +61,7 @@ class YinParams(C.Structure):
         ("thresholds", _ptr), ("beta_probs", _ptr), ("beta_cumsum", _ptr),
         ("boltz_fact", _ptr), ("boltz_exp", _ptr), ("no_trough_prob", f64),
         ("cand_bin", _ptr), ("cand_prob", _ptr), ("cand_count", _ptr), ("voiced_prob", _ptr),
-        ("overflow", _ptr),
+        ("overflow", _ptr), ("cmnd_out", _ptr),
     ]
 
 

@@ -75,21 +75,24 @@ def _check_fft(n_fft: int, hop_length: int):
 # ----------------------------------------------------------------------------------------------
 def stft_features(y: torch.Tensor, *, sr: Optional[float] = None, hop_length: int = 512, n_fft: int = N_FFT,
                   center: bool = True, n_mels: int = 128, want_mag: bool = True, want_mel: bool = False,
-                  want_rms: bool = False, mag_out: Optional[torch.Tensor] = None) -> dict:
+                  want_rms: bool = False, mag_out: Optional[torch.Tensor] = None,
+                  pad: Optional[int] = None, n_frames: Optional[int] = None) -> dict:
     """Fused STFT magnitude / mel power / RMS of a batch of clips.
 
     Returns a dict with the requested keys: ``mag`` [n_clips, 1025, T], ``mel`` [n_clips, n_mels, T],
-    ``mel_max`` [n_clips], ``rms`` [n_clips, T] (all float32, librosa layouts).
+    ``mel_max`` [n_clips], ``rms`` [n_clips, T] (all float32, librosa layouts).  ``pad`` / ``n_frames``
+    override the framing (frame t covers samples [t*hop - pad, t*hop - pad + 2048)): used when ``y`` is a
+    window cut out of a longer recording (``distributed.analyze_long_clip``).
     """
     _check_fft(n_fft, hop_length)
     y = _check_audio(y)
     dev = y.device
     n_clips, n_samples = y.shape
-    T = frame_count(n_samples, hop_length, center)
+    T = frame_count(n_samples, hop_length, center) if n_frames is None else int(n_frames)
     out: dict = {"n_frames": T}
     P = nat.StftParams()
     P.y, P.clip_stride, P.n_samples, P.n_clips = _audio_ptr(y), y.stride(0), n_samples, n_clips
-    P.hop, P.pad, P.n_frames = hop_length, (N_FFT // 2 if center else 0), T
+    P.hop, P.pad, P.n_frames = hop_length, ((N_FFT // 2 if center else 0) if pad is None else int(pad)), T
     P.window = _dev_tensor("hann32", dev, lambda: tables.hann_window().astype(np.float32)).data_ptr()
     P.twiddle = _dev_tensor("twiddle", dev, tables.fft_twiddles).data_ptr()
     if want_mag:
@@ -107,6 +110,7 @@ def stft_features(y: torch.Tensor, *, sr: Optional[float] = None, hop_length: in
         P.mel_len = _dev_tensor(key + ("l",), dev, lambda: sm.length).data_ptr()
         P.mel_off = _dev_tensor(key + ("o",), dev, lambda: sm.offset).data_ptr()
         P.mel_w = _dev_tensor(key + ("w",), dev, lambda: sm.weights).data_ptr()
+        P.mel_nnz = int(sm.weights.size)
         mel = torch.empty((n_clips, n_mels, T), dtype=torch.float32, device=dev)
         mel_max = torch.zeros((n_clips,), dtype=torch.float32, device=dev)
         P.n_mels = n_mels
@@ -194,20 +198,21 @@ def onset_peaks(onset_env: torch.Tensor, env_minmax: torch.Tensor, *, sr: float,
 # K2 + K3
 # ----------------------------------------------------------------------------------------------
 def yin_candidates(y: torch.Tensor, cfg: tables.PyinConfig, *, center: bool = True,
-                   max_cand: Optional[int] = None) -> dict:
+                   max_cand: Optional[int] = None, pad: Optional[int] = None, n_frames: Optional[int] = None,
+                   want_cmnd: bool = False) -> dict:
     """Sparse pYIN observations per frame (bins ascending, unique) + voiced probability."""
     _check_fft(cfg.frame_length, cfg.hop_length)
     y = _check_audio(y)
     dev = y.device
     n_clips, n_samples = y.shape
-    T = frame_count(n_samples, cfg.hop_length, center)
+    T = frame_count(n_samples, cfg.hop_length, center) if n_frames is None else int(n_frames)
     if max_cand is None:
         max_cand = cfg.max_troughs
     n_fr = n_clips * T
     key = ("pyin", cfg.sr, cfg.hop_length, cfg.fmin, cfg.fmax, cfg.n_thresholds)
     P = nat.YinParams()
     P.y, P.clip_stride, P.n_samples, P.n_clips = _audio_ptr(y), y.stride(0), n_samples, n_clips
-    P.hop, P.pad, P.n_frames = cfg.hop_length, (cfg.frame_length // 2 if center else 0), T
+    P.hop, P.pad, P.n_frames = cfg.hop_length, ((cfg.frame_length // 2 if center else 0) if pad is None else int(pad)), T
     P.twiddle = _dev_tensor("twiddle", dev, tables.fft_twiddles).data_ptr()
     P.sr, P.fmin = cfg.sr, cfg.fmin
     P.min_period, P.max_period = cfg.min_period, cfg.max_period
@@ -226,9 +231,16 @@ def yin_candidates(y: torch.Tensor, cfg: tables.PyinConfig, *, center: bool = Tr
     overflow = torch.zeros((1,), dtype=torch.int32, device=dev)
     P.cand_bin, P.cand_prob, P.cand_count = cand_bin.data_ptr(), cand_prob.data_ptr(), cand_count.data_ptr()
     P.voiced_prob, P.overflow = voiced_prob.data_ptr(), overflow.data_ptr()
+    cmnd = None
+    if want_cmnd:
+        cmnd = torch.empty((n_fr, cfg.n_lags), dtype=torch.float64, device=dev)
+        P.cmnd_out = cmnd.data_ptr()
     nat.call("aegis_yin_candidates", P, _stream())
-    return dict(cand_bin=cand_bin, cand_prob=cand_prob, cand_count=cand_count,
-                voiced_prob=voiced_prob.view(n_clips, T), overflow=overflow, n_frames=T, max_cand=max_cand)
+    out = dict(cand_bin=cand_bin, cand_prob=cand_prob, cand_count=cand_count,
+               voiced_prob=voiced_prob.view(n_clips, T), overflow=overflow, n_frames=T, max_cand=max_cand)
+    if cmnd is not None:
+        out["cmnd"] = cmnd.view(n_clips, T, cfg.n_lags)
+    return out
 
 
 def viterbi_decode(obs: dict, cfg: tables.PyinConfig, n_clips: int, *, fill_na: Optional[float] = float("nan")) -> dict:

@@ -144,4 +144,42 @@ AEGIS_HD void fft2048_pass3(int lt, const cf* bufB, cf* out) {
     }
 }
 
+// ---- in-place variants: one exchange buffer (BUFA_SIZE) per transform.  The caller separates
+// "load" and "store" halves of passes 2 and 3 with a barrier so every read of the previous layout
+// has completed before the buffer is overwritten with the next one.
+AEGIS_HD void fft2048_pass2_load(int lt, const cf* buf, cf* v) {
+    const int bq = lt >> 3, t0 = lt & 7;
+#pragma unroll
+    for (int t1 = 0; t1 < 16; ++t1) v[t1] = buf[bq * BUFA_PITCH + t0 + 8 * t1];
+}
+
+AEGIS_HD void fft2048_pass2_store(int lt, cf* v, const FftTwiddles& tw, cf* buf) {
+    const int bq = lt >> 3, t0 = lt & 7;
+    fft16(v);
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+        cf u = v[pos16(d)];
+        if (d) u = cmul(u, tw.tw2[d]);
+        buf[t0 * BUFB_PITCH + d * 16 + bq] = u;
+    }
+}
+
+AEGIS_HD void fft2048_pass3_load(int lt, const cf* buf, cf* v /*[16]: two 8-point problems*/) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int t0 = 0; t0 < 8; ++t0) v[8 * r + t0] = buf[t0 * BUFB_PITCH + lt + 128 * r];
+}
+
+AEGIS_HD void fft2048_pass3_store(int lt, cf* v, cf* out) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        fft8(v + 8 * r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) out[lt + 128 * r + 256 * e] = v[8 * r + pos8(e)];
+    }
+}
+
+static_assert(BUFB_SIZE <= BUFA_SIZE && FFT_N <= BUFA_SIZE, "in-place exchange needs one BUFA_SIZE buffer");
+
 }  // namespace aegis

@@ -3,16 +3,22 @@
 // Replaces librosa.stft / feature.melspectrogram / feature.rms as called from
 // aegis_engine.py:25,70 and aegis_engine_financial.py:46-50,154 (see include/aegis_b200.h).
 //
-// Work unit ("tile") = 8 consecutive frames of one clip.  A persistent CTA of 512 threads
-// (4 FFT groups x 128 threads) walks tiles with stride gridDim.x, so neighbouring CTAs work on
-// neighbouring tiles of the same clip at the same time (halo samples and partially written
-// output sectors meet in L2).  Per tile:
+// Work unit ("tile") = 8 consecutive frames of one clip.  Persistent CTAs of 256 threads (2 FFT
+// groups x 128 threads), two resident per SM so one CTA's load / store phases overlap the other's
+// transforms.  Tiles are walked with stride gridDim.x: neighbouring CTAs work on neighbouring tiles
+// of the same clip at the same time (halo samples and partially written output sectors meet in L2).
+// Per tile:
 //   1. (7*hop + 2048) samples -> shared, float4 loads, zeros outside the clip (centre padding)
-//   2. each group packs two real frames (re = frame 2g, im = frame 2g+1) into one complex FFT
-//   3. X1[k], X2[k] are separated from Z[k], conj(Z[N-k]); magnitudes go to an [1025][8] stage
-//   4. the stage is written out as rows of 8 consecutive frames (one 32 B sector per row and
-//      tile) in librosa's [1025, T] layout; mel triangles and the clip maximum are taken from
-//      the stage, RMS from the raw samples.
+//   2. two rounds; in each, a group packs two real frames (re = frame a, im = frame b) into one
+//      complex transform.  Each frame is first scaled by an exact power of two ~ 1/||w x|| so the
+//      rounding error of the shared transform stays relative to the frame's OWN norm (a quiet frame
+//      next to an onset keeps its accuracy; an all-zero frame yields exact zeros).  The sums of
+//      squares needed for that scale and for the RMS output come from the values pass 1 loads anyway.
+//      The three radix passes exchange through ONE shared buffer per group (in place).
+//   3. X_a[k], X_b[k] are separated from Z[k], conj(Z[N-k]); magnitudes go to an [1025][8] stage
+//   4. the stage is written out in librosa's [1025, T] layout (float4 per half row when the row
+//      stride allows, else 8 scalar lanes per row); mel triangles and the clip maximum are taken
+//      from the stage with each thread owning a long + a short triangle (bands b and 127-b).
 // HBM traffic per frame: hop*4 B read (+ halo, L2-served) and 1025*4 B written.
 #include "common.cuh"
 #include "fft2048.cuh"
@@ -20,35 +26,55 @@
 namespace aegis {
 
 constexpr int TILE_F = 8;
-constexpr int STFT_THREADS = 512;
+constexpr int STFT_THREADS = 256;
+constexpr int STFT_GROUPS = STFT_THREADS / FFT_THREADS;  // 2
 constexpr int MAX_HOP = 512;
 constexpr int SAMPLES_MAX = (TILE_F - 1) * MAX_HOP + FFT_N;  // 5632
 constexpr int STAGE_PITCH = TILE_F + 1;
+constexpr int MEL_NNZ_MAX = 2304;   // packed triangle weights kept in shared memory (2050 for 128 Slaney bands)
 
 struct StftSmem {
     float samples[SAMPLES_MAX];
     float window[FFT_N];
-    cf bufA[4][BUFA_SIZE];
-    cf bufB[4][BUFB_SIZE];
+    float part[STFT_GROUPS][4][4];   // per warp: sum x_a^2, x_b^2, (w x_a)^2, (w x_b)^2 (float4 rows: keep 16 B aligned)
+    cf buf[STFT_GROUPS][BUFA_SIZE];
     float stage[AEGIS_N_BINS * STAGE_PITCH];
-    float rms_part[16];
+    float melw[MEL_NNZ_MAX];         // with ~205 KB of the SM carved out as shared memory only ~20 KB of L1 is left:
+                                     // weights read through L1 would thrash, so they live here
 };
+static_assert((SAMPLES_MAX * 4) % 16 == 0 && (FFT_N * 4) % 16 == 0, "part[] must stay 16-byte aligned");
 
-__global__ void __launch_bounds__(STFT_THREADS, 1)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ int pack_exponent(float windowed_energy) {
+    return (windowed_energy > 0.f) ? (ilogbf(windowed_energy) >> 1) : 0;
+}
+
+__global__ void __launch_bounds__(STFT_THREADS, 2)
 stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const long long n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int g = tid >> 7, lt = tid & 127, lane = tid & 31, warp = tid >> 5;
+    const int g = tid >> 7, lt = tid & 127, lane = tid & 31, warp = tid >> 5, gw = warp & 3;
     const int T = p.n_frames;
     const int hop = p.hop;
     const long long N = p.n_samples;
 
     for (int i = tid; i < FFT_N; i += STFT_THREADS) s.window[i] = p.window[i];
+    if (p.mel != nullptr)
+        for (int i = tid; i < p.mel_nnz; i += STFT_THREADS) s.melw[i] = p.mel_w[i];
     FftTwiddles tw;
     fft2048_load_twiddles(lt, reinterpret_cast<const cf*>(p.twiddle), tw);
     const int n_buf = (TILE_F - 1) * hop + FFT_N;
     const bool do_fft = (p.mag != nullptr) || (p.mel != nullptr);
+    cf* const buf = s.buf[g];
+    constexpr int N_ROUNDS = TILE_F / (2 * STFT_GROUPS);
+    bool prefetched = false;  // the samples of this tile were requested with cp.async during the previous one
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int clip = static_cast<int>(tile / tiles_per_clip);
@@ -56,8 +82,10 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
         const float* __restrict__ yc = p.y + static_cast<long long>(clip) * p.clip_stride;
         const long long g0 = static_cast<long long>(t0) * hop - p.pad;
 
-        __syncthreads();  // everybody is done with the previous tile's samples / stage
-        {
+        __syncthreads();  // everybody is done with the previous tile's stage (and samples, if not prefetched)
+        if (prefetched) {
+            cp_async_wait_all();
+        } else {
             const bool vec_ok = ((reinterpret_cast<uintptr_t>(yc) & 15) == 0) && ((g0 & 3) == 0);
             for (int i = tid * 4; i < n_buf; i += STFT_THREADS * 4) {
                 const long long gi = g0 + i;
@@ -75,86 +103,148 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
         }
         __syncthreads();
 
-        if (p.rms != nullptr) {  // sum of squares of each frame, two warps per frame
-            const float* fr = s.samples + (warp >> 1) * hop + (warp & 1) * (FFT_N / 2);
-            float acc = 0.f;
-#pragma unroll 8
-            for (int i = lane; i < FFT_N / 2; i += 32) acc = fmaf(fr[i], fr[i], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) s.rms_part[warp] = acc;
-        }
-
-        if (!do_fft) {  // RMS-only call (librosa.feature.rms): no transform needed
-            __syncthreads();
-            if (p.rms != nullptr && tid < TILE_F && t0 + tid < T) {
-                p.rms[static_cast<long long>(clip) * p.rms_clip_stride + t0 + tid] =
-                    sqrtf((s.rms_part[2 * tid] + s.rms_part[2 * tid + 1]) * (1.0f / FFT_N));
-            }
-            continue;
-        }
-        {   // pass 1: window + pack two real frames
-            const float* fa = s.samples + (2 * g) * hop;
+#pragma unroll 1
+        for (int round = 0; round < N_ROUNDS; ++round) {
+            const int fa_idx = 2 * (round * STFT_GROUPS + g);  // this group's frame pair (fa_idx, fa_idx + 1)
+            const float* fa = s.samples + fa_idx * hop;
             const float* fb = fa + hop;
             cf v[16];
+            float ea2 = 0.f, eb2 = 0.f, wa2 = 0.f, wb2 = 0.f;
 #pragma unroll
             for (int a = 0; a < 16; ++a) {
                 const int n = lt + 128 * a;
-                const float w = s.window[n];
-                v[a] = cf{fa[n] * w, fb[n] * w};
+                const float w = s.window[n], xa = fa[n], xb = fb[n];
+                const float pa = xa * w, pb = xb * w;
+                ea2 = fmaf(xa, xa, ea2);
+                eb2 = fmaf(xb, xb, eb2);
+                wa2 = fmaf(pa, pa, wa2);
+                wb2 = fmaf(pb, pb, wb2);
+                v[a] = cf{pa, pb};
             }
-            fft2048_pass1(lt, v, tw, s.bufA[g]);
-        }
-        named_barrier(1 + g, FFT_THREADS);
-        fft2048_pass2(lt, tw, s.bufA[g], s.bufB[g]);
-        named_barrier(1 + g, FFT_THREADS);
-        fft2048_pass3(lt, s.bufB[g], s.bufA[g]);
-        named_barrier(1 + g, FFT_THREADS);
-
-        {   // split the packed spectrum: X1 = (Z[k] + conj Z[N-k]) / 2, X2 = (Z[k] - conj Z[N-k]) / 2i
-            const cf* Z = s.bufA[g];
+            ea2 = warp_sum(ea2);
+            eb2 = warp_sum(eb2);
+            wa2 = warp_sum(wa2);
+            wb2 = warp_sum(wb2);
+            if (lane == 0) *reinterpret_cast<float4*>(s.part[g][gw]) = make_float4(ea2, eb2, wa2, wb2);
+            if (round == N_ROUNDS - 1) {
+                // last read of this tile's samples is behind every thread: request the next tile's samples now,
+                // so their DRAM latency hides behind the rest of this tile (passes 2-3, split, stores, mel)
+                __syncthreads();
+                prefetched = false;
+                const long long nt = tile + gridDim.x;
+                if (nt < n_tiles) {
+                    const int nclip = static_cast<int>(nt / tiles_per_clip);
+                    const int nt0 = static_cast<int>(nt - static_cast<long long>(nclip) * tiles_per_clip) * TILE_F;
+                    const float* nyc = p.y + static_cast<long long>(nclip) * p.clip_stride;
+                    const long long ng0 = static_cast<long long>(nt0) * hop - p.pad;
+                    if (ng0 >= 0 && ng0 + n_buf <= N && ((ng0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(nyc) & 15) == 0)) {
+                        for (int i = tid * 4; i < n_buf; i += STFT_THREADS * 4) cp_async16(&s.samples[i], nyc + ng0 + i);
+                        prefetched = true;
+                    }
+                }
+                cp_async_commit();
+            } else {
+                named_barrier(1 + g, FFT_THREADS);
+            }
+            float4 tot = *reinterpret_cast<const float4*>(s.part[g][0]);
 #pragma unroll
-            for (int m = 0; m < 9; ++m) {
-                const int k = lt + 128 * m;
-                if (k <= FFT_N / 2) {
-                    const cf zk = Z[k];
-                    const cf zn = Z[(FFT_N - k) & (FFT_N - 1)];
-                    const float ar = zk.x + zn.x, ai = zk.y - zn.y;
-                    const float br = zk.y + zn.y, bi = zn.x - zk.x;
-                    s.stage[k * STAGE_PITCH + 2 * g] = 0.5f * sqrt_approx(fmaf(ar, ar, ai * ai));
-                    s.stage[k * STAGE_PITCH + 2 * g + 1] = 0.5f * sqrt_approx(fmaf(br, br, bi * bi));
+            for (int w4 = 1; w4 < 4; ++w4) {
+                const float4 q = *reinterpret_cast<const float4*>(s.part[g][w4]);
+                tot.x += q.x; tot.y += q.y; tot.z += q.z; tot.w += q.w;
+            }
+            if (p.rms != nullptr && lt < 2 && t0 + fa_idx + lt < T) {
+                p.rms[static_cast<long long>(clip) * p.rms_clip_stride + t0 + fa_idx + lt] =
+                    sqrtf((lt == 0 ? tot.x : tot.y) * (1.0f / FFT_N));
+            }
+            if (!do_fft) {  // RMS-only call (librosa.feature.rms)
+                named_barrier(1 + g, FFT_THREADS);  // s.part is rewritten next round
+                continue;
+            }
+            const int ea = pack_exponent(tot.z), eb = pack_exponent(tot.w);
+            {
+                const float sa = ldexpf(1.0f, -ea), sb = ldexpf(1.0f, -eb);
+#pragma unroll
+                for (int a = 0; a < 16; ++a) v[a] = cf{v[a].x * sa, v[a].y * sb};
+            }
+            fft2048_pass1(lt, v, tw, buf);
+            named_barrier(1 + g, FFT_THREADS);
+            fft2048_pass2_load(lt, buf, v);
+            named_barrier(1 + g, FFT_THREADS);
+            fft2048_pass2_store(lt, v, tw, buf);
+            named_barrier(1 + g, FFT_THREADS);
+            fft2048_pass3_load(lt, buf, v);
+            named_barrier(1 + g, FFT_THREADS);
+            fft2048_pass3_store(lt, v, buf);
+            named_barrier(1 + g, FFT_THREADS);
+            {   // split the packed spectrum: X_a = (Z[k] + conj Z[N-k]) / 2, X_b = (Z[k] - conj Z[N-k]) / 2i
+                // undo the packing scale (and the /2); an all-zero frame yields exact zeros
+                const float ua = tot.z > 0.f ? ldexpf(0.5f, ea) : 0.f, ub = tot.w > 0.f ? ldexpf(0.5f, eb) : 0.f;
+#pragma unroll
+                for (int m = 0; m < 9; ++m) {
+                    const int k = lt + 128 * m;
+                    if (k <= FFT_N / 2) {
+                        const cf zk = buf[k];
+                        const cf zn = buf[(FFT_N - k) & (FFT_N - 1)];
+                        const float ar = zk.x + zn.x, ai = zk.y - zn.y;
+                        const float br = zk.y + zn.y, bi = zn.x - zk.x;
+                        s.stage[k * STAGE_PITCH + fa_idx] = ua * sqrt_approx(fmaf(ar, ar, ai * ai));
+                        s.stage[k * STAGE_PITCH + fa_idx + 1] = ub * sqrt_approx(fmaf(br, br, bi * bi));
+                    }
                 }
             }
+            named_barrier(1 + g, FFT_THREADS);  // buf / s.part are rewritten by the next round
         }
+        if (!do_fft) continue;
         __syncthreads();
 
-        if (p.rms != nullptr && tid < TILE_F && t0 + tid < T) {
-            p.rms[static_cast<long long>(clip) * p.rms_clip_stride + t0 + tid] =
-                sqrtf((s.rms_part[2 * tid] + s.rms_part[2 * tid + 1]) * (1.0f / FFT_N));
-        }
-
-        const int f = lane & 7;
-        const bool f_ok = (t0 + f) < T;
-        if (p.mag != nullptr) {  // each warp store = 4 rows x 8 frames
-            float* __restrict__ mo = p.mag + static_cast<long long>(clip) * p.mag_clip_stride + t0 + f;
-            for (int k = warp * 4 + (lane >> 3); k < AEGIS_N_BINS; k += (STFT_THREADS / 32) * 4) {
-                if (f_ok) mo[static_cast<long long>(k) * p.mag_row_stride] = s.stage[k * STAGE_PITCH + f];
+        if (p.mag != nullptr) {
+            float* __restrict__ mo = p.mag + static_cast<long long>(clip) * p.mag_clip_stride + t0;
+            const bool vec_store = ((p.mag_row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(mo) & 15) == 0);
+            if (vec_store) {  // one float4 (4 frames) per lane, two lanes per spectrogram row
+                for (int idx = tid; idx < 2 * AEGIS_N_BINS; idx += STFT_THREADS) {
+                    const int k = idx >> 1, h = (idx & 1) * 4;
+                    const float* st = &s.stage[k * STAGE_PITCH + h];
+                    float* dst = mo + static_cast<long long>(k) * p.mag_row_stride + h;
+                    if (t0 + h + 3 < T) {
+                        *reinterpret_cast<float4*>(dst) = make_float4(st[0], st[1], st[2], st[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (t0 + h + j < T) dst[j] = st[j];
+                    }
+                }
+            } else {          // each warp store = 4 rows x 8 frames
+                const int f = lane & 7;
+                if (t0 + f < T) {
+                    for (int k = warp * 4 + (lane >> 3); k < AEGIS_N_BINS; k += (STFT_THREADS / 32) * 4)
+                        mo[static_cast<long long>(k) * p.mag_row_stride + f] = s.stage[k * STAGE_PITCH + f];
+                }
             }
         }
-        if (p.mel != nullptr) {  // sparse triangles over |X|^2
+        if (p.mel != nullptr) {  // sparse triangles over |X|^2; thread = (band pair, frame pair)
+            const int f = (tid >> 6) * 2;               // frames f, f+1
+            const int bp = tid & 63;
             float* __restrict__ me = p.mel + static_cast<long long>(clip) * p.mel_clip_stride + t0 + f;
+            const bool ok0 = (t0 + f) < T, ok1 = (t0 + f + 1) < T;
             float vmax = 0.f;
-            for (int band = tid >> 3; band < p.n_mels; band += STFT_THREADS / 8) {
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const int band = side == 0 ? bp : (2 * 64 - 1 - bp);
+                if (band >= p.n_mels) continue;
                 const int ks = __ldg(p.mel_start + band), len = __ldg(p.mel_len + band);
-                const float* __restrict__ w = p.mel_w + __ldg(p.mel_off + band);
-                float acc = 0.f;
+                const float* w = s.melw + __ldg(p.mel_off + band);
+                const float* st = &s.stage[ks * STAGE_PITCH + f];
+                float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
                 for (int i = 0; i < len; ++i) {
-                    const float m = s.stage[(ks + i) * STAGE_PITCH + f];
-                    acc = fmaf(__ldg(w + i), m * m, acc);
+                    const float wi = w[i];
+                    const float m0 = st[i * STAGE_PITCH], m1 = st[i * STAGE_PITCH + 1];
+                    acc0 = fmaf(wi, m0 * m0, acc0);
+                    acc1 = fmaf(wi, m1 * m1, acc1);
                 }
-                if (f_ok) {
-                    me[static_cast<long long>(band) * p.mel_row_stride] = acc;
-                    vmax = fmaxf(vmax, acc);
-                }
+                float* row = me + static_cast<long long>(band) * p.mel_row_stride;
+                if (ok0) { row[0] = acc0; vmax = fmaxf(vmax, acc0); }
+                if (ok1) { row[1] = acc1; vmax = fmaxf(vmax, acc1); }
             }
             if (p.mel_max != nullptr) {
                 vmax = warp_max(vmax);
@@ -173,10 +263,12 @@ extern "C" int aegis_stft_fused(const aegis_stft_params* p, void* stream) {
     AEGIS_REQUIRE(p->hop >= 4 && p->hop <= MAX_HOP && p->hop % 4 == 0,
                   "aegis_stft_fused: hop=%d unsupported (4..512, multiple of 4)", p->hop);
     AEGIS_REQUIRE(p->n_clips >= 0 && p->n_frames >= 0 && p->n_samples >= 0, "aegis_stft_fused: negative size");
+    AEGIS_REQUIRE(p->pad >= 0 && p->pad % 4 == 0, "aegis_stft_fused: pad must be a non-negative multiple of 4");
     AEGIS_REQUIRE(p->mag == nullptr || p->mag_row_stride >= p->n_frames, "aegis_stft_fused: mag_row_stride < n_frames");
     if (p->mel != nullptr) {
-        AEGIS_REQUIRE(p->mel_start && p->mel_len && p->mel_off && p->mel_w && p->n_mels > 0,
-                      "aegis_stft_fused: mel tables missing");
+        AEGIS_REQUIRE(p->mel_start && p->mel_len && p->mel_off && p->mel_w && p->n_mels > 0 && p->n_mels <= 128,
+                      "aegis_stft_fused: mel tables missing or n_mels > 128");
+        AEGIS_REQUIRE(p->mel_nnz > 0 && p->mel_nnz <= MEL_NNZ_MAX, "aegis_stft_fused: mel_nnz=%d exceeds %d", p->mel_nnz, MEL_NNZ_MAX);
         AEGIS_REQUIRE(p->mel_row_stride >= p->n_frames, "aegis_stft_fused: mel_row_stride < n_frames");
     }
     if (p->n_clips == 0 || p->n_frames == 0) return 0;
@@ -190,7 +282,11 @@ extern "C" int aegis_stft_fused(const aegis_stft_params* p, void* stream) {
             return 2;
         }
     }
-    const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_fused_kernel, STFT_THREADS, sizeof(StftSmem)) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    const long long max_grid = static_cast<long long>(sm_count()) * per_sm;
+    const int grid = static_cast<int>(n_tiles < max_grid ? n_tiles : max_grid);
     stft_fused_kernel<<<grid, STFT_THREADS, sizeof(StftSmem), static_cast<cudaStream_t>(stream)>>>(*p, tiles_per_clip, n_tiles);
     return check_launch("aegis_stft_fused");
 }

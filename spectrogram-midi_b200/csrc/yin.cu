@@ -25,6 +25,7 @@ constexpr int YIN_MAX_LAGS = 1024;     // lags 0 .. max_period, max_period <= 10
 constexpr int YIN_MAX_TROUGHS = 512;
 
 struct YinSmem {
+    float en_part[2][4];  // per-warp partial frame energies (packing scale)
     float samples[FFT_N + YIN_MAX_HOP];
     cf bufA[BUFA_SIZE];   // bufA+bufB are reused as YinScratchE once the transforms are done
     cf bufB[BUFB_SIZE];
@@ -90,16 +91,39 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
         }
         __syncthreads();
 
+        // The two frames' product spectra share the inverse transform, so (as in the STFT kernel) each
+        // frame is scaled by an exact power of two ~ 1/||frame|| first: a quiet frame next to a loud one
+        // keeps an autocorrelation error relative to its OWN energy.  acf = acf_scaled * 4^e.
+#pragma unroll
+        for (int fr = 0; fr < 2; ++fr) {
+            const float* f = s.samples + fr * hop;
+            float acc = 0.f;
+#pragma unroll
+            for (int a = 0; a < 16; ++a) acc = fmaf(f[lt + 128 * a], f[lt + 128 * a], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) s.en_part[fr][warp] = acc;
+        }
+        __syncthreads();
+        int fexp[2];
+        bool fzero[2];
+#pragma unroll
+        for (int fr = 0; fr < 2; ++fr) {
+            const float en = (s.en_part[fr][0] + s.en_part[fr][1]) + (s.en_part[fr][2] + s.en_part[fr][3]);
+            fexp[fr] = (en > 0.f) ? (ilogbf(en) >> 1) : 0;
+            fzero[fr] = !(en > 0.f);  // digital silence: acf must be exactly 0, not the partner's noise
+        }
+
         // ---- spectra: Z = FFT(frame + i*rev), rev[n] = frame[1024-n] (n < 1024), 0 otherwise
 #pragma unroll 1
         for (int fr = 0; fr < 2; ++fr) {
             const float* f = s.samples + fr * hop;
             {
+                const float sc = ldexpf(1.0f, -fexp[fr]);
                 cf v[16];
 #pragma unroll
                 for (int a = 0; a < 16; ++a) {
                     const int n = lt + 128 * a;
-                    v[a] = cf{f[n], (a < 8) ? f[FFT_N / 2 - n] : 0.f};
+                    v[a] = cf{f[n] * sc, (a < 8) ? f[FFT_N / 2 - n] * sc : 0.f};
                 }
                 fft2048_pass1(lt, v, tw, s.bufA);
             }
@@ -152,6 +176,7 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
             for (int v = 0; v < u; ++v) base += se.tot[fr][v];
             float e0f = static_cast<float>(e0);
             if (fabsf(e0f) < 1e-6f) e0f = 0.f;
+            const float acf_scale = ldexpf(1.0f / (4.0f * FFT_N), 2 * fexp[fr]);
             run = 0.0;
             double dsum = 0.0;
             for (int tau = lo; tau < hi; ++tau) {
@@ -159,8 +184,8 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
                 float e = static_cast<float>(base + run);
                 if (fabsf(e) < 1e-6f) e = 0.f;
                 const cf F = s.Z[FFT_N / 2 + tau];
-                float acf = (fr == 0 ? F.x : -F.y) * (1.0f / (4.0f * FFT_N));
-                if (fabsf(acf) < 1e-6f) acf = 0.f;
+                float acf = (fr == 0 ? F.x : -F.y) * acf_scale;
+                if (fabsf(acf) < 1e-6f || fzero[fr]) acf = 0.f;
                 const float dv = (e0f + e) - 2.0f * acf;
                 se.d[fr][tau] = dv;
                 dsum += static_cast<double>(dv);
@@ -175,7 +200,10 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
                 run += static_cast<double>(se.d[fr][tau]);
                 if (tau >= minp) {
                     const double cm = static_cast<double>(static_cast<float>(base + run)) / static_cast<double>(tau);
-                    se.yin[fr][tau - minp] = static_cast<double>(se.d[fr][tau]) / (cm + DBL_MIN);
+                    const double yv = static_cast<double>(se.d[fr][tau]) / (cm + DBL_MIN);
+                    se.yin[fr][tau - minp] = yv;
+                    if (p.cmnd_out != nullptr && t0 + fr < T)
+                        p.cmnd_out[(static_cast<long long>(clip) * T + t0 + fr) * L + (tau - minp)] = yv;
                 }
             }
         }

@@ -1,0 +1,253 @@
+"""Multi-GPU execution of the hot path: one process per GPU, ``torch.distributed`` (NCCL) plumbing.
+
+Two modes:
+
+* **by clip** (BASELINE cfg2/3/5): clips are independent -- every ``ref=np.max`` is per clip -- so each
+  rank analyses ``batch.shard_range(n_clips, rank, world)`` and nothing crosses NVLink on the data
+  path.  ``gather_counts`` is an optional reporting collective.
+* **one long clip in overlapping time windows** (BASELINE cfg4).  The reference's Turbo Mode
+  (aegis_engine.py:183-216) cuts the clip into independent chunks and concatenates, which differs
+  from the serial result at every seam; the target here is the *serial* result.  Frame-local stages
+  (STFT, mel, RMS, YIN candidates) are computed for the rank's own frame range from a window of audio
+  with a +-1024-sample halo; the couplings that remain are
+    1. ``power_to_db(ref=np.max)``: the global mel-power maximum  -> ``all_reduce(MAX)`` of one float;
+    2. the HMM is one chain over all frames.  ``mode="exact"`` all-gathers the sparse observations
+       (a few hundred bytes per frame) and decodes the single chain (identical to one GPU);
+       ``mode="windowed"`` decodes each rank's frames plus a burn-in margin on both sides and keeps the
+       interior (faster; equal to the serial path wherever the paths have coalesced, which the tests
+       measure);
+    3. results are all-gathered as ragged per-frame arrays / note-event records.
+  The collectives are latency-sized (bytes to a few MB); NCCL over NVSwitch is used as is.
+
+The per-window analysis is injected (``analyze``) so the host-side planning / stitching / collectives are
+testable on CPU with the gloo backend; the default is the CUDA path and there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .batch import shard_range
+
+N_FFT = 2048
+
+
+# ------------------------------------------------------------------------------------------------
+# process-group helpers
+# ------------------------------------------------------------------------------------------------
+def init_from_env(backend: Optional[str] = None) -> tuple:
+    """(rank, world, local_rank); initialises the default group when launched by torchrun."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    return rank, world, local_rank
+
+
+def _world(group=None) -> tuple:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def all_reduce_max(t: torch.Tensor, group=None) -> torch.Tensor:
+    if _world(group)[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t
+
+
+def all_gather_ragged(t: torch.Tensor, group=None) -> List[torch.Tensor]:
+    """All-gather tensors whose first dimension differs per rank (padded to the maximum, then trimmed)."""
+    rank, world = _world(group)
+    if world == 1:
+        return [t]
+    if t.dtype in (torch.int16, torch.bool) or t.dtype == getattr(torch, "uint16", None):
+        # neither NCCL nor gloo has a 16-bit integer type: ship the bytes
+        shape, dtype = tuple(t.shape[1:]), t.dtype
+        row_bytes = int(np.prod(shape, dtype=np.int64)) * t.element_size()
+        raw = t.contiguous().view(torch.uint8).reshape(t.shape[0], row_bytes)
+        return [p.contiguous().view(dtype).reshape((p.shape[0],) + shape) for p in all_gather_ragged(raw, group)]
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s) for s in sizes]
+    m = max(sizes)
+    padded = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    padded[: t.shape[0]] = t
+    out = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(out, padded, group=group)
+    return [o[:s] for o, s in zip(out, sizes)]
+
+
+def gather_counts(local_count: int, device=None, group=None) -> List[int]:
+    """Per-rank counts (e.g. clips analysed, events found) for reporting."""
+    t = torch.tensor([local_count], dtype=torch.int64, device=device)
+    return [int(x[0]) for x in all_gather_ragged(t, group)]
+
+
+EVENT_DTYPE = np.dtype([("note", "<i2"), ("start", "<i4"), ("end", "<i4"), ("velocity", "u1"), ("track", "u1"),
+                        ("technique", "u1"), ("_pad", "u1"), ("confidence", "<f4"), ("slope", "<f4")])
+
+
+def gather_note_events(events: np.ndarray, device=None, group=None) -> np.ndarray:
+    """All-gather note-event records (``EVENT_DTYPE``, 24 B each) from every rank, in rank order."""
+    events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+    raw = torch.from_numpy(events.view(np.uint8).reshape(len(events), EVENT_DTYPE.itemsize).copy())
+    if device is not None:
+        raw = raw.to(device)
+    parts = all_gather_ragged(raw, group)
+    flat = torch.cat(parts).cpu().numpy()
+    return flat.reshape(-1).view(EVENT_DTYPE) if flat.size else np.zeros(0, EVENT_DTYPE)
+
+
+# ------------------------------------------------------------------------------------------------
+# window planning for one long clip
+# ------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Window:
+    own_lo: int      # frames this rank contributes: [own_lo, own_hi)
+    own_hi: int
+    win_lo: int      # frames it analyses (own range + burn-in margin): [win_lo, win_hi)
+    win_hi: int
+    s0: int          # audio slice [s0, s1) handed to the kernels
+    s1: int
+    pad: int         # virtual zeros before s0 (non-zero only at the clip start)
+
+
+def plan_windows(n_samples: int, hop_length: int, world: int, burn_frames: int) -> List[Window]:
+    n_frames = 1 + n_samples // hop_length
+    out = []
+    for r in range(world):
+        own = shard_range(n_frames, r, world)
+        lo, hi = max(0, own.start - burn_frames), min(n_frames, own.stop + burn_frames)
+        first = lo * hop_length - N_FFT // 2
+        s0 = max(0, first)
+        s1 = min(n_samples, (hi - 1) * hop_length + N_FFT // 2) if hi > lo else s0
+        out.append(Window(own.start, own.stop, lo, hi, s0, max(s0, s1), s0 - first))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# per-window analysis back end (CUDA by default; injectable so the host logic is testable with gloo)
+# ------------------------------------------------------------------------------------------------
+class CudaBackend:
+    """The product path: every call goes to the sm_100a kernels.  No CPU fallback."""
+
+    def __init__(self, *, sr, hop_length, fmin, fmax, rake_sensitivity, device=None):
+        from . import tables
+
+        self.sr, self.hop, self.ratio = sr, hop_length, rake_sensitivity
+        self.cfg = tables.pyin_config(float(sr), int(hop_length), float(fmin), float(fmax))
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def features(self, y_win: np.ndarray, w: "Window") -> dict:
+        """mel power / clip-local mel max / RMS / sparse pYIN observations for frames [win_lo, win_hi)."""
+        from . import core
+
+        n = w.win_hi - w.win_lo
+        yd = torch.from_numpy(np.ascontiguousarray(y_win, dtype=np.float32)).to(self.device)[None]
+        feat = core.stft_features(yd, sr=self.sr, hop_length=self.hop, want_mag=False, want_mel=True, want_rms=True,
+                                  pad=w.pad, n_frames=n)
+        obs = core.yin_candidates(yd, self.cfg, pad=w.pad, n_frames=n)
+        mc = obs["max_cand"]
+        return {"mel": feat["mel"], "mel_max": feat["mel_max"], "rms": feat["rms"][0],
+                "cand_bin": obs["cand_bin"].view(n, mc), "cand_prob": obs["cand_prob"].view(n, mc),
+                "cand_count": obs["cand_count"], "voiced_prob": obs["voiced_prob"][0]}
+
+    def rake_mask(self, feat: dict, mel_max: torch.Tensor) -> torch.Tensor:
+        from . import core
+
+        post = core.mel_post(feat["mel"], mel_max, sr=self.sr, hop_length=self.hop, rake_ratio=self.ratio,
+                             want_sdb=False, want_rake=True)
+        return post["rake_mask"][0]
+
+    def decode(self, cand_bin, cand_prob, cand_count, voiced_prob) -> dict:
+        """Viterbi over one chain of sparse observations -> f0 (NaN unvoiced), voiced_flag."""
+        from . import core
+
+        T, mc = cand_bin.shape
+        obs = dict(cand_bin=cand_bin.contiguous(), cand_prob=cand_prob.contiguous(), cand_count=cand_count.contiguous(),
+                   voiced_prob=voiced_prob[None].contiguous(), n_frames=T, max_cand=mc)
+        dec = core.viterbi_decode(obs, self.cfg, 1)
+        return {"f0": dec["f0"][0], "voiced_flag": dec["voiced_flag"][0]}
+
+
+MIN_MARGIN_FRAMES = 32  # the rake run-length gate looks at up to 30 neighbouring columns
+
+
+def analyze_long_clip(y, *, sr: float, hop_length: int = 512, fmin: Optional[float] = None, fmax: Optional[float] = None,
+                      rake_sensitivity: float = 0.6, mode: str = "exact", burn_seconds: float = 2.0, group=None,
+                      backend=None) -> dict:
+    """Perception arrays of ONE long clip computed by all ranks of ``group`` (each rank can read the clip,
+    or at least its own window, from host memory).  Every rank returns the full-length result:
+    ``rake_mask, f0 (NaN unvoiced), voiced_flag, voiced_probs, rms`` as numpy arrays (aegis_engine.py:72-75).
+    """
+    if mode not in ("exact", "windowed"):
+        raise ValueError("mode must be 'exact' or 'windowed'")
+    rank, world = _world(group)
+    if backend is None:
+        from .batch import C6, E2
+
+        backend = CudaBackend(sr=sr, hop_length=hop_length, fmin=E2 if fmin is None else fmin,
+                              fmax=C6 if fmax is None else fmax, rake_sensitivity=rake_sensitivity)
+    n_samples = int(y.shape[-1])
+    burn = int(round(burn_seconds * sr / hop_length)) if mode == "windowed" else 0
+    w = plan_windows(n_samples, hop_length, world, max(burn, MIN_MARGIN_FRAMES))[rank]
+    feat = backend.features(np.asarray(y[w.s0 : w.s1], dtype=np.float32), w)
+
+    # coupling 1: power_to_db(ref=np.max) needs the clip-global maximum of the mel power
+    mel_max = all_reduce_max(feat["mel_max"].clone(), group)
+    rake = backend.rake_mask(feat, mel_max)
+    a, b = w.own_lo - w.win_lo, w.own_hi - w.win_lo
+    own = {"rms": feat["rms"][a:b], "rake_mask": rake[a:b], "voiced_probs": feat["voiced_prob"][a:b]}
+
+    if mode == "windowed":
+        # coupling 2, approximate: decode own frames + burn-in margin, keep the interior
+        dec = backend.decode(feat["cand_bin"], feat["cand_prob"], feat["cand_count"], feat["voiced_prob"])
+        own["f0"], own["voiced_flag"] = dec["f0"][a:b], dec["voiced_flag"][a:b]
+        full = {k: torch.cat(all_gather_ragged(v.contiguous(), group)) for k, v in own.items()}
+    else:
+        # coupling 2, exact: all-gather the sparse observations and decode the single chain
+        for k in ("cand_bin", "cand_prob", "cand_count"):
+            own[k] = feat[k][a:b]
+        full = {k: torch.cat(all_gather_ragged(v.contiguous(), group)) for k, v in own.items()}
+        dec = backend.decode(full.pop("cand_bin"), full.pop("cand_prob"), full.pop("cand_count"), full["voiced_probs"])
+        full["f0"], full["voiced_flag"] = dec["f0"], dec["voiced_flag"]
+    return {
+        "rake_mask": full["rake_mask"].cpu().numpy().astype(bool), "f0": full["f0"].cpu().numpy(),
+        "voiced_flag": full["voiced_flag"].cpu().numpy().astype(bool), "voiced_probs": full["voiced_probs"].cpu().numpy(),
+        "rms": full["rms"].cpu().numpy(),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# by-clip sharding
+# ------------------------------------------------------------------------------------------------
+def analyze_clips_sharded(load_clips: Callable[[Sequence[int]], torch.Tensor], n_clips: int, *, sr: float, group=None,
+                          **analyze_kwargs) -> dict:
+    """Each rank analyses its contiguous share of ``n_clips`` clips (``load_clips(indices)`` returns the CUDA
+    batch for those clip indices).  No collective touches the data path; the per-rank clip counts are gathered
+    for reporting only."""
+    from . import batch
+
+    rank, world = _world(group)
+    mine = shard_range(n_clips, rank, world)
+    y = load_clips(list(mine))
+    res = batch.analyze_batch(y, sr=sr, **analyze_kwargs) if len(mine) else {}
+    res["clip_indices"] = list(mine)
+    res["clips_per_rank"] = gather_counts(len(mine), device=y.device if len(mine) else None, group=group)
+    return res

@@ -117,6 +117,7 @@ class SparseMel:
     offset: np.ndarray  # int32 [n_mels] into weights
     weights: np.ndarray  # float32 [nnz]
     max_len: int
+    weights_t: np.ndarray  # float32 [max_len, n_mels]: weight i of every triangle, band-minor
 
 
 @functools.lru_cache(maxsize=None)
@@ -136,7 +137,11 @@ def sparse_mel(sr: float, n_fft: int = N_FFT, n_mels: int = 128) -> SparseMel:
         offset[b] = pos
         pos += int(length[b])
     weights = np.concatenate(chunks).astype(np.float32) if chunks else np.zeros(1, np.float32)
-    return SparseMel(n_mels, start, length, offset, weights, int(length.max()))
+    max_len = int(length.max())
+    wt = np.zeros((max(max_len, 1), n_mels), np.float32)
+    for b in range(n_mels):
+        wt[: length[b], b] = fb[b, start[b] : start[b] + length[b]]
+    return SparseMel(n_mels, start, length, offset, weights, max_len, wt)
 
 
 # ------------------------------------------------------------------------------------------
