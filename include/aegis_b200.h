@@ -61,12 +61,8 @@ typedef struct {
     int64_t mel_clip_stride;
     int32_t mel_row_stride;
     int32_t _reserved0;
-    const int32_t* mel_start;  /* [n_mels] first FFT bin of each triangle */
-    const int32_t* mel_len;    /* [n_mels] number of non-zero weights */
-    const int32_t* mel_off;    /* [n_mels] offset of each triangle in mel_w */
-    const float* mel_w;        /* [mel_nnz] packed non-zero triangle weights (staged in shared memory) */
-    int32_t mel_nnz;           /* <= 2304 */
-    int32_t _reserved1;
+    const int32_t* mel_seg_start; /* [n_mels + 2]: FFT bins [s[j], s[j+1]) lie between mel band edges j and j+1 */
+    const float* mel_rise_fall;   /* [1025][2]: weight of bin k in band seg(k) (rising side), in band seg(k)-1 (falling) */
     float* mel_max;            /* [n_clips] or NULL */
     float* rms;                /* [n_clips][rms_clip_stride] or NULL */
     int64_t rms_clip_stride;

@@ -28,7 +28,7 @@ class StftParams(C.Structure):
         ("pad", i32), ("n_frames", i32), ("window", _ptr), ("twiddle", _ptr),
         ("mag", _ptr), ("mag_clip_stride", i64), ("mag_row_stride", i32), ("n_mels", i32),
         ("mel", _ptr), ("mel_clip_stride", i64), ("mel_row_stride", i32), ("_reserved0", i32),
-        ("mel_start", _ptr), ("mel_len", _ptr), ("mel_off", _ptr), ("mel_w", _ptr), ("mel_nnz", i32), ("_reserved1", i32),
+        ("mel_seg_start", _ptr), ("mel_rise_fall", _ptr),
         ("mel_max", _ptr), ("rms", _ptr), ("rms_clip_stride", i64),
     ]
 

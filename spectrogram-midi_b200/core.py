@@ -106,11 +106,8 @@ def stft_features(y: torch.Tensor, *, sr: Optional[float] = None, hop_length: in
             raise ValueError("sr is required for the mel projection")
         sm = tables.sparse_mel(float(sr), N_FFT, n_mels)
         key = ("mel", float(sr), n_mels)
-        P.mel_start = _dev_tensor(key + ("s",), dev, lambda: sm.start).data_ptr()
-        P.mel_len = _dev_tensor(key + ("l",), dev, lambda: sm.length).data_ptr()
-        P.mel_off = _dev_tensor(key + ("o",), dev, lambda: sm.offset).data_ptr()
-        P.mel_w = _dev_tensor(key + ("w",), dev, lambda: sm.weights).data_ptr()
-        P.mel_nnz = int(sm.weights.size)
+        P.mel_seg_start = _dev_tensor(key + ("seg",), dev, lambda: sm.seg_start).data_ptr()
+        P.mel_rise_fall = _dev_tensor(key + ("rf",), dev, lambda: sm.rise_fall).data_ptr()
         mel = torch.empty((n_clips, n_mels, T), dtype=torch.float32, device=dev)
         mel_max = torch.zeros((n_clips,), dtype=torch.float32, device=dev)
         P.n_mels = n_mels

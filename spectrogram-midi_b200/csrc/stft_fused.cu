@@ -17,8 +17,8 @@
 //      The three radix passes exchange through ONE shared buffer per group (in place).
 //   3. X_a[k], X_b[k] are separated from Z[k], conj(Z[N-k]); magnitudes go to an [1025][8] stage
 //   4. the stage is written out in librosa's [1025, T] layout (float4 per half row when the row
-//      stride allows, else 8 scalar lanes per row); mel triangles and the clip maximum are taken
-//      from the stage with each thread owning a long + a short triangle (bands b and 127-b).
+//      stride allows, else 8 scalar lanes per row); the mel projection reads each stage bin once (every
+//      FFT bin lies in at most two triangles: rise/fall partial sums per band-edge segment).
 // HBM traffic per frame: hop*4 B read (+ halo, L2-served) and 1025*4 B written.
 #include "common.cuh"
 #include "fft2048.cuh"
@@ -31,7 +31,7 @@ constexpr int STFT_GROUPS = STFT_THREADS / FFT_THREADS;  // 2
 constexpr int MAX_HOP = 512;
 constexpr int SAMPLES_MAX = (TILE_F - 1) * MAX_HOP + FFT_N;  // 5632
 constexpr int STAGE_PITCH = TILE_F + 1;
-constexpr int MEL_NNZ_MAX = 2304;   // packed triangle weights kept in shared memory (2050 for 128 Slaney bands)
+constexpr int MEL_MAX = 128;
 
 struct StftSmem {
     float samples[SAMPLES_MAX];
@@ -39,9 +39,12 @@ struct StftSmem {
     float part[STFT_GROUPS][4][4];   // per warp: sum x_a^2, x_b^2, (w x_a)^2, (w x_b)^2 (float4 rows: keep 16 B aligned)
     cf buf[STFT_GROUPS][BUFA_SIZE];
     float stage[AEGIS_N_BINS * STAGE_PITCH];
-    float melw[MEL_NNZ_MAX];         // with ~205 KB of the SM carved out as shared memory only ~20 KB of L1 is left:
-                                     // weights read through L1 would thrash, so they live here
+    // mel tables live in shared memory: with ~220 KB of the SM carved out only a few KB of L1 are left, so
+    // weights read through L1 would thrash
+    float2 mel_rf[AEGIS_N_BINS];     // (rise, fall) weight of every FFT bin
+    int mel_seg[MEL_MAX + 2];        // first bin of every segment between mel band edges
 };
+static_assert(2 * (MEL_MAX + 1) * TILE_F * sizeof(float) <= sizeof(cf) * BUFA_SIZE, "mel partial sums alias buf[0]");
 static_assert((SAMPLES_MAX * 4) % 16 == 0 && (FFT_N * 4) % 16 == 0, "part[] must stay 16-byte aligned");
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -66,8 +69,10 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
     const long long N = p.n_samples;
 
     for (int i = tid; i < FFT_N; i += STFT_THREADS) s.window[i] = p.window[i];
-    if (p.mel != nullptr)
-        for (int i = tid; i < p.mel_nnz; i += STFT_THREADS) s.melw[i] = p.mel_w[i];
+    if (p.mel != nullptr) {
+        for (int i = tid; i < AEGIS_N_BINS; i += STFT_THREADS) s.mel_rf[i] = reinterpret_cast<const float2*>(p.mel_rise_fall)[i];
+        for (int i = tid; i < p.n_mels + 2; i += STFT_THREADS) s.mel_seg[i] = p.mel_seg_start[i];
+    }
     FftTwiddles tw;
     fft2048_load_twiddles(lt, reinterpret_cast<const cf*>(p.twiddle), tw);
     const int n_buf = (TILE_F - 1) * hop + FFT_N;
@@ -221,30 +226,37 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
                 }
             }
         }
-        if (p.mel != nullptr) {  // sparse triangles over |X|^2; thread = (band pair, frame pair)
-            const int f = (tid >> 6) * 2;               // frames f, f+1
-            const int bp = tid & 63;
-            float* __restrict__ me = p.mel + static_cast<long long>(clip) * p.mel_clip_stride + t0 + f;
-            const bool ok0 = (t0 + f) < T, ok1 = (t0 + f + 1) < T;
-            float vmax = 0.f;
-#pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                const int band = side == 0 ? bp : (2 * 64 - 1 - bp);
-                if (band >= p.n_mels) continue;
-                const int ks = __ldg(p.mel_start + band), len = __ldg(p.mel_len + band);
-                const float* w = s.melw + __ldg(p.mel_off + band);
-                const float* st = &s.stage[ks * STAGE_PITCH + f];
-                float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 4
-                for (int i = 0; i < len; ++i) {
-                    const float wi = w[i];
-                    const float m0 = st[i * STAGE_PITCH], m1 = st[i * STAGE_PITCH + 1];
-                    acc0 = fmaf(wi, m0 * m0, acc0);
-                    acc1 = fmaf(wi, m1 * m1, acc1);
+        if (p.mel != nullptr) {
+            // mel[b] = sum_{k in seg b} rise[k] |X_k|^2 + sum_{k in seg b+1} fall[k] |X_k|^2  (each bin read once).
+            // lane = (frame, segment-in-quad): a warp reads 4 stage rows x 8 frames per step, near conflict free.
+            float* const rise = reinterpret_cast<float*>(s.buf[0]);          // [n_mels + 1][8], buf is free here
+            float* const fall = rise + (MEL_MAX + 1) * TILE_F;
+            {
+                const int f = lane & 7;
+                for (int j = warp * 4 + (lane >> 3); j <= p.n_mels; j += (STFT_THREADS / 32) * 4) {
+                    const int k0 = s.mel_seg[j], k1 = s.mel_seg[j + 1];
+                    float r = 0.f, fl = 0.f;
+                    for (int k = k0; k < k1; ++k) {
+                        const float m = s.stage[k * STAGE_PITCH + f];
+                        const float2 w = s.mel_rf[k];
+                        const float pw = m * m;
+                        r = fmaf(w.x, pw, r);
+                        fl = fmaf(w.y, pw, fl);
+                    }
+                    rise[j * TILE_F + f] = r;
+                    fall[j * TILE_F + f] = fl;
                 }
-                float* row = me + static_cast<long long>(band) * p.mel_row_stride;
-                if (ok0) { row[0] = acc0; vmax = fmaxf(vmax, acc0); }
-                if (ok1) { row[1] = acc1; vmax = fmaxf(vmax, acc1); }
+            }
+            __syncthreads();
+            float* __restrict__ me = p.mel + static_cast<long long>(clip) * p.mel_clip_stride + t0;
+            float vmax = 0.f;
+            for (int idx = tid; idx < p.n_mels * TILE_F; idx += STFT_THREADS) {
+                const int b = idx >> 3, f = idx & 7;
+                const float v = rise[b * TILE_F + f] + fall[(b + 1) * TILE_F + f];
+                if (t0 + f < T) {
+                    me[static_cast<long long>(b) * p.mel_row_stride + f] = v;
+                    vmax = fmaxf(vmax, v);
+                }
             }
             if (p.mel_max != nullptr) {
                 vmax = warp_max(vmax);
@@ -266,9 +278,8 @@ extern "C" int aegis_stft_fused(const aegis_stft_params* p, void* stream) {
     AEGIS_REQUIRE(p->pad >= 0 && p->pad % 4 == 0, "aegis_stft_fused: pad must be a non-negative multiple of 4");
     AEGIS_REQUIRE(p->mag == nullptr || p->mag_row_stride >= p->n_frames, "aegis_stft_fused: mag_row_stride < n_frames");
     if (p->mel != nullptr) {
-        AEGIS_REQUIRE(p->mel_start && p->mel_len && p->mel_off && p->mel_w && p->n_mels > 0 && p->n_mels <= 128,
+        AEGIS_REQUIRE(p->mel_seg_start && p->mel_rise_fall && p->n_mels > 0 && p->n_mels <= MEL_MAX,
                       "aegis_stft_fused: mel tables missing or n_mels > 128");
-        AEGIS_REQUIRE(p->mel_nnz > 0 && p->mel_nnz <= MEL_NNZ_MAX, "aegis_stft_fused: mel_nnz=%d exceeds %d", p->mel_nnz, MEL_NNZ_MAX);
         AEGIS_REQUIRE(p->mel_row_stride >= p->n_frames, "aegis_stft_fused: mel_row_stride < n_frames");
     }
     if (p->n_clips == 0 || p->n_frames == 0) return 0;

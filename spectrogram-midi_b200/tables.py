@@ -117,7 +117,8 @@ class SparseMel:
     offset: np.ndarray  # int32 [n_mels] into weights
     weights: np.ndarray  # float32 [nnz]
     max_len: int
-    weights_t: np.ndarray  # float32 [max_len, n_mels]: weight i of every triangle, band-minor
+    seg_start: np.ndarray  # int32 [n_mels + 2]: bins [seg_start[j], seg_start[j+1]) lie between band edges j and j+1
+    rise_fall: np.ndarray  # float32 [n_bins, 2]: weight of bin k in band seg(k) (rising side) and band seg(k)-1 (falling)
 
 
 @functools.lru_cache(maxsize=None)
@@ -138,10 +139,42 @@ def sparse_mel(sr: float, n_fft: int = N_FFT, n_mels: int = 128) -> SparseMel:
         pos += int(length[b])
     weights = np.concatenate(chunks).astype(np.float32) if chunks else np.zeros(1, np.float32)
     max_len = int(length.max())
-    wt = np.zeros((max(max_len, 1), n_mels), np.float32)
-    for b in range(n_mels):
-        wt[: length[b], b] = fb[b, start[b] : start[b] + length[b]]
-    return SparseMel(n_mels, start, length, offset, weights, max_len, wt)
+    # Every FFT bin lies in at most two triangles: the falling side of band j-1 and the rising side of
+    # band j, where j is the "segment" between band edges j and j+1.  mel[b] = sum_{k in seg b} rise[k] P[k]
+    # + sum_{k in seg b+1} fall[k] P[k]: each bin is read once.  Built from the dense basis and verified
+    # to reproduce it exactly.
+    n_bins = fb.shape[1]
+    edges_hz = _mel_to_hz(np.linspace(_hz_to_mel(0.0)[0], _hz_to_mel(sr / 2.0)[0], n_mels + 2))
+    bins_hz = np.fft.rfftfreq(n_fft, 1.0 / sr)
+    seg = np.clip(np.searchsorted(edges_hz, bins_hz, side="right") - 1, 0, n_mels)
+    rf = np.zeros((n_bins, 2), np.float32)
+    for k in range(n_bins):
+        nz = np.flatnonzero(fb[:, k])
+        if nz.size == 2:
+            seg[k] = nz[1]
+        elif nz.size == 1:
+            b = int(nz[0])
+            seg[k] = b if bins_hz[k] < edges_hz[b + 1] else b + 1
+        elif nz.size > 2:
+            raise RuntimeError("mel basis is not a partition of triangles (bin in more than two bands)")
+        j = int(seg[k])
+        if j < n_mels:
+            rf[k, 0] = fb[j, k]
+        if j >= 1:
+            rf[k, 1] = fb[j - 1, k]
+    if np.any(np.diff(seg) < 0):
+        raise RuntimeError("mel segments are not monotone in frequency")
+    check = np.zeros_like(fb)
+    for k in range(n_bins):
+        j = int(seg[k])
+        if j < n_mels:
+            check[j, k] = rf[k, 0]
+        if j >= 1:
+            check[j - 1, k] = rf[k, 1]
+    if not np.array_equal(check, fb):
+        raise RuntimeError("segment form of the mel basis does not reproduce the dense basis")
+    seg_start = np.searchsorted(seg, np.arange(n_mels + 2), side="left").astype(np.int32)
+    return SparseMel(n_mels, start, length, offset, weights, max_len, seg_start, np.ascontiguousarray(rf))
 
 
 # ------------------------------------------------------------------------------------------
