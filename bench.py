@@ -277,6 +277,15 @@ def run_gpu(args):
             b.synchronize()
             aux["pyin_E2_C6_audio_s_per_s"] = sub.shape[0] * CLIP_SECONDS / (a.elapsed_time(b) / 1e3)
             aux["pyin_clips"] = int(sub.shape[0])
+            # the whole perception phase of audio_to_midi (spectral + rake + pYIN + RMS + trend) on the same clips
+            for _ in range(2):
+                batch.analyze_batch(sub, sr=SR, with_onsets=True, with_trend=True)
+            torch.cuda.synchronize()
+            a.record()
+            batch.analyze_batch(sub, sr=SR, with_onsets=True, with_trend=True)
+            b.record()
+            b.synchronize()
+            aux["full_perception_audio_s_per_s"] = sub.shape[0] * CLIP_SECONDS / (a.elapsed_time(b) / 1e3)
         except Exception as e:  # pragma: no cover
             aux["pyin_error"] = str(e)[:200]
 

@@ -10,8 +10,10 @@
 //   * in-band sources (|b - b'| <= half_width, both voicings) are enumerated from the banded
 //     log-transition table; rows that differ in the last ulp (librosa's pairwise row sums) are
 //     kept as "variants", the few interior ones in shared memory, truncated edge rows in global;
-//   * out-of-band sources all carry log(tiny): their best is a leftmost-max prefix/suffix query
-//     (warp-shuffle scans over V, second level recomputed per warp), O(1) per destination.
+//   * out-of-band sources all carry log(tiny): only the block's leftmost global maximum can matter
+//     (see the kernel comment), one block-wide argmax per frame;
+//   * in-band sources are pruned in chunks of 8 with exact upper bounds, so a destination typically
+//     evaluates a few dozen of its 202 in-band candidates.
 // One CTA per clip, one thread per pitch bin (it owns the voiced and the unvoiced state of that
 // bin, so every V[b'] load feeds four candidates); sequential over frames with one barrier per
 // frame; V, scans and observations are ping-ponged in shared memory.  Back-pointers stream to
@@ -23,20 +25,21 @@
 namespace aegis {
 
 constexpr int VT_MAX_BINS = 512;
-constexpr int VT_HALO = 64;            // >= half_width
+constexpr int VT_HALO = 64;            // >= half_width + 8
 constexpr int VT_MAX_W = 2 * VT_HALO + 1;
 constexpr int VT_SMEM_VARIANTS = 6;
 constexpr int VT_MAX_WARPS = VT_MAX_BINS / 32;
+constexpr int VT_CHUNK = 8;            // sources are pruned in aligned chunks of 8 bins
+constexpr int VT_CHUNK_PAD = 8;        // chunk indices -8 .. (512/8 + 8)
+constexpr int VT_N_CHUNKS = VT_MAX_BINS / VT_CHUNK + 2 * VT_CHUNK_PAD;
 
 struct VitSmem {
-    double V[2][2][VT_MAX_BINS + 2 * VT_HALO];     // [ping][voicing][halo | bins | halo]
-    double pw_val[2][2][VT_MAX_BINS];              // within-warp leftmost prefix max
-    double sw_val[2][2][VT_MAX_BINS];              // within-warp leftmost suffix max
+    double V[2][2][VT_MAX_BINS + 2 * VT_HALO];     // [ping][voicing][halo | bins | halo], halo = -inf
+    double M[2][2][VT_N_CHUNKS];                   // max of V over each aligned chunk of 8 bins (-inf outside)
     double obs_lp[2][VT_MAX_BINS];                 // log(obs + tiny) of the voiced states
-    double lt[VT_SMEM_VARIANTS][2][VT_MAX_W];      // interior transition variants
-    double seg_val[2][2][VT_MAX_WARPS];            // per-warp leftmost max
-    short pw_arg[2][2][VT_MAX_BINS];
-    short sw_arg[2][2][VT_MAX_BINS];
+    double lt[VT_SMEM_VARIANTS][2][VT_MAX_W];      // interior transition variants [variant][same|switch][offset]
+    double ubr[2][VT_MAX_W + VT_CHUNK];            // max over ALL variants and over offsets q-7..q: chunk upper bound
+    double seg_val[2][2][VT_MAX_WARPS];            // per-warp leftmost max of V
     short seg_arg[2][2][VT_MAX_WARPS];
     unsigned char rowvar[VT_MAX_BINS + 2 * VT_HALO];
 };
@@ -46,17 +49,39 @@ struct VA {
     int a;
 };
 
-__device__ __forceinline__ VA shfl_va(VA x, int src) {
-    return VA{__shfl_sync(0xffffffffu, x.v, src), __shfl_sync(0xffffffffu, x.a, src)};
+// leftmost-max combine under a butterfly exchange: every lane ends with (max value, lowest index attaining it)
+__device__ __forceinline__ VA butterfly_leftmost(VA x, int mask) {
+    const double ov = __shfl_xor_sync(0xffffffffu, x.v, mask);
+    const int oa = __shfl_xor_sync(0xffffffffu, x.a, mask);
+    if (ov > x.v || (ov == x.v && oa < x.a)) { x.v = ov; x.a = oa; }
+    return x;
 }
 
-__global__ void __launch_bounds__(VT_MAX_BINS, 1)
+// HW: half width of the transition band (compile time so the loops unroll).  MAXT/MINB: the 441-bin
+// E2..C6 configuration runs 448-thread CTAs two per SM; wider pitch ranges use one 512-thread CTA.
+//
+// Exactness of the pruning (everything is float64, first-index argmax as in numpy):
+//  * Out-of-band sources of a voicing block all cost log(tiny).  Let g be the block's LEFTMOST global
+//    maximum.  If g lies inside the band its in-band candidate (>= V[g] - 14) beats every out-of-band
+//    candidate (<= V[g] - 708); otherwise g itself is the best out-of-band source of its side and the
+//    other side can at best tie with a higher index (or is strictly smaller).  So one block-wide
+//    leftmost argmax per frame replaces the prefix/suffix scans.
+//  * In-band sources are visited in aligned chunks of 8.  A chunk is skipped when
+//    chunk_max + max(lt over its offsets, over all row variants) is < L, the value of a real candidate
+//    (the destination's own bin), or <= the running best of lower-index sources: floating-point addition
+//    is monotone, so no source in the chunk can reach the maximum or win a tie.  Chunks that survive are
+//    evaluated exactly, in ascending source order with a strict >, voiced sources before unvoiced.
+template <int HW, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 viterbi_forward_kernel(const aegis_viterbi_params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     VitSmem& s = *reinterpret_cast<VitSmem*>(smem_raw);
     const int clip = blockIdx.x;
     const int b = threadIdx.x, lane = b & 31, warp = b >> 5;
-    const int n = p.n_pitch_bins, hw = p.half_width, W = 2 * hw + 1, T = p.n_frames;
+    constexpr int hw = HW, W = 2 * HW + 1;
+    constexpr int NCH = (W + 2 * (VT_CHUNK - 1) + VT_CHUNK - 1) / VT_CHUNK;  // chunks that can touch a band
+    static_assert(HW + VT_CHUNK <= VT_HALO, "halo too small");
+    const int n = p.n_pitch_bins, T = p.n_frames;
     const int n_warps = (n + 31) >> 5;
     const int nsv = min(p.n_interior_variants, VT_SMEM_VARIANTS);
     const double NEG_INF = -INFINITY;
@@ -65,6 +90,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
 
     // ---- one-time shared set-up
     for (int i = b; i < 2 * 2 * (VT_MAX_BINS + 2 * VT_HALO); i += blockDim.x) (&s.V[0][0][0])[i] = NEG_INF;
+    for (int i = b; i < 2 * 2 * VT_N_CHUNKS; i += blockDim.x) (&s.M[0][0][0])[i] = NEG_INF;
     for (int i = b; i < 2 * VT_MAX_BINS; i += blockDim.x) (&s.obs_lp[0][0])[i] = LOGTINY;
     for (int i = b; i < VT_MAX_BINS + 2 * VT_HALO; i += blockDim.x) {
         const int src = i - VT_HALO;
@@ -73,6 +99,17 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
     for (int i = b; i < nsv * 2 * W; i += blockDim.x) {
         const int var = i / (2 * W), rem = i - var * 2 * W;
         s.lt[var][rem / W][rem % W] = __ldg(p.lt_variants + i);
+    }
+    for (int i = b; i < 2 * (W + VT_CHUNK); i += blockDim.x) {  // ubr[sel][q] = max_{j<8, var} lt[var][sel][q-j]
+        const int sel = i / (W + VT_CHUNK), q = i - sel * (W + VT_CHUNK);
+        double m = NEG_INF;
+        for (int j = 0; j < VT_CHUNK; ++j) {
+            const int o = q - j;
+            if (o < 0 || o >= W) continue;
+            for (int var = 0; var < p.n_variants; ++var)
+                m = fmax(m, __ldg(p.lt_variants + (static_cast<long long>(var) * 2 + sel) * W + o));
+        }
+        s.ubr[sel][q] = m;
     }
     __syncthreads();
 
@@ -83,18 +120,21 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
     const double* __restrict__ vprob = p.voiced_prob + f0idx;
     unsigned short* __restrict__ bp_out = p.backptr + f0idx * (2 * n);
 
-    // scatter frame 0 observations
-    {
+    {   // scatter frame 0 observations
         const int cnt = min(__ldg(ccnt), p.max_cand);
         if (b < cnt) s.obs_lp[0][cbin[b]] = log(cprob[b] + DBL_MIN);
     }
     __syncthreads();
 
+    // table entry for (source row variant, same|switch, offset)
+    auto lt_at = [&](int var, int sel, int o) -> double {
+        return (var < nsv) ? s.lt[var][sel][o] : __ldg(p.lt_variants + (static_cast<long long>(var) * 2 + sel) * W + o);
+    };
+
     double vnew0 = NEG_INF, vnew1 = NEG_INF;   // this bin's voiced / unvoiced value
     for (int t = 0; t < T; ++t) {
         const int cur = t & 1, nxt = cur ^ 1;
-        // prefetch the next frame's sparse observation
-        int ncnt = 0, nbin = 0;
+        int ncnt = 0, nbin = 0;   // prefetch the next frame's sparse observation
         double nprob = 0.0;
         if (t + 1 < T) {
             ncnt = min(__ldg(ccnt + t + 1), p.max_cand);
@@ -115,116 +155,102 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
             vnew0 = lp_v + LOGTINY;               // log(p_init = 0 + tiny)
             vnew1 = lp_u + p.log_init_unvoiced;   // log(1/n + tiny)
         } else {
-            // second-level leftmost prefix / suffix maxima over warp segments (registers, per warp)
-            VA segp[2], segs[2];
+            // leftmost global maximum of each voicing block (second level of the argmax, per warp)
+            VA gmax[2];
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
-                VA x{NEG_INF, 0};
+                VA x{NEG_INF, 0x7fffffff};
                 if (lane < n_warps) x = VA{s.seg_val[cur][v][lane], s.seg_arg[cur][v][lane]};
-                VA pf = x, sf = x;
 #pragma unroll
-                for (int o = 1; o < VT_MAX_WARPS; o <<= 1) {
-                    const VA up = shfl_va(pf, max(lane - o, 0));
-                    if (lane >= o && up.v >= pf.v) pf = up;
-                    const VA dn = shfl_va(sf, min(lane + o, 31));
-                    if (lane + o < 32 && dn.v > sf.v) sf = dn;
-                }
-                segp[v] = pf;
-                segs[v] = sf;
-            }
-            // in-band candidates; [dest voicing][source voicing]
-            double best[2][2] = {{NEG_INF, NEG_INF}, {NEG_INF, NEG_INF}};
-            int arg[2][2] = {{0, 0}, {0, 0}};
-            if (live) {
-                const double* V0 = &s.V[cur][0][VT_HALO + b - hw];
-                const double* V1 = &s.V[cur][1][VT_HALO + b - hw];
-                const unsigned char* rv = &s.rowvar[VT_HALO + b - hw];
-                for (int d = 0; d < W; ++d) {
-                    const int var = rv[d];
-                    const int o = W - 1 - d;  // dest offset inside the source row's band
-                    double ls, lx;
-                    if (var < nsv) {
-                        ls = s.lt[var][0][o];
-                        lx = s.lt[var][1][o];
-                    } else {
-                        const double* g = p.lt_variants + static_cast<long long>(var) * 2 * W + o;
-                        ls = __ldg(g);
-                        lx = __ldg(g + W);
-                    }
-                    const double x0 = V0[d], x1 = V1[d];
-                    const int src = b - hw + d;
-                    double c;
-                    c = x0 + ls; if (c > best[0][0]) { best[0][0] = c; arg[0][0] = src; }
-                    c = x1 + lx; if (c > best[0][1]) { best[0][1] = c; arg[0][1] = src; }
-                    c = x0 + lx; if (c > best[1][0]) { best[1][0] = c; arg[1][0] = src; }
-                    c = x1 + ls; if (c > best[1][1]) { best[1][1] = c; arg[1][1] = src; }
-                }
-            }
-            // out-of-band competitors: every one costs log(tiny), whatever the voicing
-            const int lo_idx = b - hw - 1, hi_idx = b + hw + 1;
-#pragma unroll
-            for (int sv = 0; sv < 2; ++sv) {
-                const int li = min(max(lo_idx, 0), VT_MAX_BINS - 1), hi = min(max(hi_idx, 0), VT_MAX_BINS - 1);
-                VA lowq{s.pw_val[cur][sv][li], s.pw_arg[cur][sv][li]};
-                const VA pseg = shfl_va(segp[sv], max((li >> 5) - 1, 0));
-                if ((li >> 5) > 0 && pseg.v >= lowq.v) lowq = pseg;
-                VA highq{s.sw_val[cur][sv][hi], s.sw_arg[cur][sv][hi]};
-                const VA sseg = shfl_va(segs[sv], min((hi >> 5) + 1, 31));
-                if ((hi >> 5) + 1 < n_warps && sseg.v > highq.v) highq = sseg;
-                if (live) {
-#pragma unroll
-                    for (int dv = 0; dv < 2; ++dv) {
-                        double bv = best[dv][sv];
-                        int ba = arg[dv][sv];
-                        if (lo_idx >= 0) {  // lower indices than the band: wins ties
-                            const double c = lowq.v + LOGTINY;
-                            if (c >= bv) { bv = c; ba = lowq.a; }
-                        }
-                        if (hi_idx < n) {   // higher indices: must be strictly better
-                            const double c = highq.v + LOGTINY;
-                            if (c > bv) { bv = c; ba = highq.a; }
-                        }
-                        best[dv][sv] = bv;
-                        arg[dv][sv] = ba;
-                    }
-                }
+                for (int m = 1; m < 32; m <<= 1) x = butterfly_leftmost(x, m);
+                gmax[v] = x;
             }
             if (live) {
-                // voiced sources (indices < n) win ties against unvoiced sources
-                const bool u0 = best[0][1] > best[0][0], u1 = best[1][1] > best[1][0];
-                const double m0 = u0 ? best[0][1] : best[0][0], m1 = u1 ? best[1][1] : best[1][0];
-                const int k0 = u0 ? n + arg[0][1] : arg[0][0], k1 = u1 ? n + arg[1][1] : arg[1][0];
-                vnew0 = lp_v + m0;
-                vnew1 = lp_u + m1;
+                const double* Vc0 = &s.V[cur][0][VT_HALO];
+                const double* Vc1 = &s.V[cur][1][VT_HALO];
+                const unsigned char* rvc = &s.rowvar[VT_HALO];
+                // lower bounds: the candidates from this destination's own bin (offset hw)
+                double L0, L1;
+                {
+                    const int var = rvc[b];
+                    const double ls = lt_at(var, 0, hw), lx = lt_at(var, 1, hw);
+                    const double x0 = Vc0[b], x1 = Vc1[b];
+                    L0 = fmax(x0 + ls, x1 + lx);
+                    L1 = fmax(x0 + lx, x1 + ls);
+                }
+                double best0 = NEG_INF, best1 = NEG_INF;
+                int arg0 = 0, arg1 = 0;
+                const int cfirst = ((b - hw + 8 * VT_CHUNK_PAD) >> 3) - VT_CHUNK_PAD;  // floor((b - hw) / 8)
+#pragma unroll
+                for (int sv = 0; sv < 2; ++sv) {          // source block: 0 voiced, 1 unvoiced
+                    const double* Vc = sv == 0 ? Vc0 : Vc1;
+                    const int sel0 = sv, sel1 = 1 - sv;   // table for destination voiced / unvoiced
+                    const int kbase = sv * n;
+                    const bool g_low = gmax[sv].a < b - hw, g_high = gmax[sv].a > b + hw;
+                    const double oob = gmax[sv].v + LOGTINY;
+                    if (g_low) {   // lower indices than the band
+                        if (oob > best0) { best0 = oob; arg0 = kbase + gmax[sv].a; }
+                        if (oob > best1) { best1 = oob; arg1 = kbase + gmax[sv].a; }
+                    }
+#pragma unroll 1
+                    for (int ci = 0; ci < NCH; ++ci) {
+                        const int c = cfirst + ci;
+                        const int ohi = b + hw - VT_CHUNK * c;   // offset of the chunk's first source
+                        if (ohi < 0) break;
+                        const double m = s.M[cur][sv][c + VT_CHUNK_PAD];
+                        const double bd0 = m + s.ubr[sel0][ohi], bd1 = m + s.ubr[sel1][ohi];
+                        const bool need0 = (bd0 >= L0) && (bd0 > best0);
+                        const bool need1 = (bd1 >= L1) && (bd1 > best1);
+                        if (need0 || need1) {
+                            const int b0 = VT_CHUNK * c;
+#pragma unroll
+                            for (int j = 0; j < VT_CHUNK; ++j) {
+                                const int o = ohi - j;
+                                if (o >= 0 && o < W) {
+                                    const int var = rvc[b0 + j];
+                                    const double x = Vc[b0 + j];
+                                    if (need0) {
+                                        const double cc = x + lt_at(var, sel0, o);
+                                        if (cc > best0) { best0 = cc; arg0 = kbase + b0 + j; }
+                                    }
+                                    if (need1) {
+                                        const double cc = x + lt_at(var, sel1, o);
+                                        if (cc > best1) { best1 = cc; arg1 = kbase + b0 + j; }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (g_high) {  // higher indices than the band
+                        if (oob > best0) { best0 = oob; arg0 = kbase + gmax[sv].a; }
+                        if (oob > best1) { best1 = oob; arg1 = kbase + gmax[sv].a; }
+                    }
+                }
+                vnew0 = lp_v + best0;
+                vnew1 = lp_u + best1;
                 unsigned short* row = bp_out + static_cast<long long>(t) * (2 * n);
-                row[b] = static_cast<unsigned short>(k0);
-                row[n + b] = static_cast<unsigned short>(k1);
+                row[b] = static_cast<unsigned short>(arg0);
+                row[n + b] = static_cast<unsigned short>(arg1);
             }
         }
 
-        // publish V[t] and its within-warp leftmost prefix / suffix maxima
+        // publish V[t], its chunk maxima and the per-warp leftmost maxima
         if (live) {
             s.V[nxt][0][VT_HALO + b] = vnew0;
             s.V[nxt][1][VT_HALO + b] = vnew1;
         }
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
-            const VA x{live ? (v == 0 ? vnew0 : vnew1) : NEG_INF, b};
-            VA pf = x, sf = x;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const VA up = shfl_va(pf, max(lane - o, 0));
-                if (lane >= o && up.v >= pf.v) pf = up;
-                const VA dn = shfl_va(sf, min(lane + o, 31));
-                if (lane + o < 32 && dn.v > sf.v) sf = dn;
-            }
-            s.pw_val[nxt][v][b] = pf.v;
-            s.pw_arg[nxt][v][b] = static_cast<short>(pf.a);
-            s.sw_val[nxt][v][b] = sf.v;
-            s.sw_arg[nxt][v][b] = static_cast<short>(sf.a);
-            if (lane == 31) {
-                s.seg_val[nxt][v][warp] = pf.v;
-                s.seg_arg[nxt][v][warp] = static_cast<short>(pf.a);
+            VA x{live ? (v == 0 ? vnew0 : vnew1) : NEG_INF, b};
+            x = butterfly_leftmost(x, 1);
+            x = butterfly_leftmost(x, 2);
+            x = butterfly_leftmost(x, 4);
+            if ((lane & 7) == 0) s.M[nxt][v][(b >> 3) + VT_CHUNK_PAD] = x.v;
+            x = butterfly_leftmost(x, 8);
+            x = butterfly_leftmost(x, 16);
+            if (lane == 0) {
+                s.seg_val[nxt][v][warp] = x.v;
+                s.seg_arg[nxt][v][warp] = static_cast<short>(x.a);
             }
         }
         if (b < ncnt) s.obs_lp[nxt][nbin] = log(nprob + DBL_MIN);
@@ -268,7 +294,7 @@ extern "C" int aegis_viterbi(const aegis_viterbi_params* p, void* stream) {
     using namespace aegis;
     AEGIS_REQUIRE(p != nullptr, "aegis_viterbi: null params");
     AEGIS_REQUIRE(p->n_pitch_bins >= 2 && p->n_pitch_bins <= VT_MAX_BINS, "aegis_viterbi: n_pitch_bins=%d unsupported (<= %d)", p->n_pitch_bins, VT_MAX_BINS);
-    AEGIS_REQUIRE(p->half_width >= 1 && p->half_width <= VT_HALO, "aegis_viterbi: half_width=%d unsupported (<= %d)", p->half_width, VT_HALO);
+    AEGIS_REQUIRE(p->half_width >= 1 && p->half_width + VT_CHUNK <= VT_HALO, "aegis_viterbi: half_width=%d unsupported (<= %d)", p->half_width, VT_HALO);
     AEGIS_REQUIRE(p->n_variants >= 1 && p->n_variants <= 255 && p->n_interior_variants >= 1, "aegis_viterbi: bad variant counts");
     AEGIS_REQUIRE(p->max_cand >= 1 && p->max_cand <= p->n_pitch_bins, "aegis_viterbi: max_cand must be 1..n_pitch_bins");
     AEGIS_REQUIRE(p->cand_bin && p->cand_prob && p->cand_count && p->voiced_prob && p->lt_variants && p->row_variant && p->freqs,
@@ -276,13 +302,21 @@ extern "C" int aegis_viterbi(const aegis_viterbi_params* p, void* stream) {
     AEGIS_REQUIRE(p->backptr && p->final_value && p->states && p->f0 && p->voiced_flag, "aegis_viterbi: outputs missing");
     if (p->n_clips == 0 || p->n_frames == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaFuncSetAttribute(viterbi_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(VitSmem)));
+    const int block = ((p->n_pitch_bins + 31) / 32) * 32;
+    const bool small = block <= 448;
+    void (*kern)(const aegis_viterbi_params) = nullptr;
+    switch (p->half_width) {   // pYIN's band: 50 bins at 22.05 kHz / hop 512, 25 at 44.1 kHz
+        case 50: kern = small ? viterbi_forward_kernel<50, 448, 2> : viterbi_forward_kernel<50, 512, 1>; break;
+        case 25: kern = small ? viterbi_forward_kernel<25, 448, 2> : viterbi_forward_kernel<25, 512, 1>; break;
+        case 12: kern = small ? viterbi_forward_kernel<12, 448, 2> : viterbi_forward_kernel<12, 512, 1>; break;
+        default: set_error("aegis_viterbi: half_width=%d has no compiled kernel (12, 25, 50)", p->half_width); return 1;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(VitSmem)));
     if (e != cudaSuccess) {
         set_error("aegis_viterbi: cannot reserve %zu B shared memory: %s", sizeof(VitSmem), cudaGetErrorString(e));
         return 2;
     }
-    const int block = ((p->n_pitch_bins + 31) / 32) * 32;
-    viterbi_forward_kernel<<<p->n_clips, block, sizeof(VitSmem), st>>>(*p);
+    kern<<<p->n_clips, block, sizeof(VitSmem), st>>>(*p);
     if (int rc = check_launch("aegis_viterbi(forward)")) return rc;
     viterbi_backtrace_kernel<<<(p->n_clips + 63) / 64, 64, 0, st>>>(*p);
     return check_launch("aegis_viterbi(backtrace)");
