@@ -32,13 +32,17 @@ constexpr int VT_MAX_WARPS = VT_MAX_BINS / 32;
 constexpr int VT_CHUNK = 8;            // sources are pruned in aligned chunks of 8 bins
 constexpr int VT_CHUNK_PAD = 8;        // chunk indices -8 .. (512/8 + 8)
 constexpr int VT_N_CHUNKS = VT_MAX_BINS / VT_CHUNK + 2 * VT_CHUNK_PAD;
+#ifndef VT_SMALL_MINB
+#define VT_SMALL_MINB 2     // 448-thread CTAs per SM for the 441-bin configuration (3 spills and is slower)
+#endif
 
 struct VitSmem {
     double V[2][2][VT_MAX_BINS + 2 * VT_HALO];     // [ping][voicing][halo | bins | halo], halo = -inf
     double M[2][2][VT_N_CHUNKS];                   // max of V over each aligned chunk of 8 bins (-inf outside)
     double obs_lp[2][VT_MAX_BINS];                 // log(obs + tiny) of the voiced states
     double lt[VT_SMEM_VARIANTS][2][VT_MAX_W];      // interior transition variants [variant][same|switch][offset]
-    double ubr[2][VT_MAX_W + VT_CHUNK];            // max over ALL variants and over offsets q-7..q: chunk upper bound
+    double ubr[2][2][VT_MAX_W + VT_CHUNK];         // [interior rows only | all rows][same|switch][q]: max of lt over
+                                                   // the row variants and over offsets q-7..q (chunk upper bound)
     double seg_val[2][2][VT_MAX_WARPS];            // per-warp leftmost max of V
     short seg_arg[2][2][VT_MAX_WARPS];
     unsigned char rowvar[VT_MAX_BINS + 2 * VT_HALO];
@@ -100,16 +104,20 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
         const int var = i / (2 * W), rem = i - var * 2 * W;
         s.lt[var][rem / W][rem % W] = __ldg(p.lt_variants + i);
     }
-    for (int i = b; i < 2 * (W + VT_CHUNK); i += blockDim.x) {  // ubr[sel][q] = max_{j<8, var} lt[var][sel][q-j]
-        const int sel = i / (W + VT_CHUNK), q = i - sel * (W + VT_CHUNK);
+    // ubr[kind][sel][q] = max_{j<8, var} lt[var][sel][q-j]; kind 0 = interior row variants only (they differ in
+    // the last ulp, so the bound is tight), kind 1 = every variant (the truncated edge rows are up to log 2 larger)
+    for (int i = b; i < 2 * 2 * (W + VT_CHUNK); i += blockDim.x) {
+        const int kind = i / (2 * (W + VT_CHUNK)), r = i - kind * 2 * (W + VT_CHUNK);
+        const int sel = r / (W + VT_CHUNK), q = r - sel * (W + VT_CHUNK);
+        const int nv = kind == 0 ? p.n_interior_variants : p.n_variants;
         double m = NEG_INF;
         for (int j = 0; j < VT_CHUNK; ++j) {
             const int o = q - j;
             if (o < 0 || o >= W) continue;
-            for (int var = 0; var < p.n_variants; ++var)
+            for (int var = 0; var < nv; ++var)
                 m = fmax(m, __ldg(p.lt_variants + (static_cast<long long>(var) * 2 + sel) * W + o));
         }
-        s.ubr[sel][q] = m;
+        s.ubr[kind][sel][q] = m;
     }
     __syncthreads();
 
@@ -132,6 +140,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
     };
 
     double vnew0 = NEG_INF, vnew1 = NEG_INF;   // this bin's voiced / unvoiced value
+    int prev0 = b, prev1 = n + b;               // winning sources of the previous frame (temporal coherence)
     for (int t = 0; t < T; ++t) {
         const int cur = t & 1, nxt = cur ^ 1;
         int ncnt = 0, nbin = 0;   // prefetch the next frame's sparse observation
@@ -178,6 +187,14 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                     L0 = fmax(x0 + ls, x1 + lx);
                     L1 = fmax(x0 + lx, x1 + ls);
                 }
+                // ... and from the source that won in the previous frame (same voicing block, same bin): decoded
+                // paths move slowly, so this real candidate is usually (near) optimal and prunes almost every chunk
+                {
+                    const int sv0 = prev0 >= n, bs0 = prev0 - sv0 * n, o0 = b - bs0 + hw;
+                    if (o0 >= 0 && o0 < W) L0 = fmax(L0, (sv0 ? Vc1 : Vc0)[bs0] + lt_at(rvc[bs0], sv0, o0));
+                    const int sv1 = prev1 >= n, bs1 = prev1 - sv1 * n, o1 = b - bs1 + hw;
+                    if (o1 >= 0 && o1 < W) L1 = fmax(L1, (sv1 ? Vc1 : Vc0)[bs1] + lt_at(rvc[bs1], 1 - sv1, o1));
+                }
                 double best0 = NEG_INF, best1 = NEG_INF;
                 int arg0 = 0, arg1 = 0;
                 const int cfirst = ((b - hw + 8 * VT_CHUNK_PAD) >> 3) - VT_CHUNK_PAD;  // floor((b - hw) / 8)
@@ -198,24 +215,51 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                         const int ohi = b + hw - VT_CHUNK * c;   // offset of the chunk's first source
                         if (ohi < 0) break;
                         const double m = s.M[cur][sv][c + VT_CHUNK_PAD];
-                        const double bd0 = m + s.ubr[sel0][ohi], bd1 = m + s.ubr[sel1][ohi];
+                        const int kind = (VT_CHUNK * c >= hw && VT_CHUNK * c + VT_CHUNK - 1 < n - hw) ? 0 : 1;  // all 8 source rows untruncated?
+                        const double bd0 = m + s.ubr[kind][sel0][ohi], bd1 = m + s.ubr[kind][sel1][ohi];
                         const bool need0 = (bd0 >= L0) && (bd0 > best0);
                         const bool need1 = (bd1 >= L1) && (bd1 > best1);
                         if (need0 || need1) {
                             const int b0 = VT_CHUNK * c;
+                            if (kind == 0 && ohi >= VT_CHUNK - 1 && ohi < W) {
+                                // all 8 sources are untruncated rows inside the band: shared-memory tables only,
+                                // vector loads (V and the row variants of an aligned chunk are 16 B / 8 B aligned)
+                                double x[VT_CHUNK];
 #pragma unroll
-                            for (int j = 0; j < VT_CHUNK; ++j) {
-                                const int o = ohi - j;
-                                if (o >= 0 && o < W) {
-                                    const int var = rvc[b0 + j];
-                                    const double x = Vc[b0 + j];
+                                for (int j = 0; j < VT_CHUNK; j += 2) {
+                                    const double2 xx = *reinterpret_cast<const double2*>(&Vc[b0 + j]);
+                                    x[j] = xx.x;
+                                    x[j + 1] = xx.y;
+                                }
+                                const unsigned long long vars = *reinterpret_cast<const unsigned long long*>(&rvc[b0]);
+#pragma unroll
+                                for (int j = 0; j < VT_CHUNK; ++j) {
+                                    const int var = static_cast<int>((vars >> (8 * j)) & 0xff);
+                                    const double* row = &s.lt[var][0][ohi - j];
                                     if (need0) {
-                                        const double cc = x + lt_at(var, sel0, o);
+                                        const double cc = x[j] + row[sel0 * VT_MAX_W];
                                         if (cc > best0) { best0 = cc; arg0 = kbase + b0 + j; }
                                     }
                                     if (need1) {
-                                        const double cc = x + lt_at(var, sel1, o);
+                                        const double cc = x[j] + row[sel1 * VT_MAX_W];
                                         if (cc > best1) { best1 = cc; arg1 = kbase + b0 + j; }
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < VT_CHUNK; ++j) {
+                                    const int o = ohi - j;
+                                    if (o >= 0 && o < W) {
+                                        const int var = rvc[b0 + j];
+                                        const double x = Vc[b0 + j];
+                                        if (need0) {
+                                            const double cc = x + lt_at(var, sel0, o);
+                                            if (cc > best0) { best0 = cc; arg0 = kbase + b0 + j; }
+                                        }
+                                        if (need1) {
+                                            const double cc = x + lt_at(var, sel1, o);
+                                            if (cc > best1) { best1 = cc; arg1 = kbase + b0 + j; }
+                                        }
                                     }
                                 }
                             }
@@ -231,6 +275,8 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                 unsigned short* row = bp_out + static_cast<long long>(t) * (2 * n);
                 row[b] = static_cast<unsigned short>(arg0);
                 row[n + b] = static_cast<unsigned short>(arg1);
+                prev0 = arg0;
+                prev1 = arg1;
             }
         }
 
@@ -306,9 +352,9 @@ extern "C" int aegis_viterbi(const aegis_viterbi_params* p, void* stream) {
     const bool small = block <= 448;
     void (*kern)(const aegis_viterbi_params) = nullptr;
     switch (p->half_width) {   // pYIN's band: 50 bins at 22.05 kHz / hop 512, 25 at 44.1 kHz
-        case 50: kern = small ? viterbi_forward_kernel<50, 448, 2> : viterbi_forward_kernel<50, 512, 1>; break;
-        case 25: kern = small ? viterbi_forward_kernel<25, 448, 2> : viterbi_forward_kernel<25, 512, 1>; break;
-        case 12: kern = small ? viterbi_forward_kernel<12, 448, 2> : viterbi_forward_kernel<12, 512, 1>; break;
+        case 50: kern = small ? viterbi_forward_kernel<50, 448, VT_SMALL_MINB> : viterbi_forward_kernel<50, 512, 1>; break;
+        case 25: kern = small ? viterbi_forward_kernel<25, 448, VT_SMALL_MINB> : viterbi_forward_kernel<25, 512, 1>; break;
+        case 12: kern = small ? viterbi_forward_kernel<12, 448, VT_SMALL_MINB> : viterbi_forward_kernel<12, 512, 1>; break;
         default: set_error("aegis_viterbi: half_width=%d has no compiled kernel (12, 25, 50)", p->half_width); return 1;
     }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(VitSmem)));
