@@ -41,8 +41,8 @@ struct VitSmem {
     double M[2][2][VT_N_CHUNKS];                   // max of V over each aligned chunk of 8 bins (-inf outside)
     double obs_lp[2][VT_MAX_BINS];                 // log(obs + tiny) of the voiced states
     double lt[VT_SMEM_VARIANTS][2][VT_MAX_W];      // interior transition variants [variant][same|switch][offset]
-    double ubr[2][2][VT_MAX_W + VT_CHUNK];         // [interior rows only | all rows][same|switch][q]: max of lt over
-                                                   // the row variants and over offsets q-7..q (chunk upper bound)
+    double ubr[2][VT_MAX_W + VT_CHUNK];            // [same|switch][q]: max over the shared-memory (interior) row
+                                                   // variants and over offsets q-7..q; other rows add their own dub
     double seg_val[2][2][VT_MAX_WARPS];            // per-warp leftmost max of V
     short seg_arg[2][2][VT_MAX_WARPS];
     unsigned char rowvar[VT_MAX_BINS + 2 * VT_HALO];
@@ -88,6 +88,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
     const int n = p.n_pitch_bins, T = p.n_frames;
     const int n_warps = (n + 31) >> 5;
     const int nsv = min(p.n_interior_variants, VT_SMEM_VARIANTS);
+    const bool interior_in_smem = p.n_interior_variants <= VT_SMEM_VARIANTS;  // fast path may index s.lt by variant
     const double NEG_INF = -INFINITY;
     const double LOGTINY = p.log_tiny;
     const bool live = b < n;
@@ -104,20 +105,35 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
         const int var = i / (2 * W), rem = i - var * 2 * W;
         s.lt[var][rem / W][rem % W] = __ldg(p.lt_variants + i);
     }
-    // ubr[kind][sel][q] = max_{j<8, var} lt[var][sel][q-j]; kind 0 = interior row variants only (they differ in
-    // the last ulp, so the bound is tight), kind 1 = every variant (the truncated edge rows are up to log 2 larger)
-    for (int i = b; i < 2 * 2 * (W + VT_CHUNK); i += blockDim.x) {
-        const int kind = i / (2 * (W + VT_CHUNK)), r = i - kind * 2 * (W + VT_CHUNK);
-        const int sel = r / (W + VT_CHUNK), q = r - sel * (W + VT_CHUNK);
-        const int nv = kind == 0 ? p.n_interior_variants : p.n_variants;
+    __syncthreads();
+    // Chunk upper bounds.  base[sel][o] = max over the interior variants held in shared memory (they differ in
+    // the last ulp); ubr[sel][q] = max_{j<8} base[sel][q-j].  A source row with any other variant (the truncated
+    // edge rows are up to log 2 larger) carries its own excess dub = max_{sel,o}(lt_row - base) + margin, which is
+    // added to V before the chunk maxima are taken: max_chunk(V + dub) + ubr bounds every candidate of the chunk.
+    for (int i = b; i < 2 * (W + VT_CHUNK); i += blockDim.x) {
+        const int sel = i / (W + VT_CHUNK), q = i - sel * (W + VT_CHUNK);
         double m = NEG_INF;
         for (int j = 0; j < VT_CHUNK; ++j) {
             const int o = q - j;
             if (o < 0 || o >= W) continue;
-            for (int var = 0; var < nv; ++var)
-                m = fmax(m, __ldg(p.lt_variants + (static_cast<long long>(var) * 2 + sel) * W + o));
+            for (int var = 0; var < nsv; ++var) m = fmax(m, s.lt[var][sel][o]);
         }
-        s.ubr[kind][sel][q] = m;
+        s.ubr[sel][q] = m;
+    }
+    double dub = 0.0;
+    if (live) {
+        const int var = __ldg(p.row_variant + b);
+        if (var >= nsv) {
+            double ex = 0.0;
+            for (int sel = 0; sel < 2; ++sel)
+                for (int o = 0; o < W; ++o) {
+                    const double v = __ldg(p.lt_variants + (static_cast<long long>(var) * 2 + sel) * W + o);
+                    double base = NEG_INF;
+                    for (int iv = 0; iv < nsv; ++iv) base = fmax(base, s.lt[iv][sel][o]);
+                    if (v > NEG_INF) ex = fmax(ex, v - base);
+                }
+            dub = ex + 1e-6;  // margin >> any rounding of the bound arithmetic (|V| < 1e10)
+        }
     }
     __syncthreads();
 
@@ -216,12 +232,12 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                         if (ohi < 0) break;
                         const double m = s.M[cur][sv][c + VT_CHUNK_PAD];
                         const int kind = (VT_CHUNK * c >= hw && VT_CHUNK * c + VT_CHUNK - 1 < n - hw) ? 0 : 1;  // all 8 source rows untruncated?
-                        const double bd0 = m + s.ubr[kind][sel0][ohi], bd1 = m + s.ubr[kind][sel1][ohi];
+                        const double bd0 = m + s.ubr[sel0][ohi], bd1 = m + s.ubr[sel1][ohi];
                         const bool need0 = (bd0 >= L0) && (bd0 > best0);
                         const bool need1 = (bd1 >= L1) && (bd1 > best1);
                         if (need0 || need1) {
                             const int b0 = VT_CHUNK * c;
-                            if (kind == 0 && ohi >= VT_CHUNK - 1 && ohi < W) {
+                            if (kind == 0 && interior_in_smem && ohi >= VT_CHUNK - 1 && ohi < W) {
                                 // all 8 sources are untruncated rows inside the band: shared-memory tables only,
                                 // vector loads (V and the row variants of an aligned chunk are 16 B / 8 B aligned)
                                 double x[VT_CHUNK];
@@ -288,10 +304,16 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
             VA x{live ? (v == 0 ? vnew0 : vnew1) : NEG_INF, b};
+            {   // chunk maxima of V + dub (plain max: no index needed)
+                double cm = x.v + dub;
+                cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+                cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+                cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 4));
+                if ((lane & 7) == 0) s.M[nxt][v][(b >> 3) + VT_CHUNK_PAD] = cm;
+            }
             x = butterfly_leftmost(x, 1);
             x = butterfly_leftmost(x, 2);
             x = butterfly_leftmost(x, 4);
-            if ((lane & 7) == 0) s.M[nxt][v][(b >> 3) + VT_CHUNK_PAD] = x.v;
             x = butterfly_leftmost(x, 8);
             x = butterfly_leftmost(x, 16);
             if (lane == 0) {
