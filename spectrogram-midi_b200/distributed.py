@@ -35,6 +35,7 @@ import torch.distributed as dist
 from .batch import shard_range
 
 N_FFT = 2048
+FRAME_ALIGN = 8  # STFT tiles are 8 frames, YIN packs frame pairs: windows start on a tile boundary
 
 
 # ------------------------------------------------------------------------------------------------
@@ -134,6 +135,7 @@ def plan_windows(n_samples: int, hop_length: int, world: int, burn_frames: int) 
     for r in range(world):
         own = shard_range(n_frames, r, world)
         lo, hi = max(0, own.start - burn_frames), min(n_frames, own.stop + burn_frames)
+        lo -= lo % FRAME_ALIGN  # keep the kernels' frame pairing / tiling identical to the full-clip run (bit-equal frames)
         first = lo * hop_length - N_FFT // 2
         s0 = max(0, first)
         s1 = min(n_samples, (hi - 1) * hop_length + N_FFT // 2) if hi > lo else s0
@@ -191,10 +193,14 @@ MIN_MARGIN_FRAMES = 32  # the rake run-length gate looks at up to 30 neighbourin
 
 def analyze_long_clip(y, *, sr: float, hop_length: int = 512, fmin: Optional[float] = None, fmax: Optional[float] = None,
                       rake_sensitivity: float = 0.6, mode: str = "exact", burn_seconds: float = 2.0, group=None,
-                      backend=None) -> dict:
+                      backend=None, windows_per_rank: int = 1) -> dict:
     """Perception arrays of ONE long clip computed by all ranks of ``group`` (each rank can read the clip,
-    or at least its own window, from host memory).  Every rank returns the full-length result:
+    or at least its own windows, from host memory).  Every rank returns the full-length result:
     ``rake_mask, f0 (NaN unvoiced), voiced_flag, voiced_probs, rms`` as numpy arrays (aegis_engine.py:72-75).
+
+    The clip is cut into ``world * windows_per_rank`` overlapping windows; rank r owns windows
+    ``r*windows_per_rank ...`` (``windows_per_rank > 1`` bounds device memory for hour-long clips and lets a
+    single GPU exercise the same stitching).
     """
     if mode not in ("exact", "windowed"):
         raise ValueError("mode must be 'exact' or 'windowed'")
@@ -206,25 +212,33 @@ def analyze_long_clip(y, *, sr: float, hop_length: int = 512, fmin: Optional[flo
                               fmax=C6 if fmax is None else fmax, rake_sensitivity=rake_sensitivity)
     n_samples = int(y.shape[-1])
     burn = int(round(burn_seconds * sr / hop_length)) if mode == "windowed" else 0
-    w = plan_windows(n_samples, hop_length, world, max(burn, MIN_MARGIN_FRAMES))[rank]
-    feat = backend.features(np.asarray(y[w.s0 : w.s1], dtype=np.float32), w)
+    plan = plan_windows(n_samples, hop_length, world * windows_per_rank, max(burn, MIN_MARGIN_FRAMES))
+    mine = plan[rank * windows_per_rank : (rank + 1) * windows_per_rank]
+    feats = [backend.features(np.asarray(y[w.s0 : w.s1], dtype=np.float32), w) for w in mine]
 
     # coupling 1: power_to_db(ref=np.max) needs the clip-global maximum of the mel power
-    mel_max = all_reduce_max(feat["mel_max"].clone(), group)
-    rake = backend.rake_mask(feat, mel_max)
-    a, b = w.own_lo - w.win_lo, w.own_hi - w.win_lo
-    own = {"rms": feat["rms"][a:b], "rake_mask": rake[a:b], "voiced_probs": feat["voiced_prob"][a:b]}
+    local_max = feats[0]["mel_max"].clone()
+    for f in feats[1:]:
+        local_max = torch.maximum(local_max, f["mel_max"])
+    mel_max = all_reduce_max(local_max, group)
 
-    if mode == "windowed":
-        # coupling 2, approximate: decode own frames + burn-in margin, keep the interior
-        dec = backend.decode(feat["cand_bin"], feat["cand_prob"], feat["cand_count"], feat["voiced_prob"])
-        own["f0"], own["voiced_flag"] = dec["f0"][a:b], dec["voiced_flag"][a:b]
-        full = {k: torch.cat(all_gather_ragged(v.contiguous(), group)) for k, v in own.items()}
-    else:
-        # coupling 2, exact: all-gather the sparse observations and decode the single chain
-        for k in ("cand_bin", "cand_prob", "cand_count"):
-            own[k] = feat[k][a:b]
-        full = {k: torch.cat(all_gather_ragged(v.contiguous(), group)) for k, v in own.items()}
+    own_parts = []
+    for w, feat in zip(mine, feats):
+        rake = backend.rake_mask(feat, mel_max)
+        a, b = w.own_lo - w.win_lo, w.own_hi - w.win_lo
+        own = {"rms": feat["rms"][a:b], "rake_mask": rake[a:b], "voiced_probs": feat["voiced_prob"][a:b]}
+        if mode == "windowed":
+            # coupling 2, approximate: decode own frames + burn-in margin, keep the interior
+            dec = backend.decode(feat["cand_bin"], feat["cand_prob"], feat["cand_count"], feat["voiced_prob"])
+            own["f0"], own["voiced_flag"] = dec["f0"][a:b], dec["voiced_flag"][a:b]
+        else:
+            for k in ("cand_bin", "cand_prob", "cand_count"):
+                own[k] = feat[k][a:b]
+        own_parts.append(own)
+    own = {k: torch.cat([o[k] for o in own_parts]) for k in own_parts[0]}
+    full = {k: torch.cat(all_gather_ragged(v.contiguous(), group)) for k, v in own.items()}
+    if mode == "exact":
+        # coupling 2, exact: the gathered sparse observations are decoded as the single chain they are
         dec = backend.decode(full.pop("cand_bin"), full.pop("cand_prob"), full.pop("cand_count"), full["voiced_probs"])
         full["f0"], full["voiced_flag"] = dec["f0"], dec["voiced_flag"]
     return {

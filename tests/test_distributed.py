@@ -43,7 +43,8 @@ def test_plan_windows_cover_the_clip(n_samples, world, burn):
         assert a.own_hi == b.own_lo
     for w in ws:
         assert w.win_lo <= w.own_lo <= w.own_hi <= w.win_hi
-        assert w.win_lo == max(0, w.own_lo - burn) and w.win_hi == min(T, w.own_hi + burn)
+        lo = max(0, w.own_lo - burn)
+        assert w.win_lo == lo - lo % 8 and w.win_hi == min(T, w.own_hi + burn)
         assert 0 <= w.s0 <= w.s1 <= n_samples and w.pad % 4 == 0 and 0 <= w.pad <= 1024
         # first frame of the window starts at s0 - pad in clip coordinates
         assert w.s0 - w.pad == w.win_lo * HOP - 1024

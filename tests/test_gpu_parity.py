@@ -494,3 +494,24 @@ def test_synth_corpus_kernel(dev):
     assert torch.allclose(y.abs().amax(dim=1), torch.full((8,), 0.9, device=dev), atol=1e-6)
     f0, vf, _ = P.librosa_compat.pyin(y[0].cpu().numpy(), fmin=E2, fmax=C6, sr=22050)
     assert vf.mean() > 0.3  # plucked strings are pitched
+
+
+# ---------------------------------------------------------------------------------- long clip in windows
+@pytest.mark.parametrize("sr,mode", [(22050, "exact"), (22050, "windowed"), (44100, "exact")])
+def test_long_clip_windows_equal_the_full_clip_result(dev, sr, mode):
+    """distributed.analyze_long_clip on one GPU with 5 windows (the per-rank windows of a multi-GPU run,
+    processed in turn): frame-local outputs and -- in exact mode -- the decode are bit-identical to analysing
+    the whole clip at once (the window starts are aligned to the kernels' 8-frame tiles)."""
+    from spectrogram_midi_b200 import distributed as D
+
+    y = np.concatenate([corpus.random_clip(300 + i, 6.0, sr) for i in range(4)])
+    ref = P.AegisEngine(sample_rate=sr).audio_to_midi(y, None)
+    res = D.analyze_long_clip(y, sr=sr, mode=mode, windows_per_rank=5, burn_seconds=2.0)
+    np.testing.assert_array_equal(res["rake_mask"], ref["rake_mask"])
+    np.testing.assert_array_equal(res["voiced_probs"], ref["voiced_probs"])
+    np.testing.assert_array_equal(res["rms"], ref["rms"])
+    if mode == "exact":
+        np.testing.assert_array_equal(res["voiced_flag"], ref["voiced_flag"])
+        np.testing.assert_array_equal(np.nan_to_num(res["f0"]), ref["f0"])
+    else:
+        assert (res["voiced_flag"] == ref["voiced_flag"]).mean() >= 0.99
