@@ -1,51 +1,61 @@
-// K1: fused frame gather + Hann window + FP32 2048-point FFT -> |X| (+ mel power, frame RMS).
+// K1: fused frame gather + Hann window + FP32 real FFT -> |X| (+ mel power, frame RMS).
 //
 // Replaces librosa.stft / feature.melspectrogram / feature.rms as called from
 // aegis_engine.py:25,70 and aegis_engine_financial.py:46-50,154 (see include/aegis_b200.h).
 //
-// Work unit ("tile") = 8 consecutive frames of one clip.  Persistent CTAs of 256 threads (2 FFT
-// groups x 128 threads), two resident per SM so one CTA's load / store phases overlap the other's
-// transforms.  Tiles are walked with stride gridDim.x: neighbouring CTAs work on neighbouring tiles
-// of the same clip at the same time (halo samples and partially written output sectors meet in L2).
-// Per tile:
-//   1. (7*hop + 2048) samples -> shared, float4 loads, zeros outside the clip (centre padding)
-//   2. two rounds; in each, a group packs two real frames (re = frame a, im = frame b) into one
-//      complex transform.  Each frame is first scaled by an exact power of two ~ 1/||w x|| so the
-//      rounding error of the shared transform stays relative to the frame's OWN norm (a quiet frame
-//      next to an onset keeps its accuracy; an all-zero frame yields exact zeros).  The sums of
-//      squares needed for that scale and for the RMS output come from the values pass 1 loads anyway.
-//      The three radix passes exchange through ONE shared buffer per group (in place).
-//   3. X_a[k], X_b[k] are separated from Z[k], conj(Z[N-k]); magnitudes go to an [1025][8] stage
-//   4. the stage is written out in librosa's [1025, T] layout (float4 per half row when the row
-//      stride allows, else 8 scalar lanes per row); the mel projection reads each stage bin once (every
-//      FFT bin lies in at most two triangles: rise/fall partial sums per band-edge segment).
+// The kernel is bound by FP32 lanes, issue slots and shared-memory bandwidth together (SURVEY H3:
+// ~9 FLOP per HBM byte), so the design minimises all three per frame:
+//   * one WARP transforms TWO frames at once in packed f32x2 arithmetic (rfft2048x2.cuh): half the
+//     issue slots of scalar code, no cross-talk between the frames, no pre-scaling;
+//   * each frame is ONE 1024-point complex transform (even/odd packing) done as 32 x 32 in
+//     registers with a single exchange through shared memory, inside the warp (no CTA barrier);
+//   * window, twiddles and mel weights are read once per frame PAIR.
+// Work unit ("tile") = 8 consecutive frames of one clip = 4 warps ("group").  One persistent CTA per
+// SM holds two groups that run out of phase: while one streams its magnitudes to HBM and projects
+// them on the mel triangles, the other transforms.  Per tile and group:
+//   1. (7*hop + 2048) samples in shared memory (cp.async prefetch issued during the previous tile;
+//      zeros outside the clip = centre padding)
+//   2. each warp: samples * window -> registers (sum of squares for the RMS on the way), pass 1,
+//      exchange, pass 2, Z -> shared, conjugate-pair split, |X| for its two frames -> shared
+//   3. the group writes |X| in librosa's [1025, T] layout, one 32-byte sector (8 frames) per row,
+//      and reduces |X|^2 over the mel triangles (each bin read once: rise/fall partial sums per
+//      band-edge segment).
 // HBM traffic per frame: hop*4 B read (+ halo, L2-served) and 1025*4 B written.
 #include "common.cuh"
-#include "fft2048.cuh"
+#include "rfft2048x2.cuh"
 
 namespace aegis {
 
 constexpr int TILE_F = 8;
-constexpr int STFT_THREADS = 256;
-constexpr int STFT_GROUPS = STFT_THREADS / FFT_THREADS;  // 2
+constexpr int GROUP_WARPS = TILE_F / 2;
+constexpr int GROUP_THREADS = GROUP_WARPS * 32;            // 128
+constexpr int STFT_GROUPS = 2;
+constexpr int STFT_THREADS = STFT_GROUPS * GROUP_THREADS;  // 256
 constexpr int MAX_HOP = 512;
-constexpr int SAMPLES_MAX = (TILE_F - 1) * MAX_HOP + FFT_N;  // 5632
-constexpr int STAGE_PITCH = TILE_F + 1;
+constexpr int SAMPLES_MAX = (TILE_F - 1) * MAX_HOP + RF_N;  // 5632
 constexpr int MEL_MAX = 128;
+constexpr int MEL_PART = (MEL_MAX + 1) * TILE_F;            // floats per rise / fall partial array
+
+// One warp's exchange buffer.  After the split it holds the warp's two magnitude columns as
+// p2 mag[1025] (8200 B) and, above MEL_PART_OFFSET, one of the group's mel partial-sum arrays.
+// The 32-byte tail skews consecutive warp buffers by 8 banks, so the 8 frames of one bin sit in 8 distinct banks.
+struct alignas(16) WarpBuf {
+    c2 e[RF_WARP_BUF];
+    float skew[8];
+};
+constexpr int MEL_PART_OFFSET = 8448;  // bytes; >= 1025 * 8
+static_assert(MEL_PART_OFFSET >= RF_BINS * 8 && MEL_PART_OFFSET + MEL_PART * 4 <= RF_WARP_BUF * 16, "mel partials alias the warp buffer");
+static_assert(RF_M <= RF_WARP_BUF, "Z (natural order) aliases the exchange buffer");
 
 struct StftSmem {
-    float samples[SAMPLES_MAX];
-    float window[FFT_N];
-    float part[STFT_GROUPS][4][4];   // per warp: sum x_a^2, x_b^2, (w x_a)^2, (w x_b)^2 (float4 rows: keep 16 B aligned)
-    cf buf[STFT_GROUPS][BUFA_SIZE];
-    float stage[AEGIS_N_BINS * STAGE_PITCH];
-    // mel tables live in shared memory: with ~220 KB of the SM carved out only a few KB of L1 are left, so
-    // weights read through L1 would thrash
-    float2 mel_rf[AEGIS_N_BINS];     // (rise, fall) weight of every FFT bin
+    WarpBuf wb[STFT_GROUPS * GROUP_WARPS];
+    float samples[STFT_GROUPS][SAMPLES_MAX];
+    float window[RF_N];              // 0.5 * analysis window (the split produces 2 X)
+    cf32 tw1[32 * 32];               // [b][lane] W1024^{lane b}
+    cf32 tw2[RF_M / 2 + 2];          // W2048^k, k <= 512
+    float4 mel_rf[RF_BINS];          // (rise, rise, fall, fall) weight of every FFT bin
     int mel_seg[MEL_MAX + 2];        // first bin of every segment between mel band edges
 };
-static_assert(2 * (MEL_MAX + 1) * TILE_F * sizeof(float) <= sizeof(cf) * BUFA_SIZE, "mel partial sums alias buf[0]");
-static_assert((SAMPLES_MAX * 4) % 16 == 0 && (FFT_N * 4) % 16 == 0, "part[] must stay 16-byte aligned");
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
@@ -54,208 +64,203 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-__device__ __forceinline__ int pack_exponent(float windowed_energy) {
-    return (windowed_energy > 0.f) ? (ilogbf(windowed_energy) >> 1) : 0;
+__device__ __forceinline__ p2 psqrt(p2 v) { return p2{sqrt_approx(v.x), sqrt_approx(v.y)}; }
+
+// synchronous tile fill with bounds checks (clip edges, unaligned rows)
+__device__ __forceinline__ void fill_samples(float* smp, const float* __restrict__ yc, long long g0, long long N, int n_buf, int gt) {
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(yc) & 15) == 0) && ((g0 & 3) == 0);
+    for (int i = gt * 4; i < n_buf; i += GROUP_THREADS * 4) {
+        const long long gi = g0 + i;
+        float4 v;
+        if (vec_ok && gi >= 0 && gi + 3 < N) {
+            v = __ldg(reinterpret_cast<const float4*>(yc + gi));
+        } else {
+            v.x = (gi >= 0 && gi < N) ? __ldg(yc + gi) : 0.f;
+            v.y = (gi + 1 >= 0 && gi + 1 < N) ? __ldg(yc + gi + 1) : 0.f;
+            v.z = (gi + 2 >= 0 && gi + 2 < N) ? __ldg(yc + gi + 2) : 0.f;
+            v.w = (gi + 3 >= 0 && gi + 3 < N) ? __ldg(yc + gi + 3) : 0.f;
+        }
+        *reinterpret_cast<float4*>(&smp[i]) = v;
+    }
 }
 
-__global__ void __launch_bounds__(STFT_THREADS, 2)
+__global__ void __launch_bounds__(STFT_THREADS, 1)
 stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const long long n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int g = tid >> 7, lt = tid & 127, lane = tid & 31, warp = tid >> 5, gw = warp & 3;
+    const int g = tid >> 7, gt = tid & 127, lane = tid & 31, wg = gt >> 5;
     const int T = p.n_frames;
     const int hop = p.hop;
     const long long N = p.n_samples;
 
-    for (int i = tid; i < FFT_N; i += STFT_THREADS) s.window[i] = p.window[i];
-    if (p.mel != nullptr) {
-        for (int i = tid; i < AEGIS_N_BINS; i += STFT_THREADS) s.mel_rf[i] = reinterpret_cast<const float2*>(p.mel_rise_fall)[i];
-        for (int i = tid; i < p.n_mels + 2; i += STFT_THREADS) s.mel_seg[i] = p.mel_seg_start[i];
+    {   // constant tables (once per CTA)
+        const cf32* tab = reinterpret_cast<const cf32*>(p.twiddle);
+        for (int i = tid; i < RF_N; i += STFT_THREADS) s.window[i] = 0.5f * p.window[i];
+        for (int i = tid; i < 32 * 32; i += STFT_THREADS) s.tw1[i] = tab[(2 * (i & 31) * (i >> 5)) & (RF_N - 1)];
+        for (int i = tid; i <= RF_M / 2; i += STFT_THREADS) s.tw2[i] = tab[i];
+        if (p.mel != nullptr) {
+            for (int i = tid; i < RF_BINS; i += STFT_THREADS) {
+                const float2 rf = reinterpret_cast<const float2*>(p.mel_rise_fall)[i];
+                s.mel_rf[i] = make_float4(rf.x, rf.x, rf.y, rf.y);
+            }
+            for (int i = tid; i < p.n_mels + 2; i += STFT_THREADS) s.mel_seg[i] = p.mel_seg_start[i];
+        }
     }
-    FftTwiddles tw;
-    fft2048_load_twiddles(lt, reinterpret_cast<const cf*>(p.twiddle), tw);
-    const int n_buf = (TILE_F - 1) * hop + FFT_N;
-    const bool do_fft = (p.mag != nullptr) || (p.mel != nullptr);
-    cf* const buf = s.buf[g];
-    constexpr int N_ROUNDS = TILE_F / (2 * STFT_GROUPS);
-    bool prefetched = false;  // the samples of this tile were requested with cp.async during the previous one
+    __syncthreads();
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int n_buf = (TILE_F - 1) * hop + RF_N;
+    const bool do_fft = (p.mag != nullptr) || (p.mel != nullptr);
+    float* const smp = s.samples[g];
+    WarpBuf* const gbuf = &s.wb[g * GROUP_WARPS];
+    c2* const xbuf = gbuf[wg].e;
+    p2* const mbuf = reinterpret_cast<p2*>(xbuf);
+    float* const rise = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(gbuf[0].e) + MEL_PART_OFFSET);
+    float* const fall = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(gbuf[1].e) + MEL_PART_OFFSET);
+    const long long tile_step = static_cast<long long>(gridDim.x) * STFT_GROUPS;
+    bool prefetched = false;  // this tile's samples were requested with cp.async during the previous tile
+
+    for (long long tile = static_cast<long long>(blockIdx.x) * STFT_GROUPS + g; tile < n_tiles; tile += tile_step) {
         const int clip = static_cast<int>(tile / tiles_per_clip);
         const int t0 = static_cast<int>(tile - static_cast<long long>(clip) * tiles_per_clip) * TILE_F;
         const float* __restrict__ yc = p.y + static_cast<long long>(clip) * p.clip_stride;
-        const long long g0 = static_cast<long long>(t0) * hop - p.pad;
 
-        __syncthreads();  // everybody is done with the previous tile's stage (and samples, if not prefetched)
-        if (prefetched) {
-            cp_async_wait_all();
-        } else {
-            const bool vec_ok = ((reinterpret_cast<uintptr_t>(yc) & 15) == 0) && ((g0 & 3) == 0);
-            for (int i = tid * 4; i < n_buf; i += STFT_THREADS * 4) {
-                const long long gi = g0 + i;
-                float4 v;
-                if (vec_ok && gi >= 0 && gi + 3 < N) {
-                    v = __ldg(reinterpret_cast<const float4*>(yc + gi));
-                } else {
-                    v.x = (gi >= 0 && gi < N) ? __ldg(yc + gi) : 0.f;
-                    v.y = (gi + 1 >= 0 && gi + 1 < N) ? __ldg(yc + gi + 1) : 0.f;
-                    v.z = (gi + 2 >= 0 && gi + 2 < N) ? __ldg(yc + gi + 2) : 0.f;
-                    v.w = (gi + 3 >= 0 && gi + 3 < N) ? __ldg(yc + gi + 3) : 0.f;
-                }
-                *reinterpret_cast<float4*>(&s.samples[i]) = v;
-            }
+        if (prefetched) cp_async_wait_all();
+        named_barrier(1 + g, GROUP_THREADS);  // previous tile's buffers are free; prefetched samples will be complete
+        if (!prefetched) {
+            fill_samples(smp, yc, static_cast<long long>(t0) * hop - p.pad, N, n_buf, gt);
+            named_barrier(1 + g, GROUP_THREADS);
         }
-        __syncthreads();
 
-#pragma unroll 1
-        for (int round = 0; round < N_ROUNDS; ++round) {
-            const int fa_idx = 2 * (round * STFT_GROUPS + g);  // this group's frame pair (fa_idx, fa_idx + 1)
-            const float* fa = s.samples + fa_idx * hop;
+        // ---- 2a. this warp's frame pair -> registers (windowed), sums of squares for the RMS
+        c2 v[32];
+        {
+            const float* fa = smp + (2 * wg) * hop + 2 * lane;
             const float* fb = fa + hop;
-            cf v[16];
-            float ea2 = 0.f, eb2 = 0.f, wa2 = 0.f, wb2 = 0.f;
+            const float* wp = s.window + 2 * lane;
+            p2 ssa = p2{0.f, 0.f}, ssb = p2{0.f, 0.f};
 #pragma unroll
-            for (int a = 0; a < 16; ++a) {
-                const int n = lt + 128 * a;
-                const float w = s.window[n], xa = fa[n], xb = fb[n];
-                const float pa = xa * w, pb = xb * w;
-                ea2 = fmaf(xa, xa, ea2);
-                eb2 = fmaf(xb, xb, eb2);
-                wa2 = fmaf(pa, pa, wa2);
-                wb2 = fmaf(pb, pb, wb2);
-                v[a] = cf{pa, pb};
+            for (int a = 0; a < 32; ++a) {
+                const float2 xa = *reinterpret_cast<const float2*>(fa + 64 * a);
+                const float2 xb = *reinterpret_cast<const float2*>(fb + 64 * a);
+                const float2 w = *reinterpret_cast<const float2*>(wp + 64 * a);
+                ssa = pfma(p2{xa.x, xa.y}, p2{xa.x, xa.y}, ssa);
+                ssb = pfma(p2{xb.x, xb.y}, p2{xb.x, xb.y}, ssb);
+                v[a] = c2{p2{xa.x * w.x, xb.x * w.x}, p2{xa.y * w.y, xb.y * w.y}};
             }
-            ea2 = warp_sum(ea2);
-            eb2 = warp_sum(eb2);
-            wa2 = warp_sum(wa2);
-            wb2 = warp_sum(wb2);
-            if (lane == 0) *reinterpret_cast<float4*>(s.part[g][gw]) = make_float4(ea2, eb2, wa2, wb2);
-            if (round == N_ROUNDS - 1) {
-                // last read of this tile's samples is behind every thread: request the next tile's samples now,
-                // so their DRAM latency hides behind the rest of this tile (passes 2-3, split, stores, mel)
-                __syncthreads();
-                prefetched = false;
-                const long long nt = tile + gridDim.x;
-                if (nt < n_tiles) {
-                    const int nclip = static_cast<int>(nt / tiles_per_clip);
-                    const int nt0 = static_cast<int>(nt - static_cast<long long>(nclip) * tiles_per_clip) * TILE_F;
-                    const float* nyc = p.y + static_cast<long long>(nclip) * p.clip_stride;
-                    const long long ng0 = static_cast<long long>(nt0) * hop - p.pad;
-                    if (ng0 >= 0 && ng0 + n_buf <= N && ((ng0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(nyc) & 15) == 0)) {
-                        for (int i = tid * 4; i < n_buf; i += STFT_THREADS * 4) cp_async16(&s.samples[i], nyc + ng0 + i);
-                        prefetched = true;
-                    }
-                }
-                cp_async_commit();
-            } else {
-                named_barrier(1 + g, FFT_THREADS);
+            if (p.rms != nullptr) {
+                const float sa = warp_sum(ssa.x + ssa.y), sb = warp_sum(ssb.x + ssb.y);
+                const int t = t0 + 2 * wg + lane;
+                if (lane < 2 && t < T)
+                    p.rms[static_cast<long long>(clip) * p.rms_clip_stride + t] = sqrtf((lane == 0 ? sa : sb) * (1.0f / RF_N));
             }
-            float4 tot = *reinterpret_cast<const float4*>(s.part[g][0]);
-#pragma unroll
-            for (int w4 = 1; w4 < 4; ++w4) {
-                const float4 q = *reinterpret_cast<const float4*>(s.part[g][w4]);
-                tot.x += q.x; tot.y += q.y; tot.z += q.z; tot.w += q.w;
-            }
-            if (p.rms != nullptr && lt < 2 && t0 + fa_idx + lt < T) {
-                p.rms[static_cast<long long>(clip) * p.rms_clip_stride + t0 + fa_idx + lt] =
-                    sqrtf((lt == 0 ? tot.x : tot.y) * (1.0f / FFT_N));
-            }
-            if (!do_fft) {  // RMS-only call (librosa.feature.rms)
-                named_barrier(1 + g, FFT_THREADS);  // s.part is rewritten next round
-                continue;
-            }
-            const int ea = pack_exponent(tot.z), eb = pack_exponent(tot.w);
-            {
-                const float sa = ldexpf(1.0f, -ea), sb = ldexpf(1.0f, -eb);
-#pragma unroll
-                for (int a = 0; a < 16; ++a) v[a] = cf{v[a].x * sa, v[a].y * sb};
-            }
-            fft2048_pass1(lt, v, tw, buf);
-            named_barrier(1 + g, FFT_THREADS);
-            fft2048_pass2_load(lt, buf, v);
-            named_barrier(1 + g, FFT_THREADS);
-            fft2048_pass2_store(lt, v, tw, buf);
-            named_barrier(1 + g, FFT_THREADS);
-            fft2048_pass3_load(lt, buf, v);
-            named_barrier(1 + g, FFT_THREADS);
-            fft2048_pass3_store(lt, v, buf);
-            named_barrier(1 + g, FFT_THREADS);
-            {   // split the packed spectrum: X_a = (Z[k] + conj Z[N-k]) / 2, X_b = (Z[k] - conj Z[N-k]) / 2i
-                // undo the packing scale (and the /2); an all-zero frame yields exact zeros
-                const float ua = tot.z > 0.f ? ldexpf(0.5f, ea) : 0.f, ub = tot.w > 0.f ? ldexpf(0.5f, eb) : 0.f;
-#pragma unroll
-                for (int m = 0; m < 9; ++m) {
-                    const int k = lt + 128 * m;
-                    if (k <= FFT_N / 2) {
-                        const cf zk = buf[k];
-                        const cf zn = buf[(FFT_N - k) & (FFT_N - 1)];
-                        const float ar = zk.x + zn.x, ai = zk.y - zn.y;
-                        const float br = zk.y + zn.y, bi = zn.x - zk.x;
-                        s.stage[k * STAGE_PITCH + fa_idx] = ua * sqrt_approx(fmaf(ar, ar, ai * ai));
-                        s.stage[k * STAGE_PITCH + fa_idx + 1] = ub * sqrt_approx(fmaf(br, br, bi * bi));
-                    }
-                }
-            }
-            named_barrier(1 + g, FFT_THREADS);  // buf / s.part are rewritten by the next round
         }
-        if (!do_fft) continue;
-        __syncthreads();
+        // every warp of the group has read its samples: request the next tile's samples now, so their DRAM latency
+        // hides behind the transforms, the stores and the mel projection of this tile
+        named_barrier(1 + g, GROUP_THREADS);
+        {
+            prefetched = false;
+            const long long nt = tile + tile_step;
+            if (nt < n_tiles) {
+                const int nclip = static_cast<int>(nt / tiles_per_clip);
+                const int nt0 = static_cast<int>(nt - static_cast<long long>(nclip) * tiles_per_clip) * TILE_F;
+                const float* nyc = p.y + static_cast<long long>(nclip) * p.clip_stride;
+                const long long ng0 = static_cast<long long>(nt0) * hop - p.pad;
+                if (ng0 >= 0 && ng0 + n_buf <= N && ((ng0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(nyc) & 15) == 0)) {
+                    for (int i = gt * 4; i < n_buf; i += GROUP_THREADS * 4) cp_async16(&smp[i], nyc + ng0 + i);
+                    prefetched = true;
+                }
+            }
+            cp_async_commit();
+        }
+        if (!do_fft) continue;  // RMS-only call (librosa.feature.rms)
 
+        // ---- 2b. two real 2048-point transforms, inside the warp
+        rfft_pass1(lane, v, s.tw1, xbuf);
+        __syncwarp();
+        rfft_pass2_load(lane, xbuf, v);
+        __syncwarp();
+        rfft_pass2_store(lane, v, xbuf);
+        __syncwarp();
+        {   // conjugate-pair split -> magnitudes in registers, then over the (now dead) spectrum
+            p2 mk[16], mn[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = lane + 32 * i;
+                p2 pk, pn;
+                rfft_split_pair(xbuf[k], xbuf[(RF_M - k) & (RF_M - 1)], s.tw2[k], pk, pn);
+                mk[i] = psqrt(pk);
+                mn[i] = psqrt(pn);
+            }
+            p2 pm, pm_unused;
+            rfft_split_pair(xbuf[RF_M / 2], xbuf[RF_M / 2], s.tw2[RF_M / 2], pm, pm_unused);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = lane + 32 * i;
+                mbuf[k] = mk[i];
+                mbuf[RF_M - k] = mn[i];
+            }
+            if (lane == 0) mbuf[RF_M / 2] = psqrt(pm);
+        }
+        named_barrier(1 + g, GROUP_THREADS);  // the group's 8 magnitude columns are complete
+
+        // ---- 3a. |X| -> HBM, librosa layout
         if (p.mag != nullptr) {
             float* __restrict__ mo = p.mag + static_cast<long long>(clip) * p.mag_clip_stride + t0;
             const bool vec_store = ((p.mag_row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(mo) & 15) == 0);
             if (vec_store) {  // one float4 (4 frames) per lane, two lanes per spectrogram row
-                for (int idx = tid; idx < 2 * AEGIS_N_BINS; idx += STFT_THREADS) {
-                    const int k = idx >> 1, h = (idx & 1) * 4;
-                    const float* st = &s.stage[k * STAGE_PITCH + h];
-                    float* dst = mo + static_cast<long long>(k) * p.mag_row_stride + h;
-                    if (t0 + h + 3 < T) {
-                        *reinterpret_cast<float4*>(dst) = make_float4(st[0], st[1], st[2], st[3]);
+                for (int idx = gt; idx < 2 * RF_BINS; idx += GROUP_THREADS) {
+                    const int k = idx >> 1, h = idx & 1;
+                    const p2 m0 = reinterpret_cast<const p2*>(gbuf[2 * h].e)[k];
+                    const p2 m1 = reinterpret_cast<const p2*>(gbuf[2 * h + 1].e)[k];
+                    float* dst = mo + static_cast<long long>(k) * p.mag_row_stride + 4 * h;
+                    if (t0 + 4 * h + 3 < T) {
+                        *reinterpret_cast<float4*>(dst) = make_float4(m0.x, m0.y, m1.x, m1.y);
                     } else {
+                        const float st[4] = {m0.x, m0.y, m1.x, m1.y};
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (t0 + h + j < T) dst[j] = st[j];
+                            if (t0 + 4 * h + j < T) dst[j] = st[j];
                     }
                 }
             } else {          // each warp store = 4 rows x 8 frames
                 const int f = lane & 7;
                 if (t0 + f < T) {
-                    for (int k = warp * 4 + (lane >> 3); k < AEGIS_N_BINS; k += (STFT_THREADS / 32) * 4)
-                        mo[static_cast<long long>(k) * p.mag_row_stride + f] = s.stage[k * STAGE_PITCH + f];
+                    const float* col = reinterpret_cast<const float*>(gbuf[f >> 1].e) + (f & 1);
+                    for (int k = wg * 4 + (lane >> 3); k < RF_BINS; k += GROUP_WARPS * 4)
+                        mo[static_cast<long long>(k) * p.mag_row_stride + f] = col[2 * k];
                 }
             }
         }
+        // ---- 3b. mel[b] = sum_{k in seg b} rise[k] |X_k|^2 + sum_{k in seg b+1} fall[k] |X_k|^2
         if (p.mel != nullptr) {
-            // mel[b] = sum_{k in seg b} rise[k] |X_k|^2 + sum_{k in seg b+1} fall[k] |X_k|^2  (each bin read once).
-            // lane = (frame, segment-in-quad): a warp reads 4 stage rows x 8 frames per step, near conflict free.
-            float* const rise = reinterpret_cast<float*>(s.buf[0]);          // [n_mels + 1][8], buf is free here
-            float* const fall = rise + (MEL_MAX + 1) * TILE_F;
-            {
-                const int f = lane & 7;
-                for (int j = warp * 4 + (lane >> 3); j <= p.n_mels; j += (STFT_THREADS / 32) * 4) {
+            {   // lane = (segment slot, warp buffer): a frame pair per lane, packed accumulation
+                const int b4 = lane & 3;
+                const p2* col = reinterpret_cast<const p2*>(gbuf[b4].e);
+                for (int j = wg * 8 + (lane >> 2); j <= p.n_mels; j += GROUP_WARPS * 8) {
                     const int k0 = s.mel_seg[j], k1 = s.mel_seg[j + 1];
-                    float r = 0.f, fl = 0.f;
+                    p2 r = p2{0.f, 0.f}, fl = p2{0.f, 0.f};
                     for (int k = k0; k < k1; ++k) {
-                        const float m = s.stage[k * STAGE_PITCH + f];
-                        const float2 w = s.mel_rf[k];
-                        const float pw = m * m;
-                        r = fmaf(w.x, pw, r);
-                        fl = fmaf(w.y, pw, fl);
+                        const p2 m = col[k];
+                        const float4 w = s.mel_rf[k];
+                        const p2 pw = m * m;
+                        r = pfma(pw, p2{w.x, w.y}, r);
+                        fl = pfma(pw, p2{w.z, w.w}, fl);
                     }
-                    rise[j * TILE_F + f] = r;
-                    fall[j * TILE_F + f] = fl;
+                    *reinterpret_cast<p2*>(&rise[j * TILE_F + 2 * b4]) = r;
+                    *reinterpret_cast<p2*>(&fall[j * TILE_F + 2 * b4]) = fl;
                 }
             }
-            __syncthreads();
+            named_barrier(1 + g, GROUP_THREADS);
             float* __restrict__ me = p.mel + static_cast<long long>(clip) * p.mel_clip_stride + t0;
             float vmax = 0.f;
-            for (int idx = tid; idx < p.n_mels * TILE_F; idx += STFT_THREADS) {
+            for (int idx = gt; idx < p.n_mels * TILE_F; idx += GROUP_THREADS) {
                 const int b = idx >> 3, f = idx & 7;
-                const float v = rise[b * TILE_F + f] + fall[(b + 1) * TILE_F + f];
+                const float val = rise[b * TILE_F + f] + fall[(b + 1) * TILE_F + f];
                 if (t0 + f < T) {
-                    me[static_cast<long long>(b) * p.mel_row_stride + f] = v;
-                    vmax = fmaxf(vmax, v);
+                    me[static_cast<long long>(b) * p.mel_row_stride + f] = val;
+                    vmax = fmaxf(vmax, val);
                 }
             }
             if (p.mel_max != nullptr) {
@@ -264,6 +269,7 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
             }
         }
     }
+    cp_async_wait_all();
 }
 
 }  // namespace aegis
@@ -293,11 +299,9 @@ extern "C" int aegis_stft_fused(const aegis_stft_params* p, void* stream) {
             return 2;
         }
     }
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_fused_kernel, STFT_THREADS, sizeof(StftSmem)) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    const long long max_grid = static_cast<long long>(sm_count()) * per_sm;
-    const int grid = static_cast<int>(n_tiles < max_grid ? n_tiles : max_grid);
+    const long long ctas_needed = (n_tiles + STFT_GROUPS - 1) / STFT_GROUPS;
+    const long long max_grid = sm_count();
+    const int grid = static_cast<int>(ctas_needed < max_grid ? ctas_needed : max_grid);
     stft_fused_kernel<<<grid, STFT_THREADS, sizeof(StftSmem), static_cast<cudaStream_t>(stream)>>>(*p, tiles_per_clip, n_tiles);
     return check_launch("aegis_stft_fused");
 }

@@ -1,0 +1,56 @@
+// Host emulation of the warp-level packed real FFT (csrc/rfft2048x2.cuh): the 32 "lanes" of each
+// phase run in a loop (forward or reverse order) over plain arrays standing in for shared memory.
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "../../spectrogram-midi_b200/csrc/rfft2048x2.cuh"
+
+using namespace aegis;
+
+// frames: [2][2048] real (already windowed); twiddle: [2048][2] (cos, -sin)(2 pi k / 2048)
+// out: [2][1025] magnitudes of the two frames' spectra (x 2, as the kernel computes before its 1/2 fold)
+extern "C" int emul_rfft2048x2(const float* frames, const float* twiddle, float* out, int reverse_order) {
+    const cf32* tab = reinterpret_cast<const cf32*>(twiddle);
+    std::vector<cf32> tw1(32 * 32), tw2(513);
+    for (int b = 0; b < 32; ++b)
+        for (int j = 0; j < 32; ++j) tw1[b * 32 + j] = tab[(2 * j * b) & 2047];
+    for (int k = 0; k <= 512; ++k) tw2[k] = tab[k];
+    std::vector<c2> buf(RF_WARP_BUF);
+    std::vector<c2> regs(32 * 32);
+    auto each = [&](auto&& body) {
+        if (reverse_order) for (int l = 31; l >= 0; --l) body(l);
+        else for (int l = 0; l < 32; ++l) body(l);
+    };
+    const float* fa = frames;
+    const float* fb = frames + 2048;
+    each([&](int lane) {
+        c2* v = &regs[lane * 32];
+        for (int a = 0; a < 32; ++a) {
+            const int m = lane + 32 * a;
+            v[a] = c2{p2{fa[2 * m], fb[2 * m]}, p2{fa[2 * m + 1], fb[2 * m + 1]}};
+        }
+        rfft_pass1(lane, v, tw1.data(), buf.data());
+    });
+    each([&](int lane) { rfft_pass2_load(lane, buf.data(), &regs[lane * 32]); });
+    each([&](int lane) { rfft_pass2_store(lane, &regs[lane * 32], buf.data()); });
+    std::vector<p2> mag(1025);
+    each([&](int lane) {
+        for (int i = 0; i < 16; ++i) {
+            const int k = lane + 32 * i;
+            p2 pk, pn;
+            rfft_split_pair(buf[k], buf[(1024 - k) & 1023], tw2[k], pk, pn);
+            mag[k] = p2{std::sqrt(pk.x), std::sqrt(pk.y)};
+            mag[1024 - k] = p2{std::sqrt(pn.x), std::sqrt(pn.y)};
+        }
+        if (lane == 0) {
+            p2 pk, pn;
+            rfft_split_pair(buf[512], buf[512], tw2[512], pk, pn);
+            mag[512] = p2{std::sqrt(pk.x), std::sqrt(pk.y)};
+        }
+    });
+    for (int k = 0; k <= 1024; ++k) {
+        out[k] = mag[k].x;
+        out[1025 + k] = mag[k].y;
+    }
+    return 0;
+}
