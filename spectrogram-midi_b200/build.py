@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libaegis_b200.so")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr", "--extended-lambda",
 ]
 
 

@@ -152,16 +152,22 @@ AEGIS_HD void fft32(c2* v) {
 constexpr int RF_N = 2048;             // real frame length
 constexpr int RF_M = 1024;             // complex transform length
 constexpr int RF_BINS = RF_N / 2 + 1;  // 1025
-constexpr int RF_XPITCH = 33;          // exchange rows of 32 c2 (+1 pad): conflict-free 128-bit stores and loads
-constexpr int RF_WARP_BUF = 32 * RF_XPITCH;  // c2 elements (16896 B)
+constexpr int RF_XPITCH = 33;          // exchange rows of 32 words (+1 pad): conflict-free 32-bit stores and loads
+constexpr int RF_PLANE = 32 * RF_XPITCH;           // words per (frame, re|im) plane
+// planes: [A re][A im][16 words][B re][B im]; frame B sits 16 banks after frame A so that the two half-warps of
+// pass 2 (lanes 0-15 frame A, lanes 16-31 frame B, 16 consecutive words each) never collide
+constexpr int RF_FRAME_B = 2 * RF_PLANE + 16;
+constexpr int RF_WARP_WORDS = RF_FRAME_B + 2 * RF_PLANE;  // 4240 words
 
 struct alignas(8) cf32 {
     float x, y;
 };
 
 // pass 1: v[a] holds z[lane + 32a] of both frames.  tw1[b * 32 + lane] = W1024^{lane * b}.
-AEGIS_HD void rfft_pass1(int lane, c2* v, const cf32* tw1, c2* xbuf) {
+// Element (lane, b) of frame A / B goes to its frame's re and im planes at [lane][b].
+AEGIS_HD void rfft_pass1(int lane, c2* v, const cf32* tw1, float* xbuf) {
     fft32(v);
+    float* const row = xbuf + lane * RF_XPITCH;
 #pragma unroll
     for (int b = 0; b < 32; ++b) {
         c2 y = v[rpos32(b)];
@@ -172,34 +178,82 @@ AEGIS_HD void rfft_pass1(int lane, c2* v, const cf32* tw1, c2* xbuf) {
             const p2 im = pfma(y.re, wi, y.im * wr);
             y = c2{re, im};
         }
-        xbuf[lane * RF_XPITCH + b] = y;
+        row[b] = y.re.x;
+        row[RF_PLANE + b] = y.im.x;
+        row[RF_FRAME_B + b] = y.re.y;
+        row[RF_FRAME_B + RF_PLANE + b] = y.im.y;
     }
 }
 
-AEGIS_HD void rfft_pass2_load(int lane, const c2* xbuf, c2* v) {
+// pass 2 works on ONE frame per half-warp (h = lane >> 4) and packs two COLUMNS of that frame:
+//   lo = column q, hi = column 32 - q   (q = lane & 15; q = 0: columns 0 and 16)
+// so that after the 32-point DFT over j the conjugate partner of lo(V[c]) = Z[q + 32c], which is
+// Z[1024 - q - 32c] = Z[(32 - q) + 32 (31 - c)], is hi(V[31 - c]) of the same thread: the real-spectrum
+// split needs no further exchange.
+AEGIS_HD constexpr int rfft_col1(int q) { return q ? 32 - q : 16; }
+
+AEGIS_HD void rfft_pass2_load(int lane, const float* xbuf, c2* v) {
+    const int h = lane >> 4, q = lane & 15;
+    const float* const p0 = xbuf + h * RF_FRAME_B + q;
+    const float* const p1 = xbuf + h * RF_FRAME_B + rfft_col1(q);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = xbuf[j * RF_XPITCH + lane];
+    for (int j = 0; j < 32; ++j)
+        v[j] = c2{p2{p0[j * RF_XPITCH], p1[j * RF_XPITCH]}, p2{p0[RF_PLANE + j * RF_XPITCH], p1[RF_PLANE + j * RF_XPITCH]}};
 }
 
-// pass 2 (after every lane finished rfft_pass2_load): Z[lane + 32c] -> zbuf (natural order, aliases xbuf)
-AEGIS_HD void rfft_pass2_store(int lane, c2* v, c2* zbuf) {
-    fft32(v);
-#pragma unroll
-    for (int c = 0; c < 32; ++c) zbuf[lane + 32 * c] = v[rpos32(c)];
+// Split one conjugate pair (scalars of one frame): from Z[k] = (kr, ki), Z[1024-k] = (nr, ni) and W2048^k to the
+// squared magnitudes of 2 X[k] and 2 X[1024-k] (the caller folds the 1/2 into the window).
+AEGIS_HD void rfft_split_pair(float kr, float ki, float nr, float ni, cf32 w, float& pow_k, float& pow_n) {
+    const float sr = kr + nr, si = ki - ni;  // S = Zk + conj Zn
+    const float dr = kr - nr, di = ki + ni;  // D = Zk - conj Zn;  O' = D / i = (di, -dr)
+    const float tr = di * w.x + dr * w.y;    // Re W O'
+    const float ti = di * w.y - dr * w.x;    // Im W O'
+    const float ar = sr + tr, ai = si + ti;  // 2 X[k]
+    const float br = sr - tr, bi = si - ti;  // conj(2 X[1024-k])
+    pow_k = ar * ar + ai * ai;
+    pow_n = br * br + bi * bi;
 }
 
-// Split one conjugate pair: from Z[k], Z[1024-k] and W2048^k to 2 X[k], 2 X[1024-k]; returns the two
-// squared magnitudes (of 2X; the caller folds the 1/2 into the window).
-AEGIS_HD void rfft_split_pair(c2 zk, c2 zn, cf32 w, p2& pow_k, p2& pow_n) {
-    const p2 sr = zk.re + zn.re, si = zk.im - zn.im;  // S = Zk + conj Zn
-    const p2 dr = zk.re - zn.re, di = zk.im + zn.im;  // D = Zk - conj Zn;  O' = D / i = (di, -dr)
-    const p2 wr = psplat(w.x), wi = psplat(w.y);
-    const p2 tr = pfma(di, wr, dr * wi);              // Re W O' = wr di + wi dr
-    const p2 ti = pfma(di, wi, -(dr * wr));           // Im W O' = wi di - wr dr
-    const p2 ar = sr + tr, ai = si + ti;              // 2 X[k]
-    const p2 br = sr - tr, bi = si - ti;              // conj(2 X[1024-k])
-    pow_k = pfma(ar, ar, ai * ai);
-    pow_n = pfma(br, br, bi * bi);
+// After fft32 of pass 2: emit |2X|^2 of every bin this thread owns through `emit(k, power)`.
+//   general lanes (q >= 1): k = q + 32c pairs with 1024 - k                          (64 bins)
+//   q == 0 lanes: column 0 (k = 32c, partner 32(32-c)), column 16 (k = 16 + 32i, partner 16 + 32(31-i)), k = 512
+// The q == 0 lanes pick different registers through selects so the warp stays converged.
+template <class Emit>
+AEGIS_HD void rfft_split_emit(int lane, const c2* v, const cf32* tw2, Emit&& emit) {
+    const int q = lane & 15;
+    const bool sp = (q == 0);
+    const int koff = sp ? -496 : 0;  // q == 0, c >= 16: k = 16 + 32 (c - 16)
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const c2 a = v[rpos32(c)], b = v[rpos32(31 - c)];
+        float kr, ki, nr, ni;
+        int k;
+        if (c < 16) {
+            const c2 b0 = v[rpos32((32 - c) & 31)];
+            kr = a.re.x;
+            ki = a.im.x;
+            nr = sp ? b0.re.x : b.re.y;
+            ni = sp ? b0.im.x : b.im.y;
+            k = q + 32 * c;
+        } else {
+            const c2 a1 = v[rpos32(c - 16)], b1 = v[rpos32(47 - c)];
+            kr = sp ? a1.re.y : a.re.x;
+            ki = sp ? a1.im.y : a.im.x;
+            nr = sp ? b1.re.y : b.re.y;
+            ni = sp ? b1.im.y : b.im.y;
+            k = q + 32 * c + koff;
+        }
+        float pk, pn;
+        rfft_split_pair(kr, ki, nr, ni, tw2[k], pk, pn);
+        emit(k, pk);
+        emit(RF_M - k, pn);
+    }
+    {
+        const c2 a = v[rpos32(16)];
+        float pk, pn;
+        rfft_split_pair(a.re.x, a.im.x, a.re.x, a.im.x, tw2[RF_M / 2], pk, pn);
+        if (sp) emit(RF_M / 2, pk);
+    }
 }
 
 }  // namespace aegis

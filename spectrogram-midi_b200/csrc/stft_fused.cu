@@ -36,26 +36,28 @@ constexpr int SAMPLES_MAX = (TILE_F - 1) * MAX_HOP + RF_N;  // 5632
 constexpr int MEL_MAX = 128;
 constexpr int MEL_PART = (MEL_MAX + 1) * TILE_F;            // floats per rise / fall partial array
 
-// One warp's exchange buffer.  After the split it holds the warp's two magnitude columns as
-// p2 mag[1025] (8200 B) and, above MEL_PART_OFFSET, one of the group's mel partial-sum arrays.
-// The 32-byte tail skews consecutive warp buffers by 8 banks, so the 8 frames of one bin sit in 8 distinct banks.
+// One warp's exchange buffer (re / im planes of its two frames, rfft2048x2.cuh).  After pass 2 has loaded them the
+// same memory holds the warp's two magnitude columns as p2 mag[1025] (8200 B) and, above MEL_PART_OFFSET, one of
+// the group's mel partial-sum arrays.  The tail pads the stride to 8 banks (mod 32): the 8 frames of one bin sit
+// in 8 distinct banks.
 struct alignas(16) WarpBuf {
-    c2 e[RF_WARP_BUF];
-    float skew[8];
+    float e[RF_WARP_WORDS];
+    float skew[24];
 };
+static_assert((sizeof(WarpBuf) / 4) % 32 == 8, "consecutive warp buffers must be skewed by 8 banks");
 constexpr int MEL_PART_OFFSET = 8448;  // bytes; >= 1025 * 8
-static_assert(MEL_PART_OFFSET >= RF_BINS * 8 && MEL_PART_OFFSET + MEL_PART * 4 <= RF_WARP_BUF * 16, "mel partials alias the warp buffer");
-static_assert(RF_M <= RF_WARP_BUF, "Z (natural order) aliases the exchange buffer");
+static_assert(MEL_PART_OFFSET >= RF_BINS * 8 && MEL_PART_OFFSET + MEL_PART * 4 <= RF_WARP_WORDS * 4, "mel partials alias the warp buffer");
 
 struct StftSmem {
     WarpBuf wb[STFT_GROUPS * GROUP_WARPS];
     float samples[STFT_GROUPS][SAMPLES_MAX];
     float window[RF_N];              // 0.5 * analysis window (the split produces 2 X)
     cf32 tw1[32 * 32];               // [b][lane] W1024^{lane b}
-    cf32 tw2[RF_M / 2 + 2];          // W2048^k, k <= 512
+    cf32 tw2[RF_M];                  // W2048^k
     float4 mel_rf[RF_BINS];          // (rise, rise, fall, fall) weight of every FFT bin
     int mel_seg[MEL_MAX + 2];        // first bin of every segment between mel band edges
 };
+static_assert(sizeof(StftSmem) <= 227 * 1024, "shared memory budget of one SM");
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
@@ -64,7 +66,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-__device__ __forceinline__ p2 psqrt(p2 v) { return p2{sqrt_approx(v.x), sqrt_approx(v.y)}; }
 
 // synchronous tile fill with bounds checks (clip edges, unaligned rows)
 __device__ __forceinline__ void fill_samples(float* smp, const float* __restrict__ yc, long long g0, long long N, int n_buf, int gt) {
@@ -98,7 +99,7 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
         const cf32* tab = reinterpret_cast<const cf32*>(p.twiddle);
         for (int i = tid; i < RF_N; i += STFT_THREADS) s.window[i] = 0.5f * p.window[i];
         for (int i = tid; i < 32 * 32; i += STFT_THREADS) s.tw1[i] = tab[(2 * (i & 31) * (i >> 5)) & (RF_N - 1)];
-        for (int i = tid; i <= RF_M / 2; i += STFT_THREADS) s.tw2[i] = tab[i];
+        for (int i = tid; i < RF_M; i += STFT_THREADS) s.tw2[i] = tab[i];
         if (p.mel != nullptr) {
             for (int i = tid; i < RF_BINS; i += STFT_THREADS) {
                 const float2 rf = reinterpret_cast<const float2*>(p.mel_rise_fall)[i];
@@ -113,8 +114,7 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
     const bool do_fft = (p.mag != nullptr) || (p.mel != nullptr);
     float* const smp = s.samples[g];
     WarpBuf* const gbuf = &s.wb[g * GROUP_WARPS];
-    c2* const xbuf = gbuf[wg].e;
-    p2* const mbuf = reinterpret_cast<p2*>(xbuf);
+    float* const xbuf = gbuf[wg].e;
     float* const rise = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(gbuf[0].e) + MEL_PART_OFFSET);
     float* const fall = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(gbuf[1].e) + MEL_PART_OFFSET);
     const long long tile_step = static_cast<long long>(gridDim.x) * STFT_GROUPS;
@@ -136,20 +136,51 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
         c2 v[32];
         {
             const float* fa = smp + (2 * wg) * hop + 2 * lane;
-            const float* fb = fa + hop;
             const float* wp = s.window + 2 * lane;
-            p2 ssa = p2{0.f, 0.f}, ssb = p2{0.f, 0.f};
+            float sa, sb;
+            if (hop == 512) {
+                // frame B = frame A shifted by 8 x 64 samples: lane reads 40 sample pairs instead of 64, each window
+                // pair once; the sum of squares of the 24 shared pairs is shared too
+                float2 wv[32];
+                p2 head = p2{0.f, 0.f}, mid = p2{0.f, 0.f}, tail = p2{0.f, 0.f};
 #pragma unroll
-            for (int a = 0; a < 32; ++a) {
-                const float2 xa = *reinterpret_cast<const float2*>(fa + 64 * a);
-                const float2 xb = *reinterpret_cast<const float2*>(fb + 64 * a);
-                const float2 w = *reinterpret_cast<const float2*>(wp + 64 * a);
-                ssa = pfma(p2{xa.x, xa.y}, p2{xa.x, xa.y}, ssa);
-                ssb = pfma(p2{xb.x, xb.y}, p2{xb.x, xb.y}, ssb);
-                v[a] = c2{p2{xa.x * w.x, xb.x * w.x}, p2{xa.y * w.y, xb.y * w.y}};
+                for (int a = 0; a < 40; ++a) {
+                    const float2 x = *reinterpret_cast<const float2*>(fa + 64 * a);
+                    const p2 xs = p2{x.x, x.y};
+                    if (a < 8) head = pfma(xs, xs, head);
+                    else if (a < 32) mid = pfma(xs, xs, mid);
+                    else tail = pfma(xs, xs, tail);
+                    if (a < 32) {
+                        wv[a] = *reinterpret_cast<const float2*>(wp + 64 * a);
+                        v[a].re.x = x.x * wv[a].x;
+                        v[a].im.x = x.y * wv[a].y;
+                    }
+                    if (a >= 8) {
+                        v[a - 8].re.y = x.x * wv[a - 8].x;
+                        v[a - 8].im.y = x.y * wv[a - 8].y;
+                    }
+                }
+                const p2 ta = head + mid, tb = mid + tail;
+                sa = ta.x + ta.y;
+                sb = tb.x + tb.y;
+            } else {
+                const float* fb = fa + hop;
+                p2 ssa = p2{0.f, 0.f}, ssb = p2{0.f, 0.f};
+#pragma unroll
+                for (int a = 0; a < 32; ++a) {
+                    const float2 xa = *reinterpret_cast<const float2*>(fa + 64 * a);
+                    const float2 xb = *reinterpret_cast<const float2*>(fb + 64 * a);
+                    const float2 w = *reinterpret_cast<const float2*>(wp + 64 * a);
+                    ssa = pfma(p2{xa.x, xa.y}, p2{xa.x, xa.y}, ssa);
+                    ssb = pfma(p2{xb.x, xb.y}, p2{xb.x, xb.y}, ssb);
+                    v[a] = c2{p2{xa.x * w.x, xb.x * w.x}, p2{xa.y * w.y, xb.y * w.y}};
+                }
+                sa = ssa.x + ssa.y;
+                sb = ssb.x + ssb.y;
             }
             if (p.rms != nullptr) {
-                const float sa = warp_sum(ssa.x + ssa.y), sb = warp_sum(ssb.x + ssb.y);
+                sa = warp_sum(sa);
+                sb = warp_sum(sb);
                 const int t = t0 + 2 * wg + lane;
                 if (lane < 2 && t < T)
                     p.rms[static_cast<long long>(clip) * p.rms_clip_stride + t] = sqrtf((lane == 0 ? sa : sb) * (1.0f / RF_N));
@@ -179,55 +210,50 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
         rfft_pass1(lane, v, s.tw1, xbuf);
         __syncwarp();
         rfft_pass2_load(lane, xbuf, v);
-        __syncwarp();
-        rfft_pass2_store(lane, v, xbuf);
-        __syncwarp();
-        {   // conjugate-pair split -> magnitudes in registers, then over the (now dead) spectrum
-            p2 mk[16], mn[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int k = lane + 32 * i;
-                p2 pk, pn;
-                rfft_split_pair(xbuf[k], xbuf[(RF_M - k) & (RF_M - 1)], s.tw2[k], pk, pn);
-                mk[i] = psqrt(pk);
-                mn[i] = psqrt(pn);
-            }
-            p2 pm, pm_unused;
-            rfft_split_pair(xbuf[RF_M / 2], xbuf[RF_M / 2], s.tw2[RF_M / 2], pm, pm_unused);
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int k = lane + 32 * i;
-                mbuf[k] = mk[i];
-                mbuf[RF_M - k] = mn[i];
-            }
-            if (lane == 0) mbuf[RF_M / 2] = psqrt(pm);
+        __syncwarp();  // the planes are dead: the magnitudes go over them
+        fft32(v);
+        {
+            float* const mcol = xbuf + (lane >> 4);  // p2 mag[k]: word 2k + frame
+            rfft_split_emit(lane, v, s.tw2, [&](int k, float pw) { mcol[2 * k] = sqrt_approx(pw); });
         }
         named_barrier(1 + g, GROUP_THREADS);  // the group's 8 magnitude columns are complete
 
         // ---- 3a. |X| -> HBM, librosa layout
+        const bool full_tile = (t0 + TILE_F <= T);
         if (p.mag != nullptr) {
             float* __restrict__ mo = p.mag + static_cast<long long>(clip) * p.mag_clip_stride + t0;
             const bool vec_store = ((p.mag_row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(mo) & 15) == 0);
             if (vec_store) {  // one float4 (4 frames) per lane, two lanes per spectrogram row
-                for (int idx = gt; idx < 2 * RF_BINS; idx += GROUP_THREADS) {
-                    const int k = idx >> 1, h = idx & 1;
-                    const p2 m0 = reinterpret_cast<const p2*>(gbuf[2 * h].e)[k];
-                    const p2 m1 = reinterpret_cast<const p2*>(gbuf[2 * h + 1].e)[k];
-                    float* dst = mo + static_cast<long long>(k) * p.mag_row_stride + 4 * h;
-                    if (t0 + 4 * h + 3 < T) {
+                const int h = gt & 1, kq = gt >> 1;
+                const p2* m0p = reinterpret_cast<const p2*>(gbuf[2 * h].e) + kq;
+                const p2* m1p = reinterpret_cast<const p2*>(gbuf[2 * h + 1].e) + kq;
+                float* dst = mo + static_cast<long long>(kq) * p.mag_row_stride + 4 * h;
+                const long long dstep = 64LL * p.mag_row_stride;
+                if (full_tile) {
+#pragma unroll 8
+                    for (int it = 0; it < 16; ++it) {
+                        const p2 m0 = m0p[64 * it], m1 = m1p[64 * it];
                         *reinterpret_cast<float4*>(dst) = make_float4(m0.x, m0.y, m1.x, m1.y);
-                    } else {
+                        dst += dstep;
+                    }
+                    if (gt < 2) {
+                        const p2 m0 = m0p[1024], m1 = m1p[1024];
+                        *reinterpret_cast<float4*>(dst) = make_float4(m0.x, m0.y, m1.x, m1.y);
+                    }
+                } else {
+                    for (int k = kq; k < RF_BINS; k += 64) {
+                        const p2 m0 = m0p[k - kq], m1 = m1p[k - kq];
                         const float st[4] = {m0.x, m0.y, m1.x, m1.y};
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             if (t0 + 4 * h + j < T) dst[j] = st[j];
+                        dst += dstep;
                     }
                 }
             } else {          // each warp store = 4 rows x 8 frames
                 const int f = lane & 7;
                 if (t0 + f < T) {
-                    const float* col = reinterpret_cast<const float*>(gbuf[f >> 1].e) + (f & 1);
+                    const float* col = gbuf[f >> 1].e + (f & 1);
                     for (int k = wg * 4 + (lane >> 3); k < RF_BINS; k += GROUP_WARPS * 4)
                         mo[static_cast<long long>(k) * p.mag_row_stride + f] = col[2 * k];
                 }
@@ -238,16 +264,24 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
             {   // lane = (segment slot, warp buffer): a frame pair per lane, packed accumulation
                 const int b4 = lane & 3;
                 const p2* col = reinterpret_cast<const p2*>(gbuf[b4].e);
+                auto body = [&](int k, p2& r, p2& fl) {
+                    const p2 m = col[k];
+                    const float4 w = s.mel_rf[k];
+                    const p2 pw = m * m;
+                    r = pfma(pw, p2{w.x, w.y}, r);
+                    fl = pfma(pw, p2{w.z, w.w}, fl);
+                };
                 for (int j = wg * 8 + (lane >> 2); j <= p.n_mels; j += GROUP_WARPS * 8) {
-                    const int k0 = s.mel_seg[j], k1 = s.mel_seg[j + 1];
+                    int k = s.mel_seg[j];
+                    const int k1 = s.mel_seg[j + 1];
                     p2 r = p2{0.f, 0.f}, fl = p2{0.f, 0.f};
-                    for (int k = k0; k < k1; ++k) {
-                        const p2 m = col[k];
-                        const float4 w = s.mel_rf[k];
-                        const p2 pw = m * m;
-                        r = pfma(pw, p2{w.x, w.y}, r);
-                        fl = pfma(pw, p2{w.z, w.w}, fl);
+                    for (; k + 4 <= k1; k += 4) {
+                        body(k, r, fl);
+                        body(k + 1, r, fl);
+                        body(k + 2, r, fl);
+                        body(k + 3, r, fl);
                     }
+                    for (; k < k1; ++k) body(k, r, fl);
                     *reinterpret_cast<p2*>(&rise[j * TILE_F + 2 * b4]) = r;
                     *reinterpret_cast<p2*>(&fall[j * TILE_F + 2 * b4]) = fl;
                 }
@@ -255,12 +289,25 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
             named_barrier(1 + g, GROUP_THREADS);
             float* __restrict__ me = p.mel + static_cast<long long>(clip) * p.mel_clip_stride + t0;
             float vmax = 0.f;
-            for (int idx = gt; idx < p.n_mels * TILE_F; idx += GROUP_THREADS) {
-                const int b = idx >> 3, f = idx & 7;
-                const float val = rise[b * TILE_F + f] + fall[(b + 1) * TILE_F + f];
-                if (t0 + f < T) {
-                    me[static_cast<long long>(b) * p.mel_row_stride + f] = val;
+            if (full_tile && p.n_mels == MEL_MAX) {
+                const int f = gt & 7;
+                float* dst = me + static_cast<long long>(gt >> 3) * p.mel_row_stride + f;
+                const long long dstep = 16LL * p.mel_row_stride;
+#pragma unroll
+                for (int it = 0; it < MEL_MAX / 16; ++it) {
+                    const float val = rise[gt + 128 * it] + fall[gt + 128 * it + TILE_F];
+                    *dst = val;
+                    dst += dstep;
                     vmax = fmaxf(vmax, val);
+                }
+            } else {
+                for (int idx = gt; idx < p.n_mels * TILE_F; idx += GROUP_THREADS) {
+                    const int b = idx >> 3, f = idx & 7;
+                    const float val = rise[b * TILE_F + f] + fall[(b + 1) * TILE_F + f];
+                    if (t0 + f < T) {
+                        me[static_cast<long long>(b) * p.mel_row_stride + f] = val;
+                        vmax = fmaxf(vmax, val);
+                    }
                 }
             }
             if (p.mel_max != nullptr) {

@@ -11,11 +11,11 @@ using namespace aegis;
 // out: [2][1025] magnitudes of the two frames' spectra (x 2, as the kernel computes before its 1/2 fold)
 extern "C" int emul_rfft2048x2(const float* frames, const float* twiddle, float* out, int reverse_order) {
     const cf32* tab = reinterpret_cast<const cf32*>(twiddle);
-    std::vector<cf32> tw1(32 * 32), tw2(513);
+    std::vector<cf32> tw1(32 * 32), tw2(1024);
     for (int b = 0; b < 32; ++b)
         for (int j = 0; j < 32; ++j) tw1[b * 32 + j] = tab[(2 * j * b) & 2047];
-    for (int k = 0; k <= 512; ++k) tw2[k] = tab[k];
-    std::vector<c2> buf(RF_WARP_BUF);
+    for (int k = 0; k < 1024; ++k) tw2[k] = tab[k];
+    std::vector<float> buf(RF_WARP_WORDS);
     std::vector<c2> regs(32 * 32);
     auto each = [&](auto&& body) {
         if (reverse_order) for (int l = 31; l >= 0; --l) body(l);
@@ -32,25 +32,17 @@ extern "C" int emul_rfft2048x2(const float* frames, const float* twiddle, float*
         rfft_pass1(lane, v, tw1.data(), buf.data());
     });
     each([&](int lane) { rfft_pass2_load(lane, buf.data(), &regs[lane * 32]); });
-    each([&](int lane) { rfft_pass2_store(lane, &regs[lane * 32], buf.data()); });
-    std::vector<p2> mag(1025);
+    std::vector<int> written(2 * 1025, 0);
     each([&](int lane) {
-        for (int i = 0; i < 16; ++i) {
-            const int k = lane + 32 * i;
-            p2 pk, pn;
-            rfft_split_pair(buf[k], buf[(1024 - k) & 1023], tw2[k], pk, pn);
-            mag[k] = p2{std::sqrt(pk.x), std::sqrt(pk.y)};
-            mag[1024 - k] = p2{std::sqrt(pn.x), std::sqrt(pn.y)};
-        }
-        if (lane == 0) {
-            p2 pk, pn;
-            rfft_split_pair(buf[512], buf[512], tw2[512], pk, pn);
-            mag[512] = p2{std::sqrt(pk.x), std::sqrt(pk.y)};
-        }
+        c2* v = &regs[lane * 32];
+        fft32(v);
+        const int h = lane >> 4;
+        rfft_split_emit(lane, v, tw2.data(), [&](int k, float pw) {
+            out[h * 1025 + k] = std::sqrt(pw);
+            written[h * 1025 + k] += 1;
+        });
     });
-    for (int k = 0; k <= 1024; ++k) {
-        out[k] = mag[k].x;
-        out[1025 + k] = mag[k].y;
-    }
+    for (int i = 0; i < 2 * 1025; ++i)
+        if (written[i] != 1) return 1 + i;  // every bin of both frames exactly once
     return 0;
 }

@@ -56,7 +56,7 @@ def remul(tmp_path_factory):
 
 @pytest.mark.parametrize("reverse", [0, 1])
 def test_packed_real_fft_matches_numpy(remul, reverse):
-    """csrc/rfft2048x2.cuh (two frames per warp, 32 x 32 complex transform + conjugate-pair split)."""
+    """csrc/rfft2048x2.cuh (two frames per warp, 32 x 32 complex transform + in-register conjugate-pair split)."""
     rng = np.random.default_rng(1)
     tw = tables.fft_twiddles()
     for trial in range(4):
@@ -70,8 +70,9 @@ def test_packed_real_fft_matches_numpy(remul, reverse):
         if trial == 3:
             fr[0] *= 1e-4     # a quiet frame keeps its relative accuracy next to a loud one
         out = np.zeros((2, 1025), np.float32)
-        remul.emul_rfft2048x2(fr.ctypes.data_as(ctypes.c_void_p), tw.ctypes.data_as(ctypes.c_void_p),
-                              out.ctypes.data_as(ctypes.c_void_p), reverse)
+        rc = remul.emul_rfft2048x2(fr.ctypes.data_as(ctypes.c_void_p), tw.ctypes.data_as(ctypes.c_void_p),
+                                   out.ctypes.data_as(ctypes.c_void_p), reverse)
+        assert rc == 0, f"bin {rc - 1} not written exactly once"
         ref = 2.0 * np.abs(np.fft.rfft(fr.astype(np.float64), axis=1))
         for f in range(2):
             assert np.abs(out[f] - ref[f]).max() <= 4e-7 * max(np.abs(ref[f]).max(), 1e-30), (trial, f)
