@@ -148,40 +148,44 @@ AEGIS_HD void fft32(c2* v) {
     for (int k1 = 0; k1 < 4; ++k1) r8(v + 8 * k1);
 }
 
-// ---- shared-memory geometry of one warp's exchange buffer --------------------------------------
+// ---- shared-memory geometry of one warp's exchange area ----------------------------------------
 constexpr int RF_N = 2048;             // real frame length
 constexpr int RF_M = 1024;             // complex transform length
 constexpr int RF_BINS = RF_N / 2 + 1;  // 1025
 constexpr int RF_XPITCH = 33;          // exchange rows of 32 words (+1 pad): conflict-free 32-bit stores and loads
 constexpr int RF_PLANE = 32 * RF_XPITCH;           // words per (frame, re|im) plane
-// planes: [A re][A im][16 words][B re][B im]; frame B sits 16 banks after frame A so that the two half-warps of
-// pass 2 (lanes 0-15 frame A, lanes 16-31 frame B, 16 consecutive words each) never collide
-constexpr int RF_FRAME_B = 2 * RF_PLANE + 16;
-constexpr int RF_WARP_WORDS = RF_FRAME_B + 2 * RF_PLANE;  // 4240 words
+// The exchange runs in two rounds (real parts, then imaginary parts) through [A plane][16 words][B plane]; frame B
+// sits 16 banks after frame A so that the two half-warps of pass 2 (lanes 0-15 frame A, lanes 16-31 frame B,
+// 16 consecutive words each) never collide.
+constexpr int RF_FRAME_B = RF_PLANE + 16;
+constexpr int RF_XCHG_WORDS = RF_FRAME_B + RF_PLANE;  // 2128 words
 
 struct alignas(8) cf32 {
     float x, y;
 };
 
 // pass 1: v[a] holds z[lane + 32a] of both frames.  tw1[b * 32 + lane] = W1024^{lane * b}.
-// Element (lane, b) of frame A / B goes to its frame's re and im planes at [lane][b].
-AEGIS_HD void rfft_pass1(int lane, c2* v, const cf32* tw1, float* xbuf) {
+// Leaves element (lane, b) of both frames in v[rpos32(b)].
+AEGIS_HD void rfft_pass1(int lane, c2* v, const cf32* tw1) {
     fft32(v);
+#pragma unroll
+    for (int b = 1; b < 32; ++b) {
+        const c2 y = v[rpos32(b)];
+        const cf32 w = tw1[b * 32 + lane];
+        const p2 wr = psplat(w.x), wi = psplat(w.y);
+        v[rpos32(b)] = c2{pfma(y.re, wr, -(y.im * wi)), pfma(y.re, wi, y.im * wr)};
+    }
+}
+
+// one exchange round, store side: the real (IM = false) or imaginary parts of element (lane, b) -> [lane][b]
+template <bool IM>
+AEGIS_HD void rfft_xstore(int lane, const c2* v, float* xbuf) {
     float* const row = xbuf + lane * RF_XPITCH;
 #pragma unroll
     for (int b = 0; b < 32; ++b) {
-        c2 y = v[rpos32(b)];
-        if (b) {
-            const cf32 w = tw1[b * 32 + lane];
-            const p2 wr = psplat(w.x), wi = psplat(w.y);
-            const p2 re = pfma(y.re, wr, -(y.im * wi));
-            const p2 im = pfma(y.re, wi, y.im * wr);
-            y = c2{re, im};
-        }
-        row[b] = y.re.x;
-        row[RF_PLANE + b] = y.im.x;
-        row[RF_FRAME_B + b] = y.re.y;
-        row[RF_FRAME_B + RF_PLANE + b] = y.im.y;
+        const p2 y = IM ? v[rpos32(b)].im : v[rpos32(b)].re;
+        row[b] = y.x;
+        row[RF_FRAME_B + b] = y.y;
     }
 }
 
@@ -192,13 +196,13 @@ AEGIS_HD void rfft_pass1(int lane, c2* v, const cf32* tw1, float* xbuf) {
 // split needs no further exchange.
 AEGIS_HD constexpr int rfft_col1(int q) { return q ? 32 - q : 16; }
 
-AEGIS_HD void rfft_pass2_load(int lane, const float* xbuf, c2* v) {
+// one exchange round, load side: out[j] = (element (j, column q), element (j, column col1)) of this half-warp's frame
+AEGIS_HD void rfft_xload(int lane, const float* xbuf, p2* out) {
     const int h = lane >> 4, q = lane & 15;
     const float* const p0 = xbuf + h * RF_FRAME_B + q;
     const float* const p1 = xbuf + h * RF_FRAME_B + rfft_col1(q);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-        v[j] = c2{p2{p0[j * RF_XPITCH], p1[j * RF_XPITCH]}, p2{p0[RF_PLANE + j * RF_XPITCH], p1[RF_PLANE + j * RF_XPITCH]}};
+    for (int j = 0; j < 32; ++j) out[j] = p2{p0[j * RF_XPITCH], p1[j * RF_XPITCH]};
 }
 
 // Split one conjugate pair (scalars of one frame): from Z[k] = (kr, ki), Z[1024-k] = (nr, ni) and W2048^k to the

@@ -4,22 +4,22 @@
 // aegis_engine.py:25,70 and aegis_engine_financial.py:46-50,154 (see include/aegis_b200.h).
 //
 // The kernel is bound by FP32 lanes, issue slots and shared-memory bandwidth together (SURVEY H3:
-// ~9 FLOP per HBM byte), so the design minimises all three per frame:
+// ~9 FLOP per HBM byte), so the design minimises all three per frame and keeps them busy at once:
 //   * one WARP transforms TWO frames at once in packed f32x2 arithmetic (rfft2048x2.cuh): half the
 //     issue slots of scalar code, no cross-talk between the frames, no pre-scaling;
 //   * each frame is ONE 1024-point complex transform (even/odd packing) done as 32 x 32 in
 //     registers with a single exchange through shared memory, inside the warp (no CTA barrier);
-//   * window, twiddles and mel weights are read once per frame PAIR.
-// Work unit ("tile") = 8 consecutive frames of one clip = 4 warps ("group").  One persistent CTA per
-// SM holds two groups that run out of phase: while one streams its magnitudes to HBM and projects
-// them on the mel triangles, the other transforms.  Per tile and group:
-//   1. (7*hop + 2048) samples in shared memory (cp.async prefetch issued during the previous tile;
-//      zeros outside the clip = centre padding)
-//   2. each warp: samples * window -> registers (sum of squares for the RMS on the way), pass 1,
-//      exchange, pass 2, Z -> shared, conjugate-pair split, |X| for its two frames -> shared
-//   3. the group writes |X| in librosa's [1025, T] layout, one 32-byte sector (8 frames) per row,
-//      and reduces |X|^2 over the mel triangles (each bin read once: rise/fall partial sums per
-//      band-edge segment).
+//     pass 2 packs a column with its conjugate-partner column, so the real-spectrum split is done
+//     in registers;
+//   * window, twiddles and mel weights are read once per frame PAIR; with hop 512 the two frames
+//     share 3/4 of their sample loads;
+//   * warp specialisation: one persistent CTA per SM = two COMPUTE groups (4 warps each, 232
+//     registers, one 8-frame tile of one clip at a time, running out of phase) + one STORE group
+//     (4 warps, 40 registers) that streams finished magnitudes to HBM in librosa's [1025, T] layout
+//     (one 32-byte sector = 8 frames per row) and reduces |X|^2 over the mel triangles (each bin
+//     read once: rise / fall partial sums per band-edge segment) while the compute groups are
+//     already transforming their next tiles.  Producer / consumer hand-over with named barriers
+//     (bar.arrive / bar.sync), registers rebalanced with setmaxnreg.
 // HBM traffic per frame: hop*4 B read (+ halo, L2-served) and 1025*4 B written.
 #include "common.cuh"
 #include "rfft2048x2.cuh"
@@ -29,24 +29,34 @@ namespace aegis {
 constexpr int TILE_F = 8;
 constexpr int GROUP_WARPS = TILE_F / 2;
 constexpr int GROUP_THREADS = GROUP_WARPS * 32;            // 128
-constexpr int STFT_GROUPS = 2;
-constexpr int STFT_THREADS = STFT_GROUPS * GROUP_THREADS;  // 256
+constexpr int STFT_GROUPS = 2;                             // compute groups
+constexpr int COMPUTE_THREADS = STFT_GROUPS * GROUP_THREADS;
+constexpr int STFT_THREADS = COMPUTE_THREADS + GROUP_THREADS;  // + the store group = 384
 constexpr int MAX_HOP = 512;
 constexpr int SAMPLES_MAX = (TILE_F - 1) * MAX_HOP + RF_N;  // 5632
 constexpr int MEL_MAX = 128;
 constexpr int MEL_PART = (MEL_MAX + 1) * TILE_F;            // floats per rise / fall partial array
+constexpr int REGS_COMPUTE = 232, REGS_STORE = 40;
+static_assert(COMPUTE_THREADS * REGS_COMPUTE + GROUP_THREADS * REGS_STORE <= STFT_THREADS * 168, "setmaxnreg trades registers inside the pool the CTA was launched with (168 per thread)");
 
-// One warp's exchange buffer (re / im planes of its two frames, rfft2048x2.cuh).  After pass 2 has loaded them the
-// same memory holds the warp's two magnitude columns as p2 mag[1025] (8200 B) and, above MEL_PART_OFFSET, one of
-// the group's mel partial-sum arrays.  The tail pads the stride to 8 banks (mod 32): the 8 frames of one bin sit
-// in 8 distinct banks.
+// named barriers (0 is __syncthreads)
+constexpr int BAR_FULL = 1;     // + g: compute group g arrives, store group waits   (magnitudes of a tile are complete)
+constexpr int BAR_EMPTY = 3;    // + g: store group arrives, compute group g waits   (magnitudes have been consumed)
+constexpr int BAR_GROUP = 5;    // + g: among the 128 threads of compute group g
+constexpr int BAR_STORE = 7;    // among the 128 threads of the store group
+
+__device__ __forceinline__ void bar_arrive(int id, int n_threads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+
+// One compute warp's shared memory: the exchange area of its transforms and the magnitude columns of its two frames
+// (p2 mag[k] = frames A, B).  Separate areas: the store group reads a tile's magnitudes while the warp already
+// exchanges the next tile.  The stride is 8 banks (mod 32): the 8 frames of one bin sit in 8 distinct banks.
 struct alignas(16) WarpBuf {
-    float e[RF_WARP_WORDS];
-    float skew[24];
+    float x[RF_XCHG_WORDS];
+    float mag[2 * RF_BINS + 22];
 };
-static_assert((sizeof(WarpBuf) / 4) % 32 == 8, "consecutive warp buffers must be skewed by 8 banks");
-constexpr int MEL_PART_OFFSET = 8448;  // bytes; >= 1025 * 8
-static_assert(MEL_PART_OFFSET >= RF_BINS * 8 && MEL_PART_OFFSET + MEL_PART * 4 <= RF_WARP_WORDS * 4, "mel partials alias the warp buffer");
+static_assert((sizeof(WarpBuf) / 4) % 32 == 8 && sizeof(WarpBuf) % 16 == 0, "consecutive warp buffers must be skewed by 8 banks");
 
 struct StftSmem {
     WarpBuf wb[STFT_GROUPS * GROUP_WARPS];
@@ -54,7 +64,8 @@ struct StftSmem {
     float window[RF_N];              // 0.5 * analysis window (the split produces 2 X)
     cf32 tw1[32 * 32];               // [b][lane] W1024^{lane b}
     cf32 tw2[RF_M];                  // W2048^k
-    float4 mel_rf[RF_BINS];          // (rise, rise, fall, fall) weight of every FFT bin
+    float2 mel_rf[RF_BINS];          // (rise, fall) weight of every FFT bin
+    float rise[MEL_PART], fall[MEL_PART];
     int mel_seg[MEL_MAX + 2];        // first bin of every segment between mel band edges
 };
 static_assert(sizeof(StftSmem) <= 227 * 1024, "shared memory budget of one SM");
@@ -65,7 +76,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 
 // synchronous tile fill with bounds checks (clip edges, unaligned rows)
 __device__ __forceinline__ void fill_samples(float* smp, const float* __restrict__ yc, long long g0, long long N, int n_buf, int gt) {
@@ -85,54 +95,60 @@ __device__ __forceinline__ void fill_samples(float* smp, const float* __restrict
     }
 }
 
-__global__ void __launch_bounds__(STFT_THREADS, 1)
-stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const long long n_tiles) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int g = tid >> 7, gt = tid & 127, lane = tid & 31, wg = gt >> 5;
+// Tiles are dealt round-robin: tile = first + i * step.  (clip, tile-in-clip) advance without divisions.
+struct TileWalk {
+    int clip, tin;          // current tile = clip * tiles_per_clip + tin
+    int step_clip, step_tin, tiles_per_clip;
+    __device__ TileWalk(long long first, long long step, int tpc) {
+        tiles_per_clip = tpc;
+        clip = static_cast<int>(first / tpc);
+        tin = static_cast<int>(first - static_cast<long long>(clip) * tpc);
+        step_clip = static_cast<int>(step / tpc);
+        step_tin = static_cast<int>(step - static_cast<long long>(step_clip) * tpc);
+    }
+    __device__ __forceinline__ void next(int& c, int& t) const {  // the tile after (c, t)
+        c += step_clip;
+        t += step_tin;
+        if (t >= tiles_per_clip) {
+            t -= tiles_per_clip;
+            ++c;
+        }
+    }
+    __device__ __forceinline__ void advance() { next(clip, tin); }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// compute group: samples -> windowed frame pair -> two real transforms -> |X| columns in shared memory
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void compute_group(const aegis_stft_params& p, StftSmem& s, const int g, const int gt,
+                                              const int tiles_per_clip, const long long n_tiles) {
+    const int lane = gt & 31, wg = gt >> 5;
     const int T = p.n_frames;
     const int hop = p.hop;
     const long long N = p.n_samples;
-
-    {   // constant tables (once per CTA)
-        const cf32* tab = reinterpret_cast<const cf32*>(p.twiddle);
-        for (int i = tid; i < RF_N; i += STFT_THREADS) s.window[i] = 0.5f * p.window[i];
-        for (int i = tid; i < 32 * 32; i += STFT_THREADS) s.tw1[i] = tab[(2 * (i & 31) * (i >> 5)) & (RF_N - 1)];
-        for (int i = tid; i < RF_M; i += STFT_THREADS) s.tw2[i] = tab[i];
-        if (p.mel != nullptr) {
-            for (int i = tid; i < RF_BINS; i += STFT_THREADS) {
-                const float2 rf = reinterpret_cast<const float2*>(p.mel_rise_fall)[i];
-                s.mel_rf[i] = make_float4(rf.x, rf.x, rf.y, rf.y);
-            }
-            for (int i = tid; i < p.n_mels + 2; i += STFT_THREADS) s.mel_seg[i] = p.mel_seg_start[i];
-        }
-    }
-    __syncthreads();
-
     const int n_buf = (TILE_F - 1) * hop + RF_N;
     const bool do_fft = (p.mag != nullptr) || (p.mel != nullptr);
     float* const smp = s.samples[g];
-    WarpBuf* const gbuf = &s.wb[g * GROUP_WARPS];
-    float* const xbuf = gbuf[wg].e;
-    float* const rise = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(gbuf[0].e) + MEL_PART_OFFSET);
-    float* const fall = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(gbuf[1].e) + MEL_PART_OFFSET);
+    WarpBuf& wb = s.wb[g * GROUP_WARPS + wg];
     const long long tile_step = static_cast<long long>(gridDim.x) * STFT_GROUPS;
+    const long long first = static_cast<long long>(blockIdx.x) * STFT_GROUPS + g;
+    TileWalk walk(first < n_tiles ? first : 0, tile_step, tiles_per_clip);
     bool prefetched = false;  // this tile's samples were requested with cp.async during the previous tile
+    bool handed_over = false; // a tile's magnitudes are with the store group
 
-    for (long long tile = static_cast<long long>(blockIdx.x) * STFT_GROUPS + g; tile < n_tiles; tile += tile_step) {
-        const int clip = static_cast<int>(tile / tiles_per_clip);
-        const int t0 = static_cast<int>(tile - static_cast<long long>(clip) * tiles_per_clip) * TILE_F;
-        const float* __restrict__ yc = p.y + static_cast<long long>(clip) * p.clip_stride;
+    for (long long tile = first; tile < n_tiles; tile += tile_step, walk.advance()) {
+        const int clip = walk.clip;
+        const int t0 = walk.tin * TILE_F;
 
         if (prefetched) cp_async_wait_all();
-        named_barrier(1 + g, GROUP_THREADS);  // previous tile's buffers are free; prefetched samples will be complete
+        named_barrier(BAR_GROUP + g, GROUP_THREADS);  // prefetched samples are complete and visible
         if (!prefetched) {
+            const float* __restrict__ yc = p.y + static_cast<long long>(clip) * p.clip_stride;
             fill_samples(smp, yc, static_cast<long long>(t0) * hop - p.pad, N, n_buf, gt);
-            named_barrier(1 + g, GROUP_THREADS);
+            named_barrier(BAR_GROUP + g, GROUP_THREADS);
         }
 
-        // ---- 2a. this warp's frame pair -> registers (windowed), sums of squares for the RMS
+        // ---- this warp's frame pair -> registers (windowed), sums of squares for the RMS
         c2 v[32];
         {
             const float* fa = smp + (2 * wg) * hop + 2 * lane;
@@ -187,18 +203,18 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
             }
         }
         // every warp of the group has read its samples: request the next tile's samples now, so their DRAM latency
-        // hides behind the transforms, the stores and the mel projection of this tile
-        named_barrier(1 + g, GROUP_THREADS);
+        // hides behind the transforms of this tile
+        named_barrier(BAR_GROUP + g, GROUP_THREADS);
         {
             prefetched = false;
-            const long long nt = tile + tile_step;
-            if (nt < n_tiles) {
-                const int nclip = static_cast<int>(nt / tiles_per_clip);
-                const int nt0 = static_cast<int>(nt - static_cast<long long>(nclip) * tiles_per_clip) * TILE_F;
+            if (tile + tile_step < n_tiles) {
+                int nclip = clip, ntin = walk.tin;
+                walk.next(nclip, ntin);
                 const float* nyc = p.y + static_cast<long long>(nclip) * p.clip_stride;
-                const long long ng0 = static_cast<long long>(nt0) * hop - p.pad;
+                const long long ng0 = static_cast<long long>(ntin) * TILE_F * hop - p.pad;
                 if (ng0 >= 0 && ng0 + n_buf <= N && ((ng0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(nyc) & 15) == 0)) {
-                    for (int i = gt * 4; i < n_buf; i += GROUP_THREADS * 4) cp_async16(&smp[i], nyc + ng0 + i);
+                    const float* src = nyc + ng0;
+                    for (int i = gt * 4; i < n_buf; i += GROUP_THREADS * 4) cp_async16(&smp[i], src + i);
                     prefetched = true;
                 }
             }
@@ -206,117 +222,186 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
         }
         if (!do_fft) continue;  // RMS-only call (librosa.feature.rms)
 
-        // ---- 2b. two real 2048-point transforms, inside the warp
-        rfft_pass1(lane, v, s.tw1, xbuf);
+        // ---- two real 2048-point transforms, inside the warp; the exchange in two rounds (re, im)
+        rfft_pass1(lane, v, s.tw1);
+        rfft_xstore<false>(lane, v, wb.x);
         __syncwarp();
-        rfft_pass2_load(lane, xbuf, v);
-        __syncwarp();  // the planes are dead: the magnitudes go over them
-        fft32(v);
+        p2 nre[32];
+        rfft_xload(lane, wb.x, nre);
+        __syncwarp();
+        rfft_xstore<true>(lane, v, wb.x);
+        __syncwarp();
         {
-            float* const mcol = xbuf + (lane >> 4);  // p2 mag[k]: word 2k + frame
+            p2 nim[32];
+            rfft_xload(lane, wb.x, nim);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = c2{nre[j], nim[j]};
+        }
+        fft32(v);
+        // the store group must have consumed the previous tile's magnitudes before they are overwritten
+        if (handed_over) named_barrier(BAR_EMPTY + g, 2 * GROUP_THREADS);
+        {
+            float* const mcol = wb.mag + (lane >> 4);  // p2 mag[k]: word 2k + frame
             rfft_split_emit(lane, v, s.tw2, [&](int k, float pw) { mcol[2 * k] = sqrt_approx(pw); });
         }
-        named_barrier(1 + g, GROUP_THREADS);  // the group's 8 magnitude columns are complete
+        bar_arrive(BAR_FULL + g, 2 * GROUP_THREADS);
+        handed_over = true;
+    }
+    cp_async_wait_all();
+    if (handed_over) named_barrier(BAR_EMPTY + g, 2 * GROUP_THREADS);  // pairs with the store group's last arrive
+}
 
-        // ---- 3a. |X| -> HBM, librosa layout
-        const bool full_tile = (t0 + TILE_F <= T);
-        if (p.mag != nullptr) {
-            float* __restrict__ mo = p.mag + static_cast<long long>(clip) * p.mag_clip_stride + t0;
-            const bool vec_store = ((p.mag_row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(mo) & 15) == 0);
-            if (vec_store) {  // one float4 (4 frames) per lane, two lanes per spectrogram row
-                const int h = gt & 1, kq = gt >> 1;
-                const p2* m0p = reinterpret_cast<const p2*>(gbuf[2 * h].e) + kq;
-                const p2* m1p = reinterpret_cast<const p2*>(gbuf[2 * h + 1].e) + kq;
-                float* dst = mo + static_cast<long long>(kq) * p.mag_row_stride + 4 * h;
-                const long long dstep = 64LL * p.mag_row_stride;
-                if (full_tile) {
-#pragma unroll 8
-                    for (int it = 0; it < 16; ++it) {
-                        const p2 m0 = m0p[64 * it], m1 = m1p[64 * it];
-                        *reinterpret_cast<float4*>(dst) = make_float4(m0.x, m0.y, m1.x, m1.y);
-                        dst += dstep;
-                    }
-                    if (gt < 2) {
-                        const p2 m0 = m0p[1024], m1 = m1p[1024];
-                        *reinterpret_cast<float4*>(dst) = make_float4(m0.x, m0.y, m1.x, m1.y);
-                    }
-                } else {
-                    for (int k = kq; k < RF_BINS; k += 64) {
-                        const p2 m0 = m0p[k - kq], m1 = m1p[k - kq];
-                        const float st[4] = {m0.x, m0.y, m1.x, m1.y};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (t0 + 4 * h + j < T) dst[j] = st[j];
-                        dst += dstep;
-                    }
-                }
-            } else {          // each warp store = 4 rows x 8 frames
-                const int f = lane & 7;
-                if (t0 + f < T) {
-                    const float* col = gbuf[f >> 1].e + (f & 1);
-                    for (int k = wg * 4 + (lane >> 3); k < RF_BINS; k += GROUP_WARPS * 4)
-                        mo[static_cast<long long>(k) * p.mag_row_stride + f] = col[2 * k];
-                }
-            }
-        }
-        // ---- 3b. mel[b] = sum_{k in seg b} rise[k] |X_k|^2 + sum_{k in seg b+1} fall[k] |X_k|^2
-        if (p.mel != nullptr) {
-            {   // lane = (segment slot, warp buffer): a frame pair per lane, packed accumulation
-                const int b4 = lane & 3;
-                const p2* col = reinterpret_cast<const p2*>(gbuf[b4].e);
-                auto body = [&](int k, p2& r, p2& fl) {
-                    const p2 m = col[k];
-                    const float4 w = s.mel_rf[k];
-                    const p2 pw = m * m;
-                    r = pfma(pw, p2{w.x, w.y}, r);
-                    fl = pfma(pw, p2{w.z, w.w}, fl);
-                };
-                for (int j = wg * 8 + (lane >> 2); j <= p.n_mels; j += GROUP_WARPS * 8) {
-                    int k = s.mel_seg[j];
-                    const int k1 = s.mel_seg[j + 1];
-                    p2 r = p2{0.f, 0.f}, fl = p2{0.f, 0.f};
-                    for (; k + 4 <= k1; k += 4) {
-                        body(k, r, fl);
-                        body(k + 1, r, fl);
-                        body(k + 2, r, fl);
-                        body(k + 3, r, fl);
-                    }
-                    for (; k < k1; ++k) body(k, r, fl);
-                    *reinterpret_cast<p2*>(&rise[j * TILE_F + 2 * b4]) = r;
-                    *reinterpret_cast<p2*>(&fall[j * TILE_F + 2 * b4]) = fl;
-                }
-            }
-            named_barrier(1 + g, GROUP_THREADS);
-            float* __restrict__ me = p.mel + static_cast<long long>(clip) * p.mel_clip_stride + t0;
-            float vmax = 0.f;
-            if (full_tile && p.n_mels == MEL_MAX) {
-                const int f = gt & 7;
-                float* dst = me + static_cast<long long>(gt >> 3) * p.mel_row_stride + f;
-                const long long dstep = 16LL * p.mel_row_stride;
-#pragma unroll
-                for (int it = 0; it < MEL_MAX / 16; ++it) {
-                    const float val = rise[gt + 128 * it] + fall[gt + 128 * it + TILE_F];
-                    *dst = val;
+// ------------------------------------------------------------------------------------------------------------
+// store group: |X| columns of a finished tile -> HBM, mel projection
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_tile(const aegis_stft_params& p, StftSmem& s, const int g, const int gt, const int clip, const int t0) {
+    const int lane = gt & 31, wg = gt >> 5;
+    const int T = p.n_frames;
+    const WarpBuf* gbuf = &s.wb[g * GROUP_WARPS];
+    const bool full_tile = (t0 + TILE_F <= T);
+    if (p.mag != nullptr) {
+        float* __restrict__ mo = p.mag + static_cast<long long>(clip) * p.mag_clip_stride + t0;
+        const bool vec_store = ((p.mag_row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(mo) & 15) == 0);
+        if (vec_store) {  // one float4 (4 frames) per lane, two lanes per spectrogram row
+            const int h = gt & 1, kq = gt >> 1;
+            const p2* m0p = reinterpret_cast<const p2*>(gbuf[2 * h].mag) + kq;
+            const p2* m1p = reinterpret_cast<const p2*>(gbuf[2 * h + 1].mag) + kq;
+            float* dst = mo + static_cast<long long>(kq) * p.mag_row_stride + 4 * h;
+            const long long dstep = 64LL * p.mag_row_stride;
+            if (full_tile) {
+#pragma unroll 4
+                for (int it = 0; it < 16; ++it) {
+                    const p2 m0 = m0p[64 * it], m1 = m1p[64 * it];
+                    *reinterpret_cast<float4*>(dst) = make_float4(m0.x, m0.y, m1.x, m1.y);
                     dst += dstep;
-                    vmax = fmaxf(vmax, val);
+                }
+                if (gt < 2) {
+                    const p2 m0 = m0p[1024], m1 = m1p[1024];
+                    *reinterpret_cast<float4*>(dst) = make_float4(m0.x, m0.y, m1.x, m1.y);
                 }
             } else {
-                for (int idx = gt; idx < p.n_mels * TILE_F; idx += GROUP_THREADS) {
-                    const int b = idx >> 3, f = idx & 7;
-                    const float val = rise[b * TILE_F + f] + fall[(b + 1) * TILE_F + f];
-                    if (t0 + f < T) {
-                        me[static_cast<long long>(b) * p.mel_row_stride + f] = val;
-                        vmax = fmaxf(vmax, val);
-                    }
+                for (int k = kq; k < RF_BINS; k += 64) {
+                    const p2 m0 = m0p[k - kq], m1 = m1p[k - kq];
+                    const float st[4] = {m0.x, m0.y, m1.x, m1.y};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (t0 + 4 * h + j < T) dst[j] = st[j];
+                    dst += dstep;
                 }
             }
-            if (p.mel_max != nullptr) {
-                vmax = warp_max(vmax);
-                if (lane == 0) atomic_max_nonneg(p.mel_max + clip, vmax);
+        } else {          // each warp store = 4 rows x 8 frames
+            const int f = lane & 7;
+            if (t0 + f < T) {
+                const float* col = gbuf[f >> 1].mag + (f & 1);
+                for (int k = wg * 4 + (lane >> 3); k < RF_BINS; k += GROUP_WARPS * 4)
+                    mo[static_cast<long long>(k) * p.mag_row_stride + f] = col[2 * k];
             }
         }
     }
-    cp_async_wait_all();
+    if (p.mel == nullptr) {
+        bar_arrive(BAR_EMPTY + g, 2 * GROUP_THREADS);
+        return;
+    }
+    // mel[b] = sum_{k in seg b} rise[k] |X_k|^2 + sum_{k in seg b+1} fall[k] |X_k|^2
+    {   // lane = (segment slot, warp buffer): a frame pair per lane
+        const int b4 = lane & 3;
+        const p2* col = reinterpret_cast<const p2*>(gbuf[b4].mag);
+        auto body = [&](int k, p2& r, p2& fl) {
+            const p2 m = col[k];
+            const float2 w = s.mel_rf[k];
+            const p2 pw = m * m;
+            r = p2{fmaf(pw.x, w.x, r.x), fmaf(pw.y, w.x, r.y)};
+            fl = p2{fmaf(pw.x, w.y, fl.x), fmaf(pw.y, w.y, fl.y)};
+        };
+        for (int j = wg * 8 + (lane >> 2); j <= p.n_mels; j += GROUP_WARPS * 8) {
+            int k = s.mel_seg[j];
+            const int k1 = s.mel_seg[j + 1];
+            p2 r = p2{0.f, 0.f}, fl = p2{0.f, 0.f};
+            for (; k + 4 <= k1; k += 4) {
+                body(k, r, fl);
+                body(k + 1, r, fl);
+                body(k + 2, r, fl);
+                body(k + 3, r, fl);
+            }
+            for (; k < k1; ++k) body(k, r, fl);
+            *reinterpret_cast<p2*>(&s.rise[j * TILE_F + 2 * b4]) = r;
+            *reinterpret_cast<p2*>(&s.fall[j * TILE_F + 2 * b4]) = fl;
+        }
+    }
+    bar_arrive(BAR_EMPTY + g, 2 * GROUP_THREADS);   // the magnitudes are consumed: the compute group may overwrite them
+    named_barrier(BAR_STORE, GROUP_THREADS);        // partial sums complete
+    float* __restrict__ me = p.mel + static_cast<long long>(clip) * p.mel_clip_stride + t0;
+    float vmax = 0.f;
+    if (full_tile && p.n_mels == MEL_MAX) {
+        const int f = gt & 7;
+        float* dst = me + static_cast<long long>(gt >> 3) * p.mel_row_stride + f;
+        const long long dstep = 16LL * p.mel_row_stride;
+#pragma unroll
+        for (int it = 0; it < MEL_MAX / 16; ++it) {
+            const float val = s.rise[gt + 128 * it] + s.fall[gt + 128 * it + TILE_F];
+            *dst = val;
+            dst += dstep;
+            vmax = fmaxf(vmax, val);
+        }
+    } else {
+        for (int idx = gt; idx < p.n_mels * TILE_F; idx += GROUP_THREADS) {
+            const int b = idx >> 3, f = idx & 7;
+            const float val = s.rise[b * TILE_F + f] + s.fall[(b + 1) * TILE_F + f];
+            if (t0 + f < T) {
+                me[static_cast<long long>(b) * p.mel_row_stride + f] = val;
+                vmax = fmaxf(vmax, val);
+            }
+        }
+    }
+    if (p.mel_max != nullptr) {
+        vmax = warp_max(vmax);
+        if (lane == 0) atomic_max_nonneg(p.mel_max + clip, vmax);
+    }
+    named_barrier(BAR_STORE, GROUP_THREADS);        // partial sums are free for the next tile
+}
+
+__device__ __forceinline__ void store_group(const aegis_stft_params& p, StftSmem& s, const int gt,
+                                            const int tiles_per_clip, const long long n_tiles) {
+    if (p.mag == nullptr && p.mel == nullptr) return;
+    const long long tile_step = static_cast<long long>(gridDim.x) * STFT_GROUPS;
+    const long long first = static_cast<long long>(blockIdx.x) * STFT_GROUPS;
+    TileWalk w0(first < n_tiles ? first : 0, tile_step, tiles_per_clip);
+    TileWalk w1(first + 1 < n_tiles ? first + 1 : 0, tile_step, tiles_per_clip);
+    for (long long tile = first; tile < n_tiles; tile += tile_step) {  // the two compute groups finish tiles alternately
+        named_barrier(BAR_FULL + 0, 2 * GROUP_THREADS);
+        store_tile(p, s, 0, gt, w0.clip, w0.tin * TILE_F);
+        w0.advance();
+        if (tile + 1 < n_tiles) {
+            named_barrier(BAR_FULL + 1, 2 * GROUP_THREADS);
+            store_tile(p, s, 1, gt, w1.clip, w1.tin * TILE_F);
+            w1.advance();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(STFT_THREADS, 1)
+stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const long long n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    {   // constant tables (once per CTA)
+        const cf32* tab = reinterpret_cast<const cf32*>(p.twiddle);
+        for (int i = tid; i < RF_N; i += STFT_THREADS) s.window[i] = 0.5f * p.window[i];
+        for (int i = tid; i < 32 * 32; i += STFT_THREADS) s.tw1[i] = tab[(2 * (i & 31) * (i >> 5)) & (RF_N - 1)];
+        for (int i = tid; i < RF_M; i += STFT_THREADS) s.tw2[i] = tab[i];
+        if (p.mel != nullptr) {
+            for (int i = tid; i < RF_BINS; i += STFT_THREADS) s.mel_rf[i] = reinterpret_cast<const float2*>(p.mel_rise_fall)[i];
+            for (int i = tid; i < p.n_mels + 2; i += STFT_THREADS) s.mel_seg[i] = p.mel_seg_start[i];
+        }
+    }
+    __syncthreads();
+    if (tid < COMPUTE_THREADS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_COMPUTE));
+        compute_group(p, s, tid >> 7, tid & 127, tiles_per_clip, n_tiles);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_STORE));
+        store_group(p, s, tid & 127, tiles_per_clip, n_tiles);
+    }
 }
 
 }  // namespace aegis

@@ -15,7 +15,8 @@ extern "C" int emul_rfft2048x2(const float* frames, const float* twiddle, float*
     for (int b = 0; b < 32; ++b)
         for (int j = 0; j < 32; ++j) tw1[b * 32 + j] = tab[(2 * j * b) & 2047];
     for (int k = 0; k < 1024; ++k) tw2[k] = tab[k];
-    std::vector<float> buf(RF_WARP_WORDS);
+    std::vector<float> buf(RF_XCHG_WORDS);
+    std::vector<p2> nre(32 * 32);
     std::vector<c2> regs(32 * 32);
     auto each = [&](auto&& body) {
         if (reverse_order) for (int l = 31; l >= 0; --l) body(l);
@@ -29,9 +30,17 @@ extern "C" int emul_rfft2048x2(const float* frames, const float* twiddle, float*
             const int m = lane + 32 * a;
             v[a] = c2{p2{fa[2 * m], fb[2 * m]}, p2{fa[2 * m + 1], fb[2 * m + 1]}};
         }
-        rfft_pass1(lane, v, tw1.data(), buf.data());
+        rfft_pass1(lane, v, tw1.data());
+        rfft_xstore<false>(lane, v, buf.data());
     });
-    each([&](int lane) { rfft_pass2_load(lane, buf.data(), &regs[lane * 32]); });
+    each([&](int lane) { rfft_xload(lane, buf.data(), &nre[lane * 32]); });
+    each([&](int lane) { rfft_xstore<true>(lane, &regs[lane * 32], buf.data()); });
+    each([&](int lane) {
+        c2* v = &regs[lane * 32];
+        p2 nim[32];
+        rfft_xload(lane, buf.data(), nim);
+        for (int j = 0; j < 32; ++j) v[j] = c2{nre[lane * 32 + j], nim[j]};
+    });
     std::vector<int> written(2 * 1025, 0);
     each([&](int lane) {
         c2* v = &regs[lane * 32];
