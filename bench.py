@@ -193,7 +193,7 @@ def run_gpu(args):
     torch.cuda.synchronize()
     log(f"[rank {rank}] corpus: {N_CLIPS} clips x {CLIP_SECONDS:.0f} s rendered in {time.perf_counter() - t0:.1f} s")
 
-    mag = torch.empty((N_CLIPS, 1025, T), dtype=torch.float32, device=dev)
+    mag = core.alloc_frames((N_CLIPS, 1025), T, dev)  # rows on 32-byte sector boundaries
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stft_ms = []
 

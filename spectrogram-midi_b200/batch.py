@@ -112,7 +112,7 @@ class HostPipeline:
         self.chunk = min(chunk_clips, n_clips)
         self.T = core.frame_count(n_samples, hop_length)
         self.inbuf = [torch.empty((self.chunk, n_samples), dtype=torch.float32, device=self.dev) for _ in range(2)]
-        self.mag = torch.empty((self.chunk, core.N_BINS, self.T), dtype=torch.float32, device=self.dev)
+        self.mag = core.alloc_frames((self.chunk, core.N_BINS), self.T, self.dev)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.in_ready = [torch.cuda.Event() for _ in range(2)]
         self.in_free = [torch.cuda.Event() for _ in range(2)]

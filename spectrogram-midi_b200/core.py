@@ -63,6 +63,19 @@ def frame_count(n_samples: int, hop_length: int, center: bool = True) -> int:
     return 1 + (n_samples - N_FFT) // hop_length if n_samples >= N_FFT else 0
 
 
+def frame_pitch(n_frames: int) -> int:
+    """Row pitch (in frames) of per-frame images in HBM: rows start on 32-byte sector boundaries, so the 8-frame
+    row chunks the STFT kernel writes are whole sectors (a dense [.., T] row pitch costs ~20 % more DRAM traffic
+    when T % 8 != 0: measured with ncu, profiles/r1_stft_notes.md)."""
+    return (int(n_frames) + 7) // 8 * 8
+
+
+def alloc_frames(shape_prefix, n_frames: int, device, dtype=torch.float32) -> torch.Tensor:
+    """[*shape_prefix, n_frames] view of a buffer whose rows are ``frame_pitch(n_frames)`` apart."""
+    full = torch.empty((*shape_prefix, frame_pitch(n_frames)), dtype=dtype, device=device)
+    return full[..., :n_frames]
+
+
 def _check_fft(n_fft: int, hop_length: int):
     if n_fft != N_FFT:
         raise NotImplementedError(f"n_fft/frame_length={n_fft}: the B200 kernels are built for 2048 (aegis_engine.py:17)")
@@ -80,7 +93,8 @@ def stft_features(y: torch.Tensor, *, sr: Optional[float] = None, hop_length: in
     """Fused STFT magnitude / mel power / RMS of a batch of clips.
 
     Returns a dict with the requested keys: ``mag`` [n_clips, 1025, T], ``mel`` [n_clips, n_mels, T],
-    ``mel_max`` [n_clips], ``rms`` [n_clips, T] (all float32, librosa layouts).  ``pad`` / ``n_frames``
+    ``mel_max`` [n_clips], ``rms`` [n_clips, T] (all float32, librosa layouts; ``mag`` / ``mel`` are views whose rows
+    start on 32-byte boundaries, see ``frame_pitch``).  ``pad`` / ``n_frames``
     override the framing (frame t covers samples [t*hop - pad, t*hop - pad + 2048)): used when ``y`` is a
     window cut out of a longer recording (``distributed.analyze_long_clip``).
     """
@@ -96,7 +110,7 @@ def stft_features(y: torch.Tensor, *, sr: Optional[float] = None, hop_length: in
     P.window = _dev_tensor("hann32", dev, lambda: tables.hann_window().astype(np.float32)).data_ptr()
     P.twiddle = _dev_tensor("twiddle", dev, tables.fft_twiddles).data_ptr()
     if want_mag:
-        mag = mag_out if mag_out is not None else torch.empty((n_clips, N_BINS, T), dtype=torch.float32, device=dev)
+        mag = mag_out if mag_out is not None else alloc_frames((n_clips, N_BINS), T, dev)
         if mag.shape != (n_clips, N_BINS, T) or mag.dtype != torch.float32 or mag.stride(2) != 1 and T > 1:
             raise ValueError("mag_out must be float32 [n_clips, 1025, T] with unit stride along T")
         P.mag, P.mag_clip_stride, P.mag_row_stride = mag.data_ptr(), mag.stride(0), mag.stride(1)
@@ -108,7 +122,7 @@ def stft_features(y: torch.Tensor, *, sr: Optional[float] = None, hop_length: in
         key = ("mel", float(sr), n_mels)
         P.mel_seg_start = _dev_tensor(key + ("seg",), dev, lambda: sm.seg_start).data_ptr()
         P.mel_rise_fall = _dev_tensor(key + ("rf",), dev, lambda: sm.rise_fall).data_ptr()
-        mel = torch.empty((n_clips, n_mels, T), dtype=torch.float32, device=dev)
+        mel = alloc_frames((n_clips, n_mels), T, dev)
         mel_max = torch.zeros((n_clips,), dtype=torch.float32, device=dev)
         P.n_mels = n_mels
         P.mel, P.mel_clip_stride, P.mel_row_stride = mel.data_ptr(), mel.stride(0), mel.stride(1)

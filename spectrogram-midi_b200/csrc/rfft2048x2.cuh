@@ -227,9 +227,17 @@ AEGIS_HD void rfft_split_emit(int lane, const c2* v, const cf32* tw2, Emit&& emi
     const int q = lane & 15;
     const bool sp = (q == 0);
     const int koff = sp ? -496 : 0;  // q == 0, c >= 16: k = 16 + 32 (c - 16)
+    const cf32* const twl = tw2 + q;          // c < 16
+    const cf32* const twh = tw2 + q + koff;   // c >= 16
+    constexpr int AHEAD = 4;                  // twiddles are fetched AHEAD iterations before use (shared-memory latency)
+    cf32 wq[AHEAD];
+#pragma unroll
+    for (int c = 0; c < AHEAD; ++c) wq[c] = twl[32 * c];
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
         const c2 a = v[rpos32(c)], b = v[rpos32(31 - c)];
+        const cf32 w = wq[c % AHEAD];
+        if (c + AHEAD < 32) wq[c % AHEAD] = (c + AHEAD < 16) ? twl[32 * (c + AHEAD)] : twh[32 * (c + AHEAD)];
         float kr, ki, nr, ni;
         int k;
         if (c < 16) {
@@ -248,7 +256,7 @@ AEGIS_HD void rfft_split_emit(int lane, const c2* v, const cf32* tw2, Emit&& emi
             k = q + 32 * c + koff;
         }
         float pk, pn;
-        rfft_split_pair(kr, ki, nr, ni, tw2[k], pk, pn);
+        rfft_split_pair(kr, ki, nr, ni, w, pk, pn);
         emit(k, pk);
         emit(RF_M - k, pn);
     }

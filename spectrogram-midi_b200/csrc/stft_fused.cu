@@ -36,7 +36,7 @@ constexpr int MAX_HOP = 512;
 constexpr int SAMPLES_MAX = (TILE_F - 1) * MAX_HOP + RF_N;  // 5632
 constexpr int MEL_MAX = 128;
 constexpr int MEL_PART = (MEL_MAX + 1) * TILE_F;            // floats per rise / fall partial array
-constexpr int REGS_COMPUTE = 232, REGS_STORE = 40;
+constexpr int REGS_COMPUTE = 224, REGS_STORE = 56;
 static_assert(COMPUTE_THREADS * REGS_COMPUTE + GROUP_THREADS * REGS_STORE <= STFT_THREADS * 168, "setmaxnreg trades registers inside the pool the CTA was launched with (168 per thread)");
 
 // named barriers (0 is __syncthreads)
@@ -157,23 +157,38 @@ __device__ __forceinline__ void compute_group(const aegis_stft_params& p, StftSm
             if (hop == 512) {
                 // frame B = frame A shifted by 8 x 64 samples: lane reads 40 sample pairs instead of 64, each window
                 // pair once; the sum of squares of the 24 shared pairs is shared too
-                float2 wv[32];
+                // loads are issued one block of 8 register indices ahead of their use (shared-memory latency)
+                float2 xv[40], wv[32];
                 p2 head = p2{0.f, 0.f}, mid = p2{0.f, 0.f}, tail = p2{0.f, 0.f};
 #pragma unroll
-                for (int a = 0; a < 40; ++a) {
-                    const float2 x = *reinterpret_cast<const float2*>(fa + 64 * a);
-                    const p2 xs = p2{x.x, x.y};
-                    if (a < 8) head = pfma(xs, xs, head);
-                    else if (a < 32) mid = pfma(xs, xs, mid);
-                    else tail = pfma(xs, xs, tail);
-                    if (a < 32) {
-                        wv[a] = *reinterpret_cast<const float2*>(wp + 64 * a);
-                        v[a].re.x = x.x * wv[a].x;
-                        v[a].im.x = x.y * wv[a].y;
+                for (int a = 0; a < 8; ++a) {
+                    xv[a] = *reinterpret_cast<const float2*>(fa + 64 * a);
+                    wv[a] = *reinterpret_cast<const float2*>(wp + 64 * a);
+                }
+#pragma unroll
+                for (int blk = 0; blk < 5; ++blk) {
+                    if (blk < 4) {
+#pragma unroll
+                        for (int a = 8 * blk + 8; a < 8 * blk + 16; ++a) {
+                            xv[a] = *reinterpret_cast<const float2*>(fa + 64 * a);
+                            if (a < 32) wv[a] = *reinterpret_cast<const float2*>(wp + 64 * a);
+                        }
                     }
-                    if (a >= 8) {
-                        v[a - 8].re.y = x.x * wv[a - 8].x;
-                        v[a - 8].im.y = x.y * wv[a - 8].y;
+#pragma unroll
+                    for (int a = 8 * blk; a < 8 * blk + 8; ++a) {
+                        const float2 x = xv[a];
+                        const p2 xs = p2{x.x, x.y};
+                        if (a < 8) head = pfma(xs, xs, head);
+                        else if (a < 32) mid = pfma(xs, xs, mid);
+                        else tail = pfma(xs, xs, tail);
+                        if (a < 32) {
+                            v[a].re.x = x.x * wv[a].x;
+                            v[a].im.x = x.y * wv[a].y;
+                        }
+                        if (a >= 8) {
+                            v[a - 8].re.y = x.x * wv[a - 8].x;
+                            v[a - 8].im.y = x.y * wv[a - 8].y;
+                        }
                     }
                 }
                 const p2 ta = head + mid, tb = mid + tail;
@@ -254,79 +269,120 @@ __device__ __forceinline__ void compute_group(const aegis_stft_params& p, StftSm
 // ------------------------------------------------------------------------------------------------------------
 // store group: |X| columns of a finished tile -> HBM, mel projection
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_tile(const aegis_stft_params& p, StftSmem& s, const int g, const int gt, const int clip, const int t0) {
+// |X| only (no mel projection requested): one float4 (4 frames) per lane, two lanes per spectrogram row
+__device__ __forceinline__ void store_mag_only(const aegis_stft_params& p, const WarpBuf* gbuf, const int gt, const int clip, const int t0) {
     const int lane = gt & 31, wg = gt >> 5;
     const int T = p.n_frames;
-    const WarpBuf* gbuf = &s.wb[g * GROUP_WARPS];
-    const bool full_tile = (t0 + TILE_F <= T);
-    if (p.mag != nullptr) {
-        float* __restrict__ mo = p.mag + static_cast<long long>(clip) * p.mag_clip_stride + t0;
-        const bool vec_store = ((p.mag_row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(mo) & 15) == 0);
-        if (vec_store) {  // one float4 (4 frames) per lane, two lanes per spectrogram row
-            const int h = gt & 1, kq = gt >> 1;
-            const p2* m0p = reinterpret_cast<const p2*>(gbuf[2 * h].mag) + kq;
-            const p2* m1p = reinterpret_cast<const p2*>(gbuf[2 * h + 1].mag) + kq;
-            float* dst = mo + static_cast<long long>(kq) * p.mag_row_stride + 4 * h;
-            const long long dstep = 64LL * p.mag_row_stride;
-            if (full_tile) {
-#pragma unroll 4
-                for (int it = 0; it < 16; ++it) {
-                    const p2 m0 = m0p[64 * it], m1 = m1p[64 * it];
-                    *reinterpret_cast<float4*>(dst) = make_float4(m0.x, m0.y, m1.x, m1.y);
-                    dst += dstep;
-                }
-                if (gt < 2) {
-                    const p2 m0 = m0p[1024], m1 = m1p[1024];
-                    *reinterpret_cast<float4*>(dst) = make_float4(m0.x, m0.y, m1.x, m1.y);
-                }
+    float* __restrict__ mo = p.mag + static_cast<long long>(clip) * p.mag_clip_stride + t0;
+    const bool vec_store = ((p.mag_row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(mo) & 15) == 0);
+    if (vec_store) {
+        const int h = gt & 1, kq = gt >> 1;
+        const p2* m0p = reinterpret_cast<const p2*>(gbuf[2 * h].mag);
+        const p2* m1p = reinterpret_cast<const p2*>(gbuf[2 * h + 1].mag);
+        float* dst = mo + static_cast<long long>(kq) * p.mag_row_stride + 4 * h;
+        const long long dstep = 64LL * p.mag_row_stride;
+        for (int k = kq; k < RF_BINS; k += 64) {
+            const p2 m0 = m0p[k], m1 = m1p[k];
+            if (t0 + 4 * h + 3 < T) {
+                *reinterpret_cast<float4*>(dst) = make_float4(m0.x, m0.y, m1.x, m1.y);
             } else {
-                for (int k = kq; k < RF_BINS; k += 64) {
-                    const p2 m0 = m0p[k - kq], m1 = m1p[k - kq];
-                    const float st[4] = {m0.x, m0.y, m1.x, m1.y};
+                const float st[4] = {m0.x, m0.y, m1.x, m1.y};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (t0 + 4 * h + j < T) dst[j] = st[j];
-                    dst += dstep;
-                }
+                for (int j = 0; j < 4; ++j)
+                    if (t0 + 4 * h + j < T) dst[j] = st[j];
             }
-        } else {          // each warp store = 4 rows x 8 frames
-            const int f = lane & 7;
-            if (t0 + f < T) {
-                const float* col = gbuf[f >> 1].mag + (f & 1);
-                for (int k = wg * 4 + (lane >> 3); k < RF_BINS; k += GROUP_WARPS * 4)
-                    mo[static_cast<long long>(k) * p.mag_row_stride + f] = col[2 * k];
-            }
+            dst += dstep;
+        }
+    } else {          // each warp store = 4 rows x 8 frames
+        const int f = lane & 7;
+        if (t0 + f < T) {
+            const float* col = gbuf[f >> 1].mag + (f & 1);
+            for (int k = wg * 4 + (lane >> 3); k < RF_BINS; k += GROUP_WARPS * 4)
+                mo[static_cast<long long>(k) * p.mag_row_stride + f] = col[2 * k];
         }
     }
+}
+
+// One pass over the tile's magnitudes: every (bin, frame pair) is read from shared memory ONCE, written to HBM and
+// accumulated into the rise / fall partial sums of its mel segment.  lane = (segment slot, frame pair): the four
+// lanes of a slot write one 32-byte sector of a spectrogram row.
+// MODE 0: no |X| output; 1: 8-byte stores (full tile, even row stride, aligned base); 2: guarded scalar stores.
+template <int MODE>
+__device__ __forceinline__ void store_mel_pass(const aegis_stft_params& p, StftSmem& s, const WarpBuf* gbuf, const int gt,
+                                               float* __restrict__ mo, const int frames_left) {
+    const int lane = gt & 31, wg = gt >> 5;
+    const int b4 = lane & 3;
+    const p2* col = reinterpret_cast<const p2*>(gbuf[b4].mag);
+    const long long rs = p.mag_row_stride;
+    float* const dcol = mo + 2 * b4;
+    const bool ok0 = 2 * b4 < frames_left, ok1 = 2 * b4 + 1 < frames_left;
+    auto put = [&](int k, p2 m) {
+        if (MODE == 1) {
+            *reinterpret_cast<p2*>(dcol + k * rs) = m;
+        } else if (MODE == 2) {
+            if (ok0) dcol[k * rs] = m.x;
+            if (ok1) dcol[k * rs + 1] = m.y;
+        }
+    };
+    auto acc = [&](p2 m, float2 w, p2& r, p2& fl) {
+        const p2 pw = m * m;
+        r = p2{fmaf(pw.x, w.x, r.x), fmaf(pw.y, w.x, r.y)};
+        fl = p2{fmaf(pw.x, w.y, fl.x), fmaf(pw.y, w.y, fl.y)};
+    };
+    for (int j = wg * 8 + (lane >> 2); j <= p.n_mels; j += GROUP_WARPS * 8) {
+        int k = s.mel_seg[j];
+        const int k1 = s.mel_seg[j + 1];
+        p2 r = p2{0.f, 0.f}, fl = p2{0.f, 0.f};
+        for (; k + 4 <= k1; k += 4) {   // all eight loads first: one shared-memory latency per four bins
+            const p2 m0 = col[k], m1 = col[k + 1], m2 = col[k + 2], m3 = col[k + 3];
+            const float2 w0 = s.mel_rf[k], w1 = s.mel_rf[k + 1], w2 = s.mel_rf[k + 2], w3 = s.mel_rf[k + 3];
+            put(k, m0);
+            put(k + 1, m1);
+            put(k + 2, m2);
+            put(k + 3, m3);
+            acc(m0, w0, r, fl);
+            acc(m1, w1, r, fl);
+            acc(m2, w2, r, fl);
+            acc(m3, w3, r, fl);
+        }
+        if (k < k1) {                   // up to three bins left: predicated, still all loads first
+            const bool h1 = k + 1 < k1, h2 = k + 2 < k1;
+            const p2 m0 = col[k], m1 = col[h1 ? k + 1 : k], m2 = col[h2 ? k + 2 : k];
+            const float2 w0 = s.mel_rf[k];
+            float2 w1 = s.mel_rf[h1 ? k + 1 : k], w2 = s.mel_rf[h2 ? k + 2 : k];
+            if (!h1) w1 = make_float2(0.f, 0.f);
+            if (!h2) w2 = make_float2(0.f, 0.f);
+            put(k, m0);
+            if (h1) put(k + 1, m1);
+            if (h2) put(k + 2, m2);
+            acc(m0, w0, r, fl);
+            acc(m1, w1, r, fl);
+            acc(m2, w2, r, fl);
+        }
+        *reinterpret_cast<p2*>(&s.rise[j * TILE_F + 2 * b4]) = r;
+        *reinterpret_cast<p2*>(&s.fall[j * TILE_F + 2 * b4]) = fl;
+    }
+}
+
+__device__ __forceinline__ void store_tile(const aegis_stft_params& p, StftSmem& s, const int g, const int gt, const int clip, const int t0) {
+    const int lane = gt & 31;
+    const int T = p.n_frames;
+    const WarpBuf* gbuf = &s.wb[g * GROUP_WARPS];
     if (p.mel == nullptr) {
+        store_mag_only(p, gbuf, gt, clip, t0);
         bar_arrive(BAR_EMPTY + g, 2 * GROUP_THREADS);
         return;
     }
+    const bool full_tile = (t0 + TILE_F <= T);
     // mel[b] = sum_{k in seg b} rise[k] |X_k|^2 + sum_{k in seg b+1} fall[k] |X_k|^2
-    {   // lane = (segment slot, warp buffer): a frame pair per lane
-        const int b4 = lane & 3;
-        const p2* col = reinterpret_cast<const p2*>(gbuf[b4].mag);
-        auto body = [&](int k, p2& r, p2& fl) {
-            const p2 m = col[k];
-            const float2 w = s.mel_rf[k];
-            const p2 pw = m * m;
-            r = p2{fmaf(pw.x, w.x, r.x), fmaf(pw.y, w.x, r.y)};
-            fl = p2{fmaf(pw.x, w.y, fl.x), fmaf(pw.y, w.y, fl.y)};
-        };
-        for (int j = wg * 8 + (lane >> 2); j <= p.n_mels; j += GROUP_WARPS * 8) {
-            int k = s.mel_seg[j];
-            const int k1 = s.mel_seg[j + 1];
-            p2 r = p2{0.f, 0.f}, fl = p2{0.f, 0.f};
-            for (; k + 4 <= k1; k += 4) {
-                body(k, r, fl);
-                body(k + 1, r, fl);
-                body(k + 2, r, fl);
-                body(k + 3, r, fl);
-            }
-            for (; k < k1; ++k) body(k, r, fl);
-            *reinterpret_cast<p2*>(&s.rise[j * TILE_F + 2 * b4]) = r;
-            *reinterpret_cast<p2*>(&s.fall[j * TILE_F + 2 * b4]) = fl;
-        }
+    if (p.mag == nullptr) {
+        store_mel_pass<0>(p, s, gbuf, gt, nullptr, 0);
+    } else {
+        float* __restrict__ mo = p.mag + static_cast<long long>(clip) * p.mag_clip_stride + t0;
+        if (full_tile && ((p.mag_row_stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(mo) & 7) == 0))
+            store_mel_pass<1>(p, s, gbuf, gt, mo, TILE_F);
+        else
+            store_mel_pass<2>(p, s, gbuf, gt, mo, T - t0);
     }
     bar_arrive(BAR_EMPTY + g, 2 * GROUP_THREADS);   // the magnitudes are consumed: the compute group may overwrite them
     named_barrier(BAR_STORE, GROUP_THREADS);        // partial sums complete
