@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libaegis_b200.so")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
-NVCC_FLAGS = [
+NVCC_FLAGS = [*os.environ.get("AEGIS_NVCC_EXTRA", "").split(), 
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr", "--extended-lambda",
 ]

@@ -164,10 +164,9 @@ struct alignas(8) cf32 {
     float x, y;
 };
 
-// pass 1: v[a] holds z[lane + 32a] of both frames.  tw1[b * 32 + lane] = W1024^{lane * b}.
-// Leaves element (lane, b) of both frames in v[rpos32(b)].
-AEGIS_HD void rfft_pass1(int lane, c2* v, const cf32* tw1) {
-    fft32(v);
+// pass 1 = fft32 over a (v[a] holds z[lane + 32a] of both frames), then these twiddles:
+// tw1[b * 32 + lane] = W1024^{lane * b}.  Leaves element (lane, b) of both frames in v[rpos32(b)].
+AEGIS_HD void rfft_twiddle1(int lane, c2* v, const cf32* tw1) {
 #pragma unroll
     for (int b = 1; b < 32; ++b) {
         const c2 y = v[rpos32(b)];
@@ -257,14 +256,14 @@ AEGIS_HD void rfft_split_emit(int lane, const c2* v, const cf32* tw2, Emit&& emi
         }
         float pk, pn;
         rfft_split_pair(kr, ki, nr, ni, w, pk, pn);
-        emit(k, pk);
-        emit(RF_M - k, pn);
+        emit(k, pk, true);
+        emit(RF_M - k, pn, false);
     }
     {
         const c2 a = v[rpos32(16)];
         float pk, pn;
         rfft_split_pair(a.re.x, a.im.x, a.re.x, a.im.x, tw2[RF_M / 2], pk, pn);
-        if (sp) emit(RF_M / 2, pk);
+        if (sp) emit(RF_M / 2, pk, true);
     }
 }
 

@@ -21,6 +21,9 @@
 //     already transforming their next tiles.  Producer / consumer hand-over with named barriers
 //     (bar.arrive / bar.sync), registers rebalanced with setmaxnreg.
 // HBM traffic per frame: hop*4 B read (+ halo, L2-served) and 1025*4 B written.
+#include <cstddef>
+#include <cstring>
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include "common.cuh"
 #include "rfft2048x2.cuh"
 
@@ -31,44 +34,52 @@ constexpr int GROUP_WARPS = TILE_F / 2;
 constexpr int GROUP_THREADS = GROUP_WARPS * 32;            // 128
 constexpr int STFT_GROUPS = 2;                             // compute groups
 constexpr int COMPUTE_THREADS = STFT_GROUPS * GROUP_THREADS;
-constexpr int STFT_THREADS = COMPUTE_THREADS + GROUP_THREADS;  // + the store group = 384
+constexpr int STFT_THREADS = 2 * COMPUTE_THREADS;             // + one store group per compute group = 512
 constexpr int MAX_HOP = 512;
 constexpr int SAMPLES_MAX = (TILE_F - 1) * MAX_HOP + RF_N;  // 5632
 constexpr int MEL_MAX = 128;
 constexpr int MEL_PART = (MEL_MAX + 1) * TILE_F;            // floats per rise / fall partial array
-constexpr int REGS_COMPUTE = 224, REGS_STORE = 56;
-static_assert(COMPUTE_THREADS * REGS_COMPUTE + GROUP_THREADS * REGS_STORE <= STFT_THREADS * 168, "setmaxnreg trades registers inside the pool the CTA was launched with (168 per thread)");
+constexpr int REGS_LAUNCH = 65536 / STFT_THREADS;            // 128: what __launch_bounds__(512, 1) gives every thread
+constexpr int REGS_COMPUTE = 184, REGS_STORE = 72;
+static_assert(COMPUTE_THREADS * (REGS_COMPUTE + REGS_STORE) <= STFT_THREADS * REGS_LAUNCH,
+              "setmaxnreg trades registers inside the pool the CTA was launched with");
 
 // named barriers (0 is __syncthreads)
 constexpr int BAR_FULL = 1;     // + g: compute group g arrives, store group waits   (magnitudes of a tile are complete)
 constexpr int BAR_EMPTY = 3;    // + g: store group arrives, compute group g waits   (magnitudes have been consumed)
 constexpr int BAR_GROUP = 5;    // + g: among the 128 threads of compute group g
-constexpr int BAR_STORE = 7;    // among the 128 threads of the store group
+constexpr int BAR_LOCKSTEP = 7; // among the 256 threads of both compute groups
+constexpr int BAR_STORE = 8;    // + g: among the 128 threads of store group g
 
 __device__ __forceinline__ void bar_arrive(int id, int n_threads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
-// One compute warp's shared memory: the exchange area of its transforms and the magnitude columns of its two frames
-// (p2 mag[k] = frames A, B).  Separate areas: the store group reads a tile's magnitudes while the warp already
-// exchanges the next tile.  The stride is 8 banks (mod 32): the 8 frames of one bin sit in 8 distinct banks.
-struct alignas(16) WarpBuf {
-    float x[RF_XCHG_WORDS];
-    float mag[2 * RF_BINS + 22];
-};
-static_assert((sizeof(WarpBuf) / 4) % 32 == 8 && sizeof(WarpBuf) % 16 == 0, "consecutive warp buffers must be skewed by 8 banks");
+// Magnitude stage of one compute group: |X| of the tile as [1025 bins][8 frames], 32 bytes per bin, in the layout
+// of a TMA box with CU_TENSOR_MAP_SWIZZLE_32B: the two 16-byte halves of a row swap when bit 7 of the byte address
+// (= bit 2 of the bin index, the stage being 256-byte aligned) is set.  The compute warps scatter single floats into it
+// (2-way bank conflicts instead of 4-way for the plain layout), the store group reads whole 16-byte halves, and one
+// thread hands the stage to the TMA unit, which writes the [1025, 8] block into librosa's [1025, T] layout by itself.
+constexpr int STAGE_WORDS = RF_BINS * TILE_F;            // 8200
+constexpr int STAGE_BOX_ROWS = 256;                      // TMA box = 8 frames x 256 bins; 5 boxes (the last one clipped)
+__host__ __device__ constexpr int stage_word(int k, int f) { return 8 * k + 4 * ((f >> 2) ^ ((k >> 2) & 1)) + (f & 3); }
 
 struct StftSmem {
-    WarpBuf wb[STFT_GROUPS * GROUP_WARPS];
+    alignas(256) float stage[STFT_GROUPS][STAGE_WORDS + 56];   // 33024 B each: keeps the second stage 256-byte aligned
+    float xchg[STFT_GROUPS * GROUP_WARPS][RF_XCHG_WORDS];      // one exchange area per compute warp
     float samples[STFT_GROUPS][SAMPLES_MAX];
     float window[RF_N];              // 0.5 * analysis window (the split produces 2 X)
     cf32 tw1[32 * 32];               // [b][lane] W1024^{lane b}
     cf32 tw2[RF_M];                  // W2048^k
     float2 mel_rf[RF_BINS];          // (rise, fall) weight of every FFT bin
-    float rise[MEL_PART], fall[MEL_PART];
+    alignas(16) float rise[STFT_GROUPS][MEL_PART];   // per store group
+    alignas(16) float fall[STFT_GROUPS][MEL_PART];
     int mel_seg[MEL_MAX + 2];        // first bin of every segment between mel band edges
 };
 static_assert(sizeof(StftSmem) <= 227 * 1024, "shared memory budget of one SM");
+static_assert(((STAGE_WORDS + 56) * 4) % 256 == 0, "stage alignment");
+// the clipped last TMA box still addresses 256 rows of shared memory: they must lie inside the allocation
+static_assert(offsetof(StftSmem, stage) + sizeof(float) * ((STFT_GROUPS - 1) * (STAGE_WORDS + 56) + (4 * STAGE_BOX_ROWS + STAGE_BOX_ROWS) * TILE_F) <= sizeof(StftSmem), "TMA box overruns shared memory");
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
@@ -129,14 +140,19 @@ __device__ __forceinline__ void compute_group(const aegis_stft_params& p, StftSm
     const int n_buf = (TILE_F - 1) * hop + RF_N;
     const bool do_fft = (p.mag != nullptr) || (p.mel != nullptr);
     float* const smp = s.samples[g];
-    WarpBuf& wb = s.wb[g * GROUP_WARPS + wg];
+    float* const xbuf = s.xchg[g * GROUP_WARPS + wg];
     const long long tile_step = static_cast<long long>(gridDim.x) * STFT_GROUPS;
     const long long first = static_cast<long long>(blockIdx.x) * STFT_GROUPS + g;
     TileWalk walk(first < n_tiles ? first : 0, tile_step, tiles_per_clip);
     bool prefetched = false;  // this tile's samples were requested with cp.async during the previous tile
     bool handed_over = false; // a tile's magnitudes are with the store group
 
-    for (long long tile = first; tile < n_tiles; tile += tile_step, walk.advance()) {
+    // The two compute groups start every tile together (one more barrier): they then run the same instructions at
+    // about the same time, which halves the instruction-cache traffic.  Group 0 never has fewer tiles than group 1;
+    // a group without a tile in the last round still joins the barrier.
+    for (long long tile = first; tile - g < n_tiles; tile += tile_step, walk.advance()) {
+        named_barrier(BAR_LOCKSTEP, COMPUTE_THREADS);
+        if (tile >= n_tiles) break;
         const int clip = walk.clip;
         const int t0 = walk.tin * TILE_F;
 
@@ -238,27 +254,36 @@ __device__ __forceinline__ void compute_group(const aegis_stft_params& p, StftSm
         if (!do_fft) continue;  // RMS-only call (librosa.feature.rms)
 
         // ---- two real 2048-point transforms, inside the warp; the exchange in two rounds (re, im)
-        rfft_pass1(lane, v, s.tw1);
-        rfft_xstore<false>(lane, v, wb.x);
-        __syncwarp();
-        p2 nre[32];
-        rfft_xload(lane, wb.x, nre);
-        __syncwarp();
-        rfft_xstore<true>(lane, v, wb.x);
-        __syncwarp();
-        {
-            p2 nim[32];
-            rfft_xload(lane, wb.x, nim);
+        // (the two 32-point passes share one copy of the butterfly code: the hot loop has to fit the 32 KB L1.5
+        // instruction cache together with the store group's loop, ncu: stall_no_instruction)
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            fft32(v);
+            if (pass == 0) {
+                rfft_twiddle1(lane, v, s.tw1);
+                rfft_xstore<false>(lane, v, xbuf);
+                __syncwarp();
+                p2 nre[32];
+                rfft_xload(lane, xbuf, nre);
+                __syncwarp();
+                rfft_xstore<true>(lane, v, xbuf);
+                __syncwarp();
+                p2 nim[32];
+                rfft_xload(lane, xbuf, nim);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = c2{nre[j], nim[j]};
+                for (int j = 0; j < 32; ++j) v[j] = c2{nre[j], nim[j]};
+            }
         }
-        fft32(v);
         // the store group must have consumed the previous tile's magnitudes before they are overwritten
         if (handed_over) named_barrier(BAR_EMPTY + g, 2 * GROUP_THREADS);
-        {
-            float* const mcol = wb.mag + (lane >> 4);  // p2 mag[k]: word 2k + frame
-            rfft_split_emit(lane, v, s.tw2, [&](int k, float pw) { mcol[2 * k] = sqrt_approx(pw); });
+        {   // this thread's frame is f = 2 wg + (lane >> 4); bins k = q + 32c and 1024 - k (rfft_split_emit): the swizzle
+            // bit (bin >> 2) & 1 is the same for all of a thread's "k" bins and for all of its "1024 - k" bins
+            const int f = 2 * wg + (lane >> 4), q = lane & 15;
+            float* const st = s.stage[g];
+            const int off_k = stage_word(q, f) - 8 * q, off_n = stage_word(RF_M - q, f) - 8 * (RF_M - q);
+            rfft_split_emit(lane, v, s.tw2, [&](int k, float pw, bool is_k) { st[8 * k + (is_k ? off_k : off_n)] = sqrt_approx(pw); });
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the TMA unit (async proxy) reads these writes
         bar_arrive(BAR_FULL + g, 2 * GROUP_THREADS);
         handed_over = true;
     }
@@ -269,123 +294,108 @@ __device__ __forceinline__ void compute_group(const aegis_stft_params& p, StftSm
 // ------------------------------------------------------------------------------------------------------------
 // store group: |X| columns of a finished tile -> HBM, mel projection
 // ------------------------------------------------------------------------------------------------------------
-// |X| only (no mel projection requested): one float4 (4 frames) per lane, two lanes per spectrogram row
-__device__ __forceinline__ void store_mag_only(const aegis_stft_params& p, const WarpBuf* gbuf, const int gt, const int clip, const int t0) {
-    const int lane = gt & 31, wg = gt >> 5;
+// |X| of a finished tile -> HBM without the TMA unit (row pitch or base address not 16-byte aligned, or no tensor map):
+// one 16-byte half row (4 frames) per lane, two lanes per spectrogram row
+__device__ __forceinline__ void store_mag_lsu(const aegis_stft_params& p, const float* st, const int gt, const int clip, const int t0) {
     const int T = p.n_frames;
     float* __restrict__ mo = p.mag + static_cast<long long>(clip) * p.mag_clip_stride + t0;
     const bool vec_store = ((p.mag_row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(mo) & 15) == 0);
-    if (vec_store) {
-        const int h = gt & 1, kq = gt >> 1;
-        const p2* m0p = reinterpret_cast<const p2*>(gbuf[2 * h].mag);
-        const p2* m1p = reinterpret_cast<const p2*>(gbuf[2 * h + 1].mag);
-        float* dst = mo + static_cast<long long>(kq) * p.mag_row_stride + 4 * h;
-        const long long dstep = 64LL * p.mag_row_stride;
-        for (int k = kq; k < RF_BINS; k += 64) {
-            const p2 m0 = m0p[k], m1 = m1p[k];
-            if (t0 + 4 * h + 3 < T) {
-                *reinterpret_cast<float4*>(dst) = make_float4(m0.x, m0.y, m1.x, m1.y);
-            } else {
-                const float st[4] = {m0.x, m0.y, m1.x, m1.y};
+    const int h = gt & 1;
+    float* dst = mo + static_cast<long long>(gt >> 1) * p.mag_row_stride + 4 * h;
+    const long long dstep = 64LL * p.mag_row_stride;
+    for (int k = gt >> 1; k < RF_BINS; k += 64) {
+        const float4 m = *reinterpret_cast<const float4*>(st + stage_word(k, 4 * h));
+        if (vec_store && t0 + 4 * h + 3 < T) {
+            *reinterpret_cast<float4*>(dst) = m;
+        } else {
+            const float mv[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (t0 + 4 * h + j < T) dst[j] = st[j];
-            }
-            dst += dstep;
+            for (int j = 0; j < 4; ++j)
+                if (t0 + 4 * h + j < T) dst[j] = mv[j];
         }
-    } else {          // each warp store = 4 rows x 8 frames
-        const int f = lane & 7;
-        if (t0 + f < T) {
-            const float* col = gbuf[f >> 1].mag + (f & 1);
-            for (int k = wg * 4 + (lane >> 3); k < RF_BINS; k += GROUP_WARPS * 4)
-                mo[static_cast<long long>(k) * p.mag_row_stride + f] = col[2 * k];
-        }
+        dst += dstep;
     }
 }
 
-// One pass over the tile's magnitudes: every (bin, frame pair) is read from shared memory ONCE, written to HBM and
-// accumulated into the rise / fall partial sums of its mel segment.  lane = (segment slot, frame pair): the four
-// lanes of a slot write one 32-byte sector of a spectrogram row.
-// MODE 0: no |X| output; 1: 8-byte stores (full tile, even row stride, aligned base); 2: guarded scalar stores.
-template <int MODE>
-__device__ __forceinline__ void store_mel_pass(const aegis_stft_params& p, StftSmem& s, const WarpBuf* gbuf, const int gt,
-                                               float* __restrict__ mo, const int frames_left) {
-    const int lane = gt & 31, wg = gt >> 5;
-    const int b4 = lane & 3;
-    const p2* col = reinterpret_cast<const p2*>(gbuf[b4].mag);
-    const long long rs = p.mag_row_stride;
-    float* const dcol = mo + 2 * b4;
-    const bool ok0 = 2 * b4 < frames_left, ok1 = 2 * b4 + 1 < frames_left;
-    auto put = [&](int k, p2 m) {
-        if (MODE == 1) {
-            *reinterpret_cast<p2*>(dcol + k * rs) = m;
-        } else if (MODE == 2) {
-            if (ok0) dcol[k * rs] = m.x;
-            if (ok1) dcol[k * rs + 1] = m.y;
-        }
+// rise / fall partial sums of the mel projection: lane = (segment slot, 4-frame half); every (bin, half) is read from
+// the stage once with one 16-byte load
+__device__ __forceinline__ void mel_partials(const aegis_stft_params& p, const StftSmem& s, float* rise, float* fall, const float* st, const int gt) {
+    const int h = gt & 1;
+    // neighbouring lanes take neighbouring segments (similar lengths: little divergence inside a warp)
+    const int slot = gt >> 1;
+    struct q4 { p2 a, b; };   // four frames as two packed pairs
+    auto acc = [&](float4 m, float2 w, q4& r, q4& fl) {
+        const p2 pa = p2{m.x, m.y} * p2{m.x, m.y}, pb = p2{m.z, m.w} * p2{m.z, m.w};
+        r.a = pfma(pa, w.x, r.a);
+        r.b = pfma(pb, w.x, r.b);
+        fl.a = pfma(pa, w.y, fl.a);
+        fl.b = pfma(pb, w.y, fl.b);
     };
-    auto acc = [&](p2 m, float2 w, p2& r, p2& fl) {
-        const p2 pw = m * m;
-        r = p2{fmaf(pw.x, w.x, r.x), fmaf(pw.y, w.x, r.y)};
-        fl = p2{fmaf(pw.x, w.y, fl.x), fmaf(pw.y, w.y, fl.y)};
-    };
-    for (int j = wg * 8 + (lane >> 2); j <= p.n_mels; j += GROUP_WARPS * 8) {
+    auto ld = [&](int k) { return *reinterpret_cast<const float4*>(st + stage_word(k, 4 * h)); };
+    constexpr int NB = 8;   // bins per round: all loads of a round are issued before the first use
+    for (int j = slot; j <= p.n_mels; j += GROUP_THREADS / 2) {
         int k = s.mel_seg[j];
         const int k1 = s.mel_seg[j + 1];
-        p2 r = p2{0.f, 0.f}, fl = p2{0.f, 0.f};
-        for (; k + 4 <= k1; k += 4) {   // all eight loads first: one shared-memory latency per four bins
-            const p2 m0 = col[k], m1 = col[k + 1], m2 = col[k + 2], m3 = col[k + 3];
-            const float2 w0 = s.mel_rf[k], w1 = s.mel_rf[k + 1], w2 = s.mel_rf[k + 2], w3 = s.mel_rf[k + 3];
-            put(k, m0);
-            put(k + 1, m1);
-            put(k + 2, m2);
-            put(k + 3, m3);
-            acc(m0, w0, r, fl);
-            acc(m1, w1, r, fl);
-            acc(m2, w2, r, fl);
-            acc(m3, w3, r, fl);
+        q4 r = q4{p2{0.f, 0.f}, p2{0.f, 0.f}}, fl = r;
+        for (; k + NB <= k1; k += NB) {
+            float4 m[NB];
+            float2 w[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                m[i] = ld(k + i);
+                w[i] = s.mel_rf[k + i];
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) acc(m[i], w[i], r, fl);
         }
-        if (k < k1) {                   // up to three bins left: predicated, still all loads first
-            const bool h1 = k + 1 < k1, h2 = k + 2 < k1;
-            const p2 m0 = col[k], m1 = col[h1 ? k + 1 : k], m2 = col[h2 ? k + 2 : k];
-            const float2 w0 = s.mel_rf[k];
-            float2 w1 = s.mel_rf[h1 ? k + 1 : k], w2 = s.mel_rf[h2 ? k + 2 : k];
-            if (!h1) w1 = make_float2(0.f, 0.f);
-            if (!h2) w2 = make_float2(0.f, 0.f);
-            put(k, m0);
-            if (h1) put(k + 1, m1);
-            if (h2) put(k + 2, m2);
-            acc(m0, w0, r, fl);
-            acc(m1, w1, r, fl);
-            acc(m2, w2, r, fl);
+        if (k < k1) {   // up to NB - 1 bins left: clamped loads, zero weights
+            float4 m[NB - 1];
+            float2 w[NB - 1];
+#pragma unroll
+            for (int i = 0; i < NB - 1; ++i) {
+                const bool in = k + i < k1;
+                const int kk = in ? k + i : k;
+                m[i] = ld(kk);
+                w[i] = s.mel_rf[kk];
+                if (!in) w[i] = make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < NB - 1; ++i) acc(m[i], w[i], r, fl);
         }
-        *reinterpret_cast<p2*>(&s.rise[j * TILE_F + 2 * b4]) = r;
-        *reinterpret_cast<p2*>(&s.fall[j * TILE_F + 2 * b4]) = fl;
+        *reinterpret_cast<float4*>(&rise[j * TILE_F + 4 * h]) = make_float4(r.a.x, r.a.y, r.b.x, r.b.y);
+        *reinterpret_cast<float4*>(&fall[j * TILE_F + 4 * h]) = make_float4(fl.a.x, fl.a.y, fl.b.x, fl.b.y);
     }
 }
 
-__device__ __forceinline__ void store_tile(const aegis_stft_params& p, StftSmem& s, const int g, const int gt, const int clip, const int t0) {
+__device__ __forceinline__ void store_tile(const aegis_stft_params& p, const CUtensorMap* tmap, const bool use_tma, StftSmem& s,
+                                           const int g, const int gt, const int clip, const int t0) {
+    float* const rise = s.rise[g];
+    float* const fall = s.fall[g];
     const int lane = gt & 31;
     const int T = p.n_frames;
-    const WarpBuf* gbuf = &s.wb[g * GROUP_WARPS];
-    if (p.mel == nullptr) {
-        store_mag_only(p, gbuf, gt, clip, t0);
-        bar_arrive(BAR_EMPTY + g, 2 * GROUP_THREADS);
-        return;
+    const float* st = s.stage[g];
+    if (p.mag != nullptr) {
+        if (use_tma) {
+            if (gt == 0) {   // five boxes of 256 bins x 8 frames; frames >= T and bins > 1024 are clipped by the tensor map
+                const unsigned src = static_cast<unsigned>(__cvta_generic_to_shared(st));
+#pragma unroll
+                for (int bx = 0; bx < 5; ++bx)
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                                     reinterpret_cast<unsigned long long>(tmap)),
+                                 "r"(src + bx * STAGE_BOX_ROWS * TILE_F * 4), "r"(t0), "r"(bx * STAGE_BOX_ROWS), "r"(clip)
+                                 : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            store_mag_lsu(p, st, gt, clip, t0);
+        }
     }
-    const bool full_tile = (t0 + TILE_F <= T);
-    // mel[b] = sum_{k in seg b} rise[k] |X_k|^2 + sum_{k in seg b+1} fall[k] |X_k|^2
-    if (p.mag == nullptr) {
-        store_mel_pass<0>(p, s, gbuf, gt, nullptr, 0);
-    } else {
-        float* __restrict__ mo = p.mag + static_cast<long long>(clip) * p.mag_clip_stride + t0;
-        if (full_tile && ((p.mag_row_stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(mo) & 7) == 0))
-            store_mel_pass<1>(p, s, gbuf, gt, mo, TILE_F);
-        else
-            store_mel_pass<2>(p, s, gbuf, gt, mo, T - t0);
-    }
+    if (p.mel != nullptr) mel_partials(p, s, rise, fall, st, gt);
+    if (p.mag != nullptr && use_tma && gt == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // stage has been read
     bar_arrive(BAR_EMPTY + g, 2 * GROUP_THREADS);   // the magnitudes are consumed: the compute group may overwrite them
-    named_barrier(BAR_STORE, GROUP_THREADS);        // partial sums complete
+    if (p.mel == nullptr) return;
+    named_barrier(BAR_STORE + g, GROUP_THREADS);        // partial sums complete (and every thread is done with the other buffer)
+    const bool full_tile = (t0 + TILE_F <= T);
     float* __restrict__ me = p.mel + static_cast<long long>(clip) * p.mel_clip_stride + t0;
     float vmax = 0.f;
     if (full_tile && p.n_mels == MEL_MAX) {
@@ -394,7 +404,7 @@ __device__ __forceinline__ void store_tile(const aegis_stft_params& p, StftSmem&
         const long long dstep = 16LL * p.mel_row_stride;
 #pragma unroll
         for (int it = 0; it < MEL_MAX / 16; ++it) {
-            const float val = s.rise[gt + 128 * it] + s.fall[gt + 128 * it + TILE_F];
+            const float val = rise[gt + 128 * it] + fall[gt + 128 * it + TILE_F];
             *dst = val;
             dst += dstep;
             vmax = fmaxf(vmax, val);
@@ -402,7 +412,7 @@ __device__ __forceinline__ void store_tile(const aegis_stft_params& p, StftSmem&
     } else {
         for (int idx = gt; idx < p.n_mels * TILE_F; idx += GROUP_THREADS) {
             const int b = idx >> 3, f = idx & 7;
-            const float val = s.rise[b * TILE_F + f] + s.fall[(b + 1) * TILE_F + f];
+            const float val = rise[b * TILE_F + f] + fall[(b + 1) * TILE_F + f];
             if (t0 + f < T) {
                 me[static_cast<long long>(b) * p.mel_row_stride + f] = val;
                 vmax = fmaxf(vmax, val);
@@ -413,30 +423,24 @@ __device__ __forceinline__ void store_tile(const aegis_stft_params& p, StftSmem&
         vmax = warp_max(vmax);
         if (lane == 0) atomic_max_nonneg(p.mel_max + clip, vmax);
     }
-    named_barrier(BAR_STORE, GROUP_THREADS);        // partial sums are free for the next tile
+    named_barrier(BAR_STORE + g, GROUP_THREADS);        // partial sums are free for the next tile
 }
 
-__device__ __forceinline__ void store_group(const aegis_stft_params& p, StftSmem& s, const int gt,
-                                            const int tiles_per_clip, const long long n_tiles) {
+__device__ __forceinline__ void store_group(const aegis_stft_params& p, const CUtensorMap* tmap, const bool use_tma, StftSmem& s,
+                                            const int g, const int gt, const int tiles_per_clip, const long long n_tiles) {
     if (p.mag == nullptr && p.mel == nullptr) return;
     const long long tile_step = static_cast<long long>(gridDim.x) * STFT_GROUPS;
-    const long long first = static_cast<long long>(blockIdx.x) * STFT_GROUPS;
-    TileWalk w0(first < n_tiles ? first : 0, tile_step, tiles_per_clip);
-    TileWalk w1(first + 1 < n_tiles ? first + 1 : 0, tile_step, tiles_per_clip);
-    for (long long tile = first; tile < n_tiles; tile += tile_step) {  // the two compute groups finish tiles alternately
-        named_barrier(BAR_FULL + 0, 2 * GROUP_THREADS);
-        store_tile(p, s, 0, gt, w0.clip, w0.tin * TILE_F);
-        w0.advance();
-        if (tile + 1 < n_tiles) {
-            named_barrier(BAR_FULL + 1, 2 * GROUP_THREADS);
-            store_tile(p, s, 1, gt, w1.clip, w1.tin * TILE_F);
-            w1.advance();
-        }
+    const long long first = static_cast<long long>(blockIdx.x) * STFT_GROUPS + g;
+    TileWalk w(first < n_tiles ? first : 0, tile_step, tiles_per_clip);
+    for (long long tile = first; tile < n_tiles; tile += tile_step, w.advance()) {
+        named_barrier(BAR_FULL + g, 2 * GROUP_THREADS);
+        store_tile(p, tmap, use_tma, s, g, gt, w.clip, w.tin * TILE_F);
     }
 }
 
 __global__ void __launch_bounds__(STFT_THREADS, 1)
-stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const long long n_tiles) {
+stft_fused_kernel(const aegis_stft_params p, const __grid_constant__ CUtensorMap mag_map, const int use_tma,
+                  const int tiles_per_clip, const long long n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -456,10 +460,38 @@ stft_fused_kernel(const aegis_stft_params p, const int tiles_per_clip, const lon
         compute_group(p, s, tid >> 7, tid & 127, tiles_per_clip, n_tiles);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_STORE));
-        store_group(p, s, tid & 127, tiles_per_clip, n_tiles);
+        store_group(p, &mag_map, use_tma != 0, s, (tid - COMPUTE_THREADS) >> 7, tid & 127, tiles_per_clip, n_tiles);
     }
 }
 
+}  // namespace aegis
+
+namespace aegis {
+// Tensor map of the |X| output, [n_clips][1025][T] with the caller's row / clip pitch, boxes of 8 frames x 256 bins.
+// Returns false when the layout cannot be described (pitches or base not 16-byte aligned, driver entry point missing):
+// the kernel then stores through the LSU path.
+static bool make_mag_map(const aegis_stft_params* p, CUtensorMap* map) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static bool looked_up = false;
+    if (!looked_up) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<encode_fn>(fn);
+        looked_up = true;
+    }
+    if (encode == nullptr || p->mag == nullptr) return false;
+    if ((reinterpret_cast<uintptr_t>(p->mag) & 15) || (p->mag_row_stride & 3) || (p->mag_clip_stride & 3)) return false;
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(p->n_frames), static_cast<cuuint64_t>(AEGIS_N_BINS), static_cast<cuuint64_t>(p->n_clips)};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(p->mag_row_stride) * 4, static_cast<cuuint64_t>(p->mag_clip_stride) * 4};
+    const cuuint32_t box[3] = {TILE_F, STAGE_BOX_ROWS, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p->mag, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 }  // namespace aegis
 
 extern "C" int aegis_stft_fused(const aegis_stft_params* p, void* stream) {
@@ -490,6 +522,9 @@ extern "C" int aegis_stft_fused(const aegis_stft_params* p, void* stream) {
     const long long ctas_needed = (n_tiles + STFT_GROUPS - 1) / STFT_GROUPS;
     const long long max_grid = sm_count();
     const int grid = static_cast<int>(ctas_needed < max_grid ? ctas_needed : max_grid);
-    stft_fused_kernel<<<grid, STFT_THREADS, sizeof(StftSmem), static_cast<cudaStream_t>(stream)>>>(*p, tiles_per_clip, n_tiles);
+    alignas(64) CUtensorMap mag_map;
+    memset(&mag_map, 0, sizeof(mag_map));
+    const int use_tma = make_mag_map(p, &mag_map) ? 1 : 0;
+    stft_fused_kernel<<<grid, STFT_THREADS, sizeof(StftSmem), static_cast<cudaStream_t>(stream)>>>(*p, mag_map, use_tma, tiles_per_clip, n_tiles);
     return check_launch("aegis_stft_fused");
 }

@@ -30,7 +30,8 @@ extern "C" int emul_rfft2048x2(const float* frames, const float* twiddle, float*
             const int m = lane + 32 * a;
             v[a] = c2{p2{fa[2 * m], fb[2 * m]}, p2{fa[2 * m + 1], fb[2 * m + 1]}};
         }
-        rfft_pass1(lane, v, tw1.data());
+        fft32(v);
+        rfft_twiddle1(lane, v, tw1.data());
         rfft_xstore<false>(lane, v, buf.data());
     });
     each([&](int lane) { rfft_xload(lane, buf.data(), &nre[lane * 32]); });
@@ -46,7 +47,7 @@ extern "C" int emul_rfft2048x2(const float* frames, const float* twiddle, float*
         c2* v = &regs[lane * 32];
         fft32(v);
         const int h = lane >> 4;
-        rfft_split_emit(lane, v, tw2.data(), [&](int k, float pw) {
+        rfft_split_emit(lane, v, tw2.data(), [&](int k, float pw, bool) {
             out[h * 1025 + k] = std::sqrt(pw);
             written[h * 1025 + k] += 1;
         });
