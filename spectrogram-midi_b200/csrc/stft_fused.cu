@@ -13,13 +13,18 @@
 //     in registers;
 //   * window, twiddles and mel weights are read once per frame PAIR; with hop 512 the two frames
 //     share 3/4 of their sample loads;
-//   * warp specialisation: one persistent CTA per SM = two COMPUTE groups (4 warps each, 232
-//     registers, one 8-frame tile of one clip at a time, running out of phase) + one STORE group
-//     (4 warps, 40 registers) that streams finished magnitudes to HBM in librosa's [1025, T] layout
-//     (one 32-byte sector = 8 frames per row) and reduces |X|^2 over the mel triangles (each bin
-//     read once: rise / fall partial sums per band-edge segment) while the compute groups are
-//     already transforming their next tiles.  Producer / consumer hand-over with named barriers
-//     (bar.arrive / bar.sync), registers rebalanced with setmaxnreg.
+//   * warp specialisation: one persistent CTA of 512 threads per SM = two COMPUTE groups (4 warps each, 184
+//     registers, one 8-frame tile of one clip at a time) + two STORE groups (4 warps each, 72 registers), one per
+//     compute group.  A compute group leaves |X| of its tile in a shared-memory stage laid out as a TMA box
+//     (CU_TENSOR_MAP_SWIZZLE_32B) and goes on with its next tile; its store group has the TMA unit write the stage
+//     into librosa's [1025, T] layout (cp.async.bulk.tensor, one thread, no LSU traffic) and meanwhile reduces |X|^2
+//     over the mel triangles (each bin read once: rise / fall partial sums per band-edge segment).  Producer /
+//     consumer hand-over with named barriers (bar.arrive / bar.sync), registers rebalanced with setmaxnreg.
+//   * the hot loop is ~3000 instructions; the two compute groups are kept in step (one barrier per tile) and the two
+//     32-point passes share one copy of the butterfly code, because the instruction cache (32 KB L1.5) was the
+//     limiter once the arithmetic was packed (ncu: stall_no_instruction).
+// What bounds it now (ncu, profiles/): the FP32 pipe during the transform phases (both compute warps of an SM
+// sub-partition in step), shared-memory latency in the store groups.
 // HBM traffic per frame: hop*4 B read (+ halo, L2-served) and 1025*4 B written.
 #include <cstddef>
 #include <cstring>
