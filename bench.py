@@ -263,6 +263,16 @@ def run_gpu(args):
     stft_avg_ms = float(np.mean(stft_ms))
     achieved = alg_bytes / (stft_avg_ms / 1e3) / 1e9
 
+    # DRAM traffic of that kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum from the committed
+    # `ncu --set full` capture of the same launch shape (not re-measured here: no profiler inside a timed run)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_stft_traffic.json")))
+        if N_CLIPS == 1024:
+            traffic = float(tr["dram_bytes_read"]) + float(tr["dram_bytes_write"])
+    except (OSError, KeyError, ValueError):
+        pass
+
     aux = {}
     if rank == 0 and not args.no_pyin:  # cfg3 on the same clips (not the headline; reported for context)
         try:
@@ -312,7 +322,7 @@ def run_gpu(args):
             "config": {"workload": "cfg2: 1024 x 30 s clips @22050 Hz per GPU, STFT |X| + onset strength/peaks + RMS (n_fft 2048, hop 512)",
                        "clips_per_gpu": N_CLIPS, "clip_seconds": CLIP_SECONDS, "sr": SR, "frames_per_clip": T, "sharding": "by clip",
                        "l2": "inputs (2.7 GB) and outputs (5.4 GB) per step exceed the 126 MB L2; no flush needed"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "stft_fused_kernel", "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": stft_avg_ms,
                          "peak_source": peak_src, "share_of_step": stft_avg_ms / (elapsed_ms / args.steps)},
             "cpu_baseline": cpu,
