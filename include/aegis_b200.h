@@ -237,6 +237,41 @@ typedef struct {
 int aegis_trend_filters(const aegis_trend_params* p, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K6  electric-guitar filters on the perception outputs (v2 engine)
+ * replaces: apply_guitar_filters (aegis_engine_core_v2/guitar_specific.py:240-277; caller
+ *           aegis_engine_financial.py:132-147) = filter_subharmonic_noise (:24-61),
+ *           detect_rake_enhanced (:112-151), detect_palm_mute (:63-110), classify_distortion_level
+ *           (:209-233).
+ * Any output may be NULL (skipped).  s_db is only needed for rake_out / mute_out / distortion,
+ * f0 / voiced only for f0_out / voiced_out.  distortion needs the workspace dist_work of
+ * 2 * n_clips * aegis_guitar_blocks(n_frames) doubles.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* s_db;         /* [n_clips][n_mels][sdb_row_stride] mel spectrogram in dB */
+    int64_t sdb_clip_stride;
+    int32_t sdb_row_stride;
+    int32_t n_mels;
+    int32_t n_clips;
+    int32_t n_frames;
+    int32_t mute_max_frames;   /* int(50 / ms_per_frame), <= 30 */
+    int32_t rake_frames;       /* int(30 / ms_per_frame), <= 30 */
+    double fmin_hz;            /* 82.4 in the reference */
+    const double* f0;          /* [n_clips][n_frames], NaN = unvoiced */
+    const uint8_t* voiced;     /* [n_clips][n_frames] */
+    const uint8_t* rake_in;    /* [n_clips][n_frames] basic rake mask (NULL = all zero) */
+    double* f0_out;            /* [n_clips][n_frames] */
+    uint8_t* voiced_out;       /* [n_clips][n_frames] */
+    uint8_t* rake_out;         /* [n_clips][n_frames] enhanced rake mask */
+    uint8_t* mute_out;         /* [n_clips][n_frames] palm-mute mask */
+    int32_t* distortion;       /* [n_clips]: 0 clean, 1 light, 2 heavy */
+    double* dist_work;         /* workspace, see above */
+} aegis_guitar_params;
+
+int aegis_guitar_filters(const aegis_guitar_params* p, void* stream);
+/* column blocks per clip of the K6 launch (sizes dist_work) */
+int aegis_guitar_blocks(int n_frames);
+
+/* ---------------------------------------------------------------------------------------------
  * Corpus synthesis on device (Karplus-Strong plucks + noise rakes, generate_test_signal.py:5-53)
  * One event per note/rake; events of a clip do not overlap.  out must be zero-filled.
  * ------------------------------------------------------------------------------------------- */

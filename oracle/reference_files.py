@@ -357,3 +357,69 @@ def get_midi_events(rake_mask, f0, voiced_flag, active_probs, rms, sr, hop_lengt
 def events_key(events):
     """Integer-exact comparison key of a note-event list (note, start, end, velocity, track, technique)."""
     return [(e["note"], int(e["start"]), int(e["end"]), e["velocity"], e["track"], e.get("technique")) for e in events]
+
+
+# --------------------------------------------------------------------------------------------
+# aegis_engine_core_v2/guitar_specific.py:24-277 (caller: aegis_engine_financial.py:132-147)
+# Pinned by tests/golden/guitar_golden.npz (tests/golden/make_golden_guitar.py runs the real file).
+# --------------------------------------------------------------------------------------------
+def filter_subharmonic_noise(f0, voiced_flag, fmin_hz=82.4):
+    """guitar_specific.py:24-61: below fmin -> NaN / unvoiced, unless the octave above lands in [fmin, 4 fmin)."""
+    f0 = np.asarray(f0, dtype=np.float64)
+    out_f0 = f0.copy()
+    out_v = np.asarray(voiced_flag, dtype=bool).copy()
+    with np.errstate(invalid="ignore"):
+        sub = f0 < fmin_hz                      # NaN compares False: unvoiced frames are left alone
+        corrected = f0 * 2
+        fix = sub & (fmin_hz <= corrected) & (corrected < fmin_hz * 4)
+    out_f0[sub] = np.nan
+    out_v[sub] = False
+    out_f0[fix] = corrected[fix]
+    out_v[fix] = True
+    return out_f0, out_v
+
+
+def palm_mute_columns(S_dB):
+    """guitar_specific.py:84-94: mean dB of the low half > 2 x mean dB of the high half (float32 arithmetic)."""
+    S_dB = np.asarray(S_dB)
+    mid = S_dB.shape[0] // 2
+    low = np.mean(S_dB[:mid, :], axis=0)
+    high = np.mean(S_dB[mid:, :], axis=0)
+    return (low / (high + 1e-6)) > 2.0
+
+
+def detect_palm_mute(S_dB, hop_length, sr, duration_ms=50):
+    """guitar_specific.py:63-110: closed runs of mute columns of at most int(duration_ms / ms_per_frame) frames."""
+    ms_per_frame = (hop_length / sr) * 1000
+    return run_length_gate(palm_mute_columns(S_dB), 0, int(duration_ms / ms_per_frame))
+
+
+def detect_rake_enhanced(S_dB, hop_length, sr, rake_mask_basic):
+    """guitar_specific.py:112-151: a > 10 dB jump of the mean dB whose next `threshold_frames` differences average
+    below zero marks those frames."""
+    S_dB = np.asarray(S_dB)
+    out = np.asarray(rake_mask_basic, dtype=bool).copy()
+    total = np.mean(S_dB, axis=0)
+    diff = np.diff(total, prepend=total[0]) if total.size else total
+    n = int(30 / ((hop_length / sr) * 1000))
+    if n <= 0:
+        return out      # np.mean of an empty slice is NaN: the reference never fires
+    for i in np.flatnonzero(diff > 10):
+        if i >= 1 and i + n < len(diff) and np.mean(diff[i : i + n]) < 0:
+            out[i : i + n] = True
+    return out
+
+
+def classify_distortion_level(S_dB):
+    """guitar_specific.py:209-233."""
+    S_dB = np.asarray(S_dB)
+    high = np.mean(S_dB[int(S_dB.shape[0] * 0.7):, :])
+    ratio = high / (np.mean(S_dB) + 1e-6)
+    return "heavy" if ratio > 0.4 else ("light" if ratio > 0.25 else "clean")
+
+
+def apply_guitar_filters(f0, voiced_flag, S_dB, hop_length, sr, rake_mask):
+    """guitar_specific.py:240-277."""
+    f0f, vf = filter_subharmonic_noise(f0, voiced_flag, fmin_hz=82.4)
+    return {"f0": f0f, "voiced": vf, "rake_mask": detect_rake_enhanced(S_dB, hop_length, sr, rake_mask),
+            "mute_mask": detect_palm_mute(S_dB, hop_length, sr), "distortion": classify_distortion_level(S_dB)}

@@ -98,6 +98,16 @@ class SynthParams(C.Structure):
     ]
 
 
+class GuitarParams(C.Structure):
+    _fields_ = [
+        ("s_db", _ptr), ("sdb_clip_stride", i64), ("sdb_row_stride", i32), ("n_mels", i32),
+        ("n_clips", i32), ("n_frames", i32), ("mute_max_frames", i32), ("rake_frames", i32),
+        ("fmin_hz", f64), ("f0", _ptr), ("voiced", _ptr), ("rake_in", _ptr),
+        ("f0_out", _ptr), ("voiced_out", _ptr), ("rake_out", _ptr), ("mute_out", _ptr),
+        ("distortion", _ptr), ("dist_work", _ptr),
+    ]
+
+
 ENTRY_POINTS = {
     "aegis_stft_fused": StftParams,
     "aegis_mel_post": MelPostParams,
@@ -106,6 +116,7 @@ ENTRY_POINTS = {
     "aegis_viterbi": ViterbiParams,
     "aegis_trend_filters": TrendParams,
     "aegis_synth_ks": SynthParams,
+    "aegis_guitar_filters": GuitarParams,
 }
 
 _lib = None
@@ -128,6 +139,8 @@ def load() -> C.CDLL:
     lib.aegis_abi_version.restype = C.c_int
     lib.aegis_last_error.restype = C.c_char_p
     lib.aegis_device_sm_count.restype = C.c_int
+    lib.aegis_guitar_blocks.restype = C.c_int
+    lib.aegis_guitar_blocks.argtypes = [C.c_int]
     for name, struct in ENTRY_POINTS.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int

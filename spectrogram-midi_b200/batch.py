@@ -52,18 +52,33 @@ def spectral_features(y: torch.Tensor, *, sr: float, hop_length: int = 512, rake
 
 def analyze_batch(y: torch.Tensor, *, sr: float, hop_length: int = 512, rake_sensitivity: float = 0.6,
                   fmin: float = E2, fmax: float = C6, with_sdb: bool = False, with_onsets: bool = False,
-                  with_trend: bool = False, nan_to_num: bool = True, clips_per_launch: Optional[int] = None) -> dict:
+                  with_trend: bool = False, nan_to_num: bool = True, clips_per_launch: Optional[int] = None,
+                  with_guitar: bool = False) -> dict:
     """Full perception phase for a batch: keys of aegis_engine.py:72-75 (+ optional extras).
 
     ``f0`` follows v1 (`np.nan_to_num`, aegis_engine.py:69) unless ``nan_to_num=False`` (v2 keeps NaN,
     aegis_engine_financial.py:122).  ``with_trend`` adds ``multi_filter_consensus`` on the NaN-masked f0
-    (midi_logic_financial.py:158-161).
+    (midi_logic_financial.py:158-161).  ``with_guitar`` applies ``apply_guitar_filters`` the way
+    ``audio_to_midi_financial`` does (aegis_engine_financial.py:132-147): octave-corrected f0 / voiced flags,
+    enhanced rake mask, and the palm-mute frames removed from the voiced flags; adds ``mute_mask`` and
+    ``distortion``.
     """
     spec = spectral_features(y, sr=sr, hop_length=hop_length, rake_sensitivity=rake_sensitivity,
-                             with_sdb=with_sdb, with_onsets=with_onsets)
+                             with_sdb=with_sdb or with_guitar, with_onsets=with_onsets)
     pit = core.pyin_batch(y, sr=sr, fmin=fmin, fmax=fmax, hop_length=hop_length, clips_per_launch=clips_per_launch)
     f0_nan = pit["f0"]
+    extra = {}
+    if with_guitar:
+        gf = core.guitar_filters(spec["S_dB"], sr=sr, hop_length=hop_length, f0=f0_nan, voiced_flag=pit["voiced_flag"],
+                                 rake_mask=spec["rake_mask"])
+        f0_nan = gf["f0"]
+        spec["rake_mask"] = gf["rake_mask"]
+        pit["voiced_flag"] = gf["voiced"] & (gf["mute_mask"] ^ 1)   # voiced_flag & ~mute_mask (:147)
+        extra = {"mute_mask": gf["mute_mask"], "distortion": gf["distortion"]}
+        if not with_sdb:
+            del spec["S_dB"]
     out = {
+        **extra,
         "rake_mask": spec["rake_mask"], "voiced_flag": pit["voiced_flag"], "voiced_probs": pit["voiced_prob"],
         "rms": spec["rms"], "f0": torch.nan_to_num(f0_nan, nan=0.0) if nan_to_num else f0_nan,
         "states": pit["states"], "n_frames": spec["n_frames"],
@@ -91,6 +106,9 @@ def to_host(result: dict, clip: int, y: Optional[np.ndarray] = None) -> dict:
     for k in ("S_dB", "onset_env", "trend", "trend_conf"):
         if k in result:
             host[k] = result[k][clip].cpu().numpy()
+    if "mute_mask" in result:
+        host["mute_mask"] = result["mute_mask"][clip].cpu().numpy().astype(bool)
+        host["distortion"] = core.DISTORTION_LABELS[int(result["distortion"][clip])]
     if "onset_peaks" in result:
         host["onset_frames"] = np.flatnonzero(result["onset_peaks"][clip].cpu().numpy())
     return host

@@ -353,6 +353,73 @@ def trend_filters(x: torch.Tensor, *, want=TREND_OUTPUTS, savgol_window: int = 1
 
 
 # ----------------------------------------------------------------------------------------------
+# K6
+# ----------------------------------------------------------------------------------------------
+DISTORTION_LABELS = ("clean", "light", "heavy")
+
+
+def guitar_frame_limits(hop_length: int, sr: float, duration_ms: float = 50):
+    """(mute_max_frames, rake_frames) of guitar_specific.py:97-98,137-138."""
+    ms_per_frame = (hop_length / sr) * 1000
+    return int(duration_ms / ms_per_frame), int(30 / ms_per_frame)
+
+
+def guitar_filters(s_db: Optional[torch.Tensor], *, sr: float, hop_length: int = 512, f0: Optional[torch.Tensor] = None,
+                   voiced_flag: Optional[torch.Tensor] = None, rake_mask: Optional[torch.Tensor] = None,
+                   fmin_hz: float = 82.4, duration_ms: float = 50, want_rake: bool = True, want_mute: bool = True,
+                   want_distortion: bool = True) -> dict:
+    """``apply_guitar_filters`` for a batch (aegis_engine_core_v2/guitar_specific.py:240-277).
+
+    ``s_db`` f32 [n_clips, n_mels, T] dB images; ``f0`` f64 [n_clips, T] (NaN unvoiced) with ``voiced_flag`` u8/bool;
+    ``rake_mask`` u8/bool [n_clips, T] basic mask.  Returns the requested keys among ``f0``, ``voiced``, ``rake_mask``,
+    ``mute_mask`` (u8), ``distortion`` (int32 codes into ``DISTORTION_LABELS``).
+    """
+    P = nat.GuitarParams()
+    out: dict = {}
+    dev = None
+    n_clips = T = 0
+    if s_db is not None:
+        if s_db.dtype != torch.float32 or s_db.stride(2) != 1:
+            s_db = s_db.float().contiguous()
+        n_clips, n_mels, T = s_db.shape
+        dev = s_db.device
+        P.s_db, P.sdb_clip_stride, P.sdb_row_stride, P.n_mels = s_db.data_ptr() if s_db.numel() else None, s_db.stride(0), s_db.stride(1), n_mels
+        P.mute_max_frames, P.rake_frames = guitar_frame_limits(hop_length, sr, duration_ms)
+        if want_rake:
+            if rake_mask is not None:
+                rake_mask = rake_mask.to(torch.uint8).contiguous()
+                P.rake_in = rake_mask.data_ptr()
+            out["rake_mask"] = torch.empty((n_clips, T), dtype=torch.uint8, device=dev)
+            P.rake_out = out["rake_mask"].data_ptr()
+        if want_mute:
+            out["mute_mask"] = torch.empty((n_clips, T), dtype=torch.uint8, device=dev)
+            P.mute_out = out["mute_mask"].data_ptr()
+        if want_distortion:
+            nb = int(nat.load().aegis_guitar_blocks(T))
+            out["distortion"] = torch.zeros((n_clips,), dtype=torch.int32, device=dev)
+            work = torch.empty((max(1, n_clips * nb * 2),), dtype=torch.float64, device=dev)
+            P.distortion, P.dist_work = out["distortion"].data_ptr(), work.data_ptr()
+    if f0 is not None:
+        f0 = f0.to(torch.float64).contiguous()
+        if s_db is not None and tuple(f0.shape) != (n_clips, T):
+            raise ValueError("f0 must be [n_clips, T] like the dB images")
+        n_clips, T = f0.shape
+        dev = f0.device
+        P.f0 = f0.data_ptr()
+        if voiced_flag is not None:
+            voiced_flag = voiced_flag.to(torch.uint8).contiguous()
+            P.voiced = voiced_flag.data_ptr()
+        out["f0"] = torch.empty_like(f0)
+        out["voiced"] = torch.empty((n_clips, T), dtype=torch.uint8, device=dev)
+        P.f0_out, P.voiced_out = out["f0"].data_ptr(), out["voiced"].data_ptr()
+    if dev is None:
+        raise ValueError("guitar_filters needs s_db and / or f0")
+    P.n_clips, P.n_frames, P.fmin_hz = n_clips, T, float(fmin_hz)
+    nat.call("aegis_guitar_filters", P, _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # corpus synthesis
 # ----------------------------------------------------------------------------------------------
 def synth_events(n_clips: int, n_samples: int, events: dict, device, decay: float = 0.996) -> torch.Tensor:

@@ -104,14 +104,16 @@ class AegisFinancialEngine:
 
     def perception(self, input_wav, **kwargs):
         """Arrays ``audio_to_midi_financial`` hands to its note logic (:105-160): rake mask, pYIN with NaN
-        f0, RMS, S_dB, plus the consensus trend of ``analyze_pitch_financial`` (financial_analysis.py:386-391)."""
+        f0, RMS, S_dB, plus the consensus trend of ``analyze_pitch_financial`` (financial_analysis.py:386-391).
+        ``use_guitar_filters`` (default True, :128) applies ``apply_guitar_filters`` as :132-147 do."""
         y = _as_audio(input_wav, self.sr, kwargs.get("start_time", 0), kwargs.get("end_time", None))
         if len(y) == 0:
             return None
         yd = torch.from_numpy(y).to(librosa._device())[None]
         res = batch.analyze_batch(yd, sr=self.sr, hop_length=self.hop_length,
                                   rake_sensitivity=kwargs.get("rake_sensitivity", 0.6), with_sdb=True,
-                                  with_trend=True, nan_to_num=False)
+                                  with_trend=True, nan_to_num=False,
+                                  with_guitar=kwargs.get("use_guitar_filters", True))
         host = batch.to_host(res, 0, y=y)
         host["sr"], host["hop_length"] = self.sr, self.hop_length  # financial_app_realtime.py:224-233
         return host

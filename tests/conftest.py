@@ -19,3 +19,12 @@ def golden():
     path = os.path.join(ROOT, "tests", "golden", "reference_golden.npz")
     with np.load(path, allow_pickle=False) as z:
         return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def guitar_golden():
+    import numpy as np
+
+    path = os.path.join(ROOT, "tests", "golden", "guitar_golden.npz")
+    with np.load(path, allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}

@@ -18,7 +18,7 @@ STRUCTS = {
     "aegis_stft_params": _native.StftParams, "aegis_melpost_params": _native.MelPostParams,
     "aegis_peaks_params": _native.PeaksParams, "aegis_yin_params": _native.YinParams,
     "aegis_viterbi_params": _native.ViterbiParams, "aegis_trend_params": _native.TrendParams,
-    "aegis_synth_params": _native.SynthParams,
+    "aegis_synth_params": _native.SynthParams, "aegis_guitar_params": _native.GuitarParams,
 }
 
 
@@ -77,7 +77,8 @@ def test_library_exports_every_declared_symbol(lib_path):
     text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
     declared = set(re.findall(r"\b(aegis_[a-z0-9_]+)\s*\(", text))
     assert {"aegis_stft_fused", "aegis_mel_post", "aegis_onset_peaks", "aegis_yin_candidates", "aegis_viterbi",
-            "aegis_trend_filters", "aegis_synth_ks", "aegis_abi_version", "aegis_last_error"} <= declared
+            "aegis_trend_filters", "aegis_synth_ks", "aegis_guitar_filters", "aegis_guitar_blocks", "aegis_abi_version",
+            "aegis_last_error"} <= declared
     lib = ctypes.CDLL(lib_path)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/aegis_b200.h but not exported"

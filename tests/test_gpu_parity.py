@@ -438,6 +438,86 @@ def test_filter_classes_mirror_reference_api(dev, golden):
     assert (conf == 1).all()
 
 
+# ---------------------------------------------------------------------------------- K6 guitar filters
+def test_guitar_filters_match_reference_golden(dev, guitar_golden):
+    """aegis_guitar_filters against the outputs of the real aegis_engine_core_v2/guitar_specific.py (bit-exact)."""
+    from spectrogram_midi_b200 import guitar_specific as G
+
+    g = guitar_golden
+    names = sorted({k.split("/")[1] for k in g})
+    assert len(names) >= 8
+    code = {"clean": 0, "light": 1, "heavy": 2}
+    for n in names:
+        hop, sr = (int(v) for v in g[f"guitar/{n}/args"])
+        res = G.apply_guitar_filters(g[f"guitar/{n}/f0"], g[f"guitar/{n}/voiced"], g[f"guitar/{n}/S_dB"], hop, sr, g[f"guitar/{n}/rake_in"])
+        np.testing.assert_array_equal(res["f0"], g[f"guitar/{n}/out_f0"], err_msg=n)
+        assert res["f0"].dtype == np.float64 and res["voiced"].dtype == bool and res["mute_mask"].dtype == bool
+        np.testing.assert_array_equal(res["voiced"], g[f"guitar/{n}/out_voiced"], err_msg=n)
+        np.testing.assert_array_equal(res["rake_mask"], g[f"guitar/{n}/out_rake"], err_msg=n)
+        np.testing.assert_array_equal(res["mute_mask"], g[f"guitar/{n}/out_mute"], err_msg=n)
+        assert code[res["distortion"]] == int(g[f"guitar/{n}/out_distortion"][0]), n
+        # the individual static methods of the reference's class
+        F = G.GuitarSpecificFilters
+        f0o, vo = F.filter_subharmonic_noise(g[f"guitar/{n}/f0"], g[f"guitar/{n}/voiced"])
+        np.testing.assert_array_equal(f0o, g[f"guitar/{n}/out_f0"])
+        np.testing.assert_array_equal(vo, g[f"guitar/{n}/out_voiced"])
+        np.testing.assert_array_equal(F.detect_palm_mute(g[f"guitar/{n}/S_dB"], hop, sr), g[f"guitar/{n}/out_mute"])
+        np.testing.assert_array_equal(F.detect_rake_enhanced(g[f"guitar/{n}/S_dB"], hop, sr, g[f"guitar/{n}/rake_in"]), g[f"guitar/{n}/out_rake"])
+        assert code[F.classify_distortion_level(g[f"guitar/{n}/S_dB"])] == int(g[f"guitar/{n}/out_distortion"][0])
+
+
+def test_guitar_filters_batch_long_and_block_edges(dev):
+    """Batch of ragged-content images longer than one 192-column block: every clip equals the oracle; runs and
+    triggers that straddle block boundaries are handled by the halo."""
+    rng = np.random.default_rng(11)
+    T, n = 1000, 5
+    imgs = rng.uniform(-62.0, -48.0, size=(n, 128, T)).astype(np.float32)
+    imgs[:, 64:] -= 6.0
+    for c in range(n):
+        for s in rng.integers(1, T - 12, 60):
+            ln = int(rng.integers(1, 7))
+            if rng.random() < 0.5:   # mute-like run (also across columns 191/192, 383/384, ...)
+                imgs[c, :64, s:s + ln] = rng.uniform(-75.0, -65.0, size=(64, ln))
+                imgs[c, 64:, s:s + ln] = rng.uniform(-32.0, -28.0, size=(64, ln))
+            else:                    # broadband burst
+                imgs[c, :, s:s + ln] = rng.uniform(-14.0, -2.0, size=(128, ln))
+        for edge in (192, 384, 576):
+            imgs[c, :64, edge - 2:edge + 1] = -70.0
+            imgs[c, 64:, edge - 2:edge + 1] = -30.0
+            imgs[c, :, edge + 20 - 1:edge + 20 + 1] = -5.0
+    f0 = rng.uniform(30.0, 500.0, (n, T))
+    f0[rng.random((n, T)) < 0.3] = np.nan
+    vf = ~np.isnan(f0)
+    rk = rng.random((n, T)) < 0.05
+    for sr, hop in ((22050, 512), (44100, 512), (44100, 256)):
+        res = P.core.guitar_filters(torch.from_numpy(imgs).to(dev), sr=sr, hop_length=hop, f0=torch.from_numpy(f0).to(dev),
+                                    voiced_flag=torch.from_numpy(vf).to(dev), rake_mask=torch.from_numpy(rk).to(dev))
+        fired = 0
+        for c in range(n):
+            ref = R.apply_guitar_filters(f0[c], vf[c], imgs[c], hop, sr, rk[c])
+            np.testing.assert_array_equal(res["f0"][c].cpu().numpy(), ref["f0"])
+            np.testing.assert_array_equal(res["voiced"][c].cpu().numpy().astype(bool), ref["voiced"])
+            np.testing.assert_array_equal(res["rake_mask"][c].cpu().numpy().astype(bool), ref["rake_mask"], err_msg=f"{sr}/{hop}/{c}")
+            np.testing.assert_array_equal(res["mute_mask"][c].cpu().numpy().astype(bool), ref["mute_mask"], err_msg=f"{sr}/{hop}/{c}")
+            assert P.core.DISTORTION_LABELS[int(res["distortion"][c])] == ref["distortion"]
+            fired += int(ref["mute_mask"].sum()) + int((ref["rake_mask"] ^ rk[c]).sum())
+        assert fired > 0
+
+
+def test_financial_perception_applies_guitar_filters(dev):
+    """AegisFinancialEngine.perception = the arrays audio_to_midi_financial builds (:105-154) incl. guitar filters."""
+    y = corpus.test_track(22050, 0)
+    eng = P.AegisFinancialEngine()
+    got = eng.perception(y)
+    plain = eng.perception(y, use_guitar_filters=False)
+    ref = R.apply_guitar_filters(plain["f0"], plain["voiced_flag"], plain["S_dB"], 512, 22050, plain["rake_mask"])
+    np.testing.assert_array_equal(got["f0"], ref["f0"])
+    np.testing.assert_array_equal(got["rake_mask"], ref["rake_mask"])
+    np.testing.assert_array_equal(got["mute_mask"], ref["mute_mask"])
+    np.testing.assert_array_equal(got["voiced_flag"], ref["voiced"] & ~ref["mute_mask"])
+    assert got["distortion"] == ref["distortion"]
+
+
 # ---------------------------------------------------------------------------------- end to end: note events
 def test_midi_note_events_identical_to_reference(dev, golden):
     """GPU perception -> the (pinned) restatement of midi_logic.get_midi_events == the events the REAL

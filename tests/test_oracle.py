@@ -30,6 +30,28 @@ def test_rake_mask_matches_reference(golden):
     assert fired > 0  # the fixtures actually exercise the positive branch
 
 
+def test_guitar_filters_match_reference(guitar_golden):
+    """oracle restatement of aegis_engine_core_v2/guitar_specific.py against the real file's outputs"""
+    g = guitar_golden
+    names = _cases(g, "guitar")
+    assert len(names) >= 8
+    code = {"clean": 0, "light": 1, "heavy": 2}
+    mute = added = 0
+    seen = set()
+    for n in names:
+        hop, sr = (int(v) for v in g[f"guitar/{n}/args"])
+        res = R.apply_guitar_filters(g[f"guitar/{n}/f0"], g[f"guitar/{n}/voiced"], g[f"guitar/{n}/S_dB"], hop, sr, g[f"guitar/{n}/rake_in"])
+        np.testing.assert_array_equal(res["f0"], g[f"guitar/{n}/out_f0"], err_msg=n)
+        np.testing.assert_array_equal(res["voiced"], g[f"guitar/{n}/out_voiced"], err_msg=n)
+        np.testing.assert_array_equal(res["rake_mask"], g[f"guitar/{n}/out_rake"], err_msg=n)
+        np.testing.assert_array_equal(res["mute_mask"], g[f"guitar/{n}/out_mute"], err_msg=n)
+        assert code[res["distortion"]] == int(g[f"guitar/{n}/out_distortion"][0]), n
+        mute += int(res["mute_mask"].sum())
+        added += int((res["rake_mask"] ^ g[f"guitar/{n}/rake_in"]).sum())
+        seen.add(code[res["distortion"]])
+    assert mute > 0 and added > 0 and seen == {0, 1, 2}  # every branch is exercised
+
+
 @pytest.mark.parametrize("key,fn", [
     ("savgol", lambda f: R.savitzky_golay(f)),
     ("kalman", lambda f: R.kalman_filter(f)),
