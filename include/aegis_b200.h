@@ -272,6 +272,56 @@ int aegis_guitar_filters(const aegis_guitar_params* p, void* stream);
 int aegis_guitar_blocks(int n_frames);
 
 /* ---------------------------------------------------------------------------------------------
+ * K7  frame -> note-event state machine (v1 logic filter)
+ * replaces: get_midi_events + detect_articulations (aegis_engine_core/midi_logic.py:6-148; caller
+ *           aegis_engine.py:88-96 extract_events) with the raw-f0 branch the reference always takes
+ *           (:43-49: librosa.util.softmask has no `margin` keyword).
+ * One record per note event, in time order; n_events[clip] is the number found (if it exceeds
+ * max_events the list is truncated).  The MIDI note of a frame is note_lut[pitch_index[frame]] when
+ * both are given (the host computes round(hz_to_midi(f)) with numpy for every distinct f0 value, so
+ * exact quarter-tone ties round as in the reference), else rint(12 log2(f/440) + 69) on the device.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t note;              /* MIDI note number */
+    int32_t start;             /* first frame */
+    int32_t end;               /* last frame (inclusive) */
+    int32_t velocity;          /* int(clip((rms_dB + 80) * 1.5, 0, 127)) at the start frame */
+    float rms_energy;          /* rms_dB at the start frame */
+    uint8_t track;             /* 1 = main (confidence >= threshold), 0 = safe */
+    uint8_t technique;         /* 0 none, 1 vibrato, 2 bend, 3 slide, 4 hammer_on, 5 pull_off */
+    uint8_t _pad[2];
+    double confidence;         /* voiced probability at the start frame */
+    double slope;              /* semitones per frame (0 when no technique / hammer_on / pull_off) */
+} aegis_note_event;
+
+typedef struct {
+    const uint8_t* rake_mask;  /* [n_clips][n_frames] */
+    const double* f0;          /* [n_clips][n_frames] Hz; <= 0 or NaN = no pitch */
+    const uint8_t* voiced_flag;/* [n_clips][n_frames] */
+    const double* voiced_prob; /* [n_clips][n_frames] */
+    const float* rms;          /* [n_clips][rms_clip_stride] */
+    int64_t rms_clip_stride;
+    const uint16_t* pitch_index; /* [n_clips][n_frames] index into note_lut, or NULL */
+    const int16_t* note_lut;   /* [n_lut] MIDI note of every distinct f0 value, or NULL */
+    int32_t n_lut;
+    int32_t n_clips;
+    int32_t n_frames;
+    int32_t hop;
+    double sr;
+    double confidence_threshold;
+    float noise_gate_db;       /* -40 in the reference */
+    int32_t min_note_frames;   /* int(min_note_duration_ms / 1000 * sr / hop) */
+    int32_t sustain_frames;    /* int(sustain_ms / 1000 * sr / hop) */
+    int32_t max_events;        /* capacity of events per clip */
+    aegis_note_event* events;  /* [n_clips][max_events], buffer of aegis_note_events_bytes(...) bytes */
+    int32_t* n_events;         /* [n_clips] */
+} aegis_notes_params;
+
+int aegis_note_events(const aegis_notes_params* p, void* stream);
+/* bytes to provide at `events`: n_clips * max_events records followed by the kernel's per-frame scratch */
+long long aegis_note_events_bytes(int n_clips, int n_frames, int max_events);
+
+/* ---------------------------------------------------------------------------------------------
  * Corpus synthesis on device (Karplus-Strong plucks + noise rakes, generate_test_signal.py:5-53)
  * One event per note/rake; events of a clip do not overlap.  out must be zero-filled.
  * ------------------------------------------------------------------------------------------- */

@@ -108,6 +108,25 @@ class GuitarParams(C.Structure):
     ]
 
 
+class NoteEvent(C.Structure):
+    _fields_ = [
+        ("note", i32), ("start", i32), ("end", i32), ("velocity", i32), ("rms_energy", f32),
+        ("track", C.c_uint8), ("technique", C.c_uint8), ("_pad", C.c_uint8 * 2),
+        ("confidence", f64), ("slope", f64),
+    ]
+
+
+class NotesParams(C.Structure):
+    _fields_ = [
+        ("rake_mask", _ptr), ("f0", _ptr), ("voiced_flag", _ptr), ("voiced_prob", _ptr),
+        ("rms", _ptr), ("rms_clip_stride", i64), ("pitch_index", _ptr), ("note_lut", _ptr),
+        ("n_lut", i32), ("n_clips", i32), ("n_frames", i32), ("hop", i32),
+        ("sr", f64), ("confidence_threshold", f64), ("noise_gate_db", f32),
+        ("min_note_frames", i32), ("sustain_frames", i32), ("max_events", i32),
+        ("events", _ptr), ("n_events", _ptr),
+    ]
+
+
 ENTRY_POINTS = {
     "aegis_stft_fused": StftParams,
     "aegis_mel_post": MelPostParams,
@@ -117,6 +136,7 @@ ENTRY_POINTS = {
     "aegis_trend_filters": TrendParams,
     "aegis_synth_ks": SynthParams,
     "aegis_guitar_filters": GuitarParams,
+    "aegis_note_events": NotesParams,
 }
 
 _lib = None
@@ -139,6 +159,8 @@ def load() -> C.CDLL:
     lib.aegis_abi_version.restype = C.c_int
     lib.aegis_last_error.restype = C.c_char_p
     lib.aegis_device_sm_count.restype = C.c_int
+    lib.aegis_note_events_bytes.restype = C.c_longlong
+    lib.aegis_note_events_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.aegis_guitar_blocks.restype = C.c_int
     lib.aegis_guitar_blocks.argtypes = [C.c_int]
     for name, struct in ENTRY_POINTS.items():

@@ -92,6 +92,20 @@ def analyze_batch(y: torch.Tensor, *, sr: float, hop_length: int = 512, rake_sen
     return out
 
 
+def note_events_batch(result: dict, *, sr: float, hop_length: int = 512, fmin: float = E2, fmax: float = C6,
+                      confidence_threshold: float = 0.7, **kwargs) -> dict:
+    """Logic-filter phase for a whole batch on the device: ``get_midi_events`` (midi_logic.py:32-148) applied to an
+    ``analyze_batch`` result (v1 arrays: f0 with zeros).  The note numbers come from the Viterbi states through a
+    table computed with the reference's expression ``int(round(hz_to_midi(f)))`` on the pYIN frequency grid."""
+    cfg = tables.pyin_config(float(sr), hop_length, fmin, fmax)
+    lut = np.array([int(round(float(tables.hz_to_midi(f)))) for f in cfg.freqs], dtype=np.int16)
+    dev = result["f0"].device
+    f0 = torch.nan_to_num(result["f0"], nan=0.0)
+    return core.note_events(result["rake_mask"], f0, result["voiced_flag"], result["voiced_probs"], result["rms"],
+                            sr=sr, hop_length=hop_length, confidence_threshold=confidence_threshold,
+                            pitch_index=result["states"], note_lut=torch.from_numpy(lut).to(dev), **kwargs)
+
+
 def to_host(result: dict, clip: int, y: Optional[np.ndarray] = None) -> dict:
     """One clip of a batch result as the reference's perception dict (numpy, aegis_engine.py:72-75)."""
     host = {

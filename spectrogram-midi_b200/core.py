@@ -420,6 +420,83 @@ def guitar_filters(s_db: Optional[torch.Tensor], *, sr: float, hop_length: int =
 
 
 # ----------------------------------------------------------------------------------------------
+# K7
+# ----------------------------------------------------------------------------------------------
+NOTE_EVENT_DTYPE = np.dtype([("note", "<i4"), ("start", "<i4"), ("end", "<i4"), ("velocity", "<i4"), ("rms_energy", "<f4"),
+                             ("track", "u1"), ("technique", "u1"), ("_pad", "u1", (2,)), ("confidence", "<f8"), ("slope", "<f8")])
+TECHNIQUES = (None, "vibrato", "bend", "slide", "hammer_on", "pull_off")
+assert NOTE_EVENT_DTYPE.itemsize == 40
+
+
+def note_frame_limits(sr: float, hop_length: int, sustain_ms: float = 50, min_note_duration_ms: float = 50):
+    """(min_note_duration_frames, sustain_frames) of midi_logic.py:56-57."""
+    return int((min_note_duration_ms / 1000.0) * sr / hop_length), int((sustain_ms / 1000.0) * sr / hop_length)
+
+
+def note_events(rake_mask: torch.Tensor, f0: torch.Tensor, voiced_flag: torch.Tensor, voiced_prob: torch.Tensor,
+                rms: torch.Tensor, *, sr: float, hop_length: int = 512, confidence_threshold: float = 0.7,
+                noise_gate_db: float = -40, sustain_ms: float = 50, min_note_duration_ms: float = 50,
+                pitch_index: Optional[torch.Tensor] = None, note_lut: Optional[torch.Tensor] = None,
+                max_events: Optional[int] = None) -> dict:
+    """``get_midi_events`` for a batch (aegis_engine_core/midi_logic.py:32-148): frame arrays [n_clips, T] in,
+    ``events`` (uint8 [n_clips, max_events, 40], records of ``NOTE_EVENT_DTYPE``) and ``n_events`` int32 [n_clips] out.
+
+    ``f0`` is the v1 pitch track (0 where unvoiced, aegis_engine.py:69).  With ``pitch_index`` (uint16 index of every
+    frame's f0 value, stored in an int16 tensor, e.g. the Viterbi states) and ``note_lut`` (int16 MIDI note per index, computed on the host with the
+    reference's numpy expression) note numbers are exact even at quarter-tone ties.
+    """
+    f0 = f0.to(torch.float64).contiguous()
+    n_clips, T = f0.shape
+    dev = f0.device
+    rake_mask = rake_mask.to(torch.uint8).contiguous()
+    voiced_flag = voiced_flag.to(torch.uint8).contiguous()
+    voiced_prob = voiced_prob.to(torch.float64).contiguous()
+    if rms.dtype != torch.float32 or rms.stride(-1) != 1:
+        rms = rms.float().contiguous()
+    for name, t in (("rake_mask", rake_mask), ("voiced_flag", voiced_flag), ("voiced_prob", voiced_prob), ("rms", rms)):
+        if tuple(t.shape) != (n_clips, T):
+            raise ValueError(f"{name} must be [n_clips, T] like f0")
+    min_frames, sustain_frames = note_frame_limits(sr, hop_length, sustain_ms, min_note_duration_ms)
+    if max_events is None:   # an event that survives the duration filter spans min_frames + 1 frames
+        max_events = T // (min_frames + 1) + 1
+    P = nat.NotesParams()
+    P.rake_mask, P.f0, P.voiced_flag, P.voiced_prob = rake_mask.data_ptr(), f0.data_ptr(), voiced_flag.data_ptr(), voiced_prob.data_ptr()
+    P.rms, P.rms_clip_stride = rms.data_ptr(), rms.stride(0)
+    if (pitch_index is None) != (note_lut is None):
+        raise ValueError("pitch_index and note_lut go together")
+    if pitch_index is not None:
+        if pitch_index.dtype != torch.int16:   # the uint16 bit pattern travels in an int16 tensor (as the Viterbi states do)
+            raise ValueError("pitch_index must be an int16 tensor holding uint16 bit patterns")
+        pitch_index = pitch_index.contiguous()
+        note_lut = note_lut.to(torch.int16).contiguous()
+        P.pitch_index, P.note_lut, P.n_lut = pitch_index.data_ptr(), note_lut.data_ptr(), note_lut.numel()
+    P.n_clips, P.n_frames, P.hop, P.sr = n_clips, T, hop_length, float(sr)
+    P.confidence_threshold, P.noise_gate_db = float(confidence_threshold), float(noise_gate_db)
+    P.min_note_frames, P.sustain_frames, P.max_events = min_frames, sustain_frames, max_events
+    n_bytes = int(nat.load().aegis_note_events_bytes(n_clips, T, max_events))
+    buf = torch.empty((n_bytes,), dtype=torch.uint8, device=dev)
+    n_events = torch.zeros((n_clips,), dtype=torch.int32, device=dev)
+    P.events, P.n_events = buf.data_ptr(), n_events.data_ptr()
+    nat.call("aegis_note_events", P, _stream())
+    events = buf[: n_clips * max_events * NOTE_EVENT_DTYPE.itemsize].view(n_clips, max_events, NOTE_EVENT_DTYPE.itemsize)
+    return {"events": events, "n_events": n_events, "max_events": max_events}
+
+
+def note_events_to_list(events: torch.Tensor, n_events: torch.Tensor, clip: int) -> list:
+    """One clip's records as the reference's list of dicts (keys and value types of midi_logic.py:71-104)."""
+    n = int(n_events[clip])
+    if n > events.shape[1]:
+        raise nat.AegisNativeError(f"clip {clip}: {n} note events exceed the buffer of {events.shape[1]}")
+    rec = events[clip, :n].cpu().numpy().reshape(-1).view(NOTE_EVENT_DTYPE) if n else np.zeros(0, NOTE_EVENT_DTYPE)
+    out = []
+    for r in rec:
+        out.append({"note": int(r["note"]), "start": int(r["start"]), "end": int(r["end"]), "confidence": r["confidence"],
+                    "velocity": int(r["velocity"]), "track": "main" if r["track"] else "safe", "rms_energy": r["rms_energy"],
+                    "technique": TECHNIQUES[int(r["technique"])], "slope": float(r["slope"])})
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # corpus synthesis
 # ----------------------------------------------------------------------------------------------
 def synth_events(n_clips: int, n_samples: int, events: dict, device, decay: float = 0.996) -> torch.Tensor:

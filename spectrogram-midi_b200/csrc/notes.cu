@@ -1,0 +1,232 @@
+// K7: frame -> note-event state machine of the v1 logic filter.
+//
+// Replaces get_midi_events / detect_articulations (aegis_engine_core/midi_logic.py:6-148, called from
+// aegis_engine.py:88-96).  The reference walks the frames in Python; its state machine is equivalent to: events =
+// maximal runs of frames with the same MIDI note among the frames that are voiced, above the noise gate, pitched and
+// not rake noise (:63-105); drop events shorter than min_note_duration (:108); merge neighbours of equal note whose
+// gap is <= sustain_frames when the first has no technique (:111-123); mark hammer-on / pull-off pairs (:126-146).
+//
+// Kernel 1 (frame parallel): rms -> dB relative to the clip maximum (librosa.amplitude_to_db(ref=np.max), float32
+// arithmetic as in numpy; log10 is evaluated in double and rounded once, i.e. correctly rounded float32) and the
+// per-frame MIDI note (-1 = inactive).  Kernel 2: one thread per clip walks its frames once (independent loads,
+// L2 resident), keeps least-squares sums of the running event, finishes events (slope, vibrato range), and applies
+// the duration filter, the merge and the hammer-on / pull-off rule in streaming form: an event is written once the
+// next surviving event is known.  A clip is a sequential chain of ~T steps of a few dozen instructions: 1292 frames
+// take ~50 us, all clips in parallel.
+#include <cfloat>
+#include <cmath>
+#include "common.cuh"
+
+namespace aegis {
+
+constexpr int NT_THREADS = 256;
+
+__device__ __forceinline__ float db10_f32(float power, float amin) {
+    // 10.0 * np.log10(np.maximum(amin, power)) in float32
+    const float v = fmaxf(amin, power);
+    return __fmul_rn(10.0f, static_cast<float>(log10(static_cast<double>(v))));
+}
+
+// per clip: max of |rms| (the reference of amplitude_to_db)
+__global__ void __launch_bounds__(NT_THREADS)
+notes_rms_max_kernel(const aegis_notes_params p, float* __restrict__ rms_max) {
+    __shared__ float red[NT_THREADS / 32];
+    const int clip = blockIdx.x;
+    const float* r = p.rms + static_cast<long long>(clip) * p.rms_clip_stride;
+    float m = 0.f;
+    for (int t = threadIdx.x; t < p.n_frames; t += NT_THREADS) m = fmaxf(m, fabsf(r[t]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < NT_THREADS / 32; ++w) m = fmaxf(m, red[w]);
+        rms_max[clip] = m;
+    }
+}
+
+// per frame: rms dB and MIDI note (or -1)
+__global__ void __launch_bounds__(NT_THREADS)
+notes_frames_kernel(const aegis_notes_params p, const float* __restrict__ rms_max, float* __restrict__ rms_db, short* __restrict__ note) {
+    const int clip = blockIdx.y;
+    const int t = blockIdx.x * NT_THREADS + threadIdx.x;
+    if (t >= p.n_frames) return;
+    const long long i = static_cast<long long>(clip) * p.n_frames + t;
+    // amplitude_to_db(rms, ref=np.max): power_to_db(rms**2, ref=max**2, amin=1e-10, top_db=80) (librosa, float32)
+    const float amin = 1e-10f;
+    const float mag = fabsf(p.rms[static_cast<long long>(clip) * p.rms_clip_stride + t]);
+    const float ref = rms_max[clip];
+    float e = __fadd_rn(db10_f32(__fmul_rn(mag, mag), amin), -db10_f32(__fmul_rn(ref, ref), amin));
+    // top_db: max(log_spec, log_spec.max() - 80); the maximum is the reference frame itself
+    const float top = __fadd_rn(__fadd_rn(db10_f32(__fmul_rn(ref, ref), amin), -db10_f32(__fmul_rn(ref, ref), amin)), -80.0f);
+    e = fmaxf(e, top);
+    rms_db[i] = e;
+    const double f = p.f0[i];
+    const bool active = p.voiced_flag[i] != 0 && !(e < p.noise_gate_db) && f > 0.0 && p.rake_mask[i] == 0;
+    int n = -1;
+    if (active) {
+        if (p.note_lut != nullptr && p.pitch_index != nullptr) {
+            const int idx = p.pitch_index[i];
+            n = idx < p.n_lut ? p.note_lut[idx] : -1;
+        } else {
+            n = static_cast<int>(rint(12.0 * (log2(f) - log2(440.0)) + 69.0));  // round half to even, as Python's round()
+        }
+    }
+    note[i] = static_cast<short>(n);
+}
+
+struct Ev {
+    int note, start, end, velocity;
+    float energy;
+    int track, technique;
+    double confidence, slope;
+};
+
+__device__ __forceinline__ void write_event(aegis_note_event* dst, const Ev& e) {
+    dst->note = e.note;
+    dst->start = e.start;
+    dst->end = e.end;
+    dst->velocity = e.velocity;
+    dst->rms_energy = e.energy;
+    dst->track = static_cast<uint8_t>(e.track);
+    dst->technique = static_cast<uint8_t>(e.technique);
+    dst->_pad[0] = dst->_pad[1] = 0;
+    dst->confidence = e.confidence;
+    dst->slope = e.slope;
+}
+
+__global__ void __launch_bounds__(64)
+notes_events_kernel(const aegis_notes_params p, const float* __restrict__ rms_db, const short* __restrict__ note) {
+    const int clip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (clip >= p.n_clips) return;
+    const int T = p.n_frames;
+    const long long base = static_cast<long long>(clip) * T;
+    const short* nt = note + base;
+    const double* f0 = p.f0 + base;
+    aegis_note_event* out = p.events + static_cast<long long>(clip) * p.max_events;
+    const double LOG2_440 = log2(440.0);
+    const double ms_per_frame = (static_cast<double>(p.hop) / p.sr) * 1000;
+    int n_out = 0;
+    bool have_pending = false, have_last = false;
+    Ev pending{}, last{};   // pending: survived the duration filter, may still absorb merges; last: previous event written
+
+    auto emit = [&](Ev e) {   // hammer-on / pull-off against the previously written event (:126-146), then write
+        if (have_last) {
+            const double gap_ms = (e.start - last.end) * ms_per_frame;
+            if (gap_ms < 30) {
+                const int dp = e.note - last.note;
+                const double v_ratio = static_cast<double>(e.velocity) / static_cast<double>(max(last.velocity, 1));
+                const float denom = fmaxf(last.energy, -80.0f);
+                const float e_ratio = __fdiv_rn(e.energy, denom);
+                const bool weak = v_ratio < 0.7 || e_ratio < 0.8f;
+                if (dp > 0 && dp <= 2 && weak) { e.technique = 4; e.slope = 0.0; }
+                else if (dp >= -2 && dp < 0 && weak) { e.technique = 5; e.slope = 0.0; }
+            }
+        }
+        if (n_out < p.max_events) write_event(out + n_out, e);
+        ++n_out;
+        // the rule reads note / velocity / energy / end of the predecessor: none of them is changed by the rule itself
+        last = e;
+        have_last = true;
+    };
+    auto finish = [&](Ev e, double sy, double sxy) {   // articulation of a completed run (:6-30), filter, merge
+        const int n = e.end - e.start + 1;
+        e.technique = 0;
+        e.slope = 0.0;
+        if (n >= 3) {
+            // least squares of the MIDI pitch against the frame index 0..n-1
+            const double xm = 0.5 * (n - 1), sxx = static_cast<double>(n) * (static_cast<double>(n) * n - 1.0) / 12.0;
+            const double ym = sy / n;
+            const double slope = (sxy - xm * sy) / sxx;
+            const double icpt = ym - slope * xm;
+            double rmin = DBL_MAX, rmax = -DBL_MAX;
+            for (int t = e.start; t <= e.end; ++t) {
+                const double y = 12.0 * (log2(f0[t]) - LOG2_440) + 69.0;
+                const double r = y - (slope * (t - e.start) + icpt);
+                rmin = fmin(rmin, r);
+                rmax = fmax(rmax, r);
+            }
+            if (rmax - rmin > 0.3) { e.technique = 1; e.slope = slope; }
+            else if (slope > 0.05) { e.technique = 2; e.slope = slope; }
+            else if (fabs(slope) > 0.02) { e.technique = 3; e.slope = slope; }
+        }
+        if (e.end - e.start < p.min_note_frames) return;          // :108
+        if (have_pending) {
+            if (e.note == pending.note && (e.start - pending.end) <= p.sustain_frames && pending.technique == 0) {
+                pending.end = e.end;                               // :117-118
+                return;
+            }
+            emit(pending);
+        }
+        pending = e;
+        have_pending = true;
+    };
+
+    Ev cur{};
+    bool open = false;
+    double sy = 0.0, sxy = 0.0;
+    for (int t = 0; t < T; ++t) {
+        const int n = nt[t];
+        if (open && n != cur.note) {
+            finish(cur, sy, sxy);
+            open = false;
+        }
+        if (n >= 0) {
+            const double y = 12.0 * (log2(f0[t]) - LOG2_440) + 69.0;
+            if (!open) {
+                const float energy = rms_db[base + t];
+                const double conf = p.voiced_prob[base + t];
+                cur.note = n;
+                cur.start = t;
+                cur.energy = energy;
+                cur.confidence = conf;
+                cur.velocity = static_cast<int>(fminf(fmaxf(__fmul_rn(__fadd_rn(energy, 80.0f), 1.5f), 0.0f), 127.0f));
+                cur.track = conf >= p.confidence_threshold ? 1 : 0;
+                sy = 0.0;
+                sxy = 0.0;
+                open = true;
+            }
+            cur.end = t;
+            sy += y;
+            sxy += y * (t - cur.start);
+        }
+    }
+    if (open) finish(cur, sy, sxy);
+    if (have_pending) emit(pending);
+    p.n_events[clip] = n_out;
+}
+
+}  // namespace aegis
+
+extern "C" int aegis_note_events(const aegis_notes_params* p, void* stream) {
+    using namespace aegis;
+    AEGIS_REQUIRE(p != nullptr, "aegis_note_events: null params");
+    AEGIS_REQUIRE(p->n_clips >= 0 && p->n_frames >= 0 && p->max_events >= 0, "aegis_note_events: negative size");
+    AEGIS_REQUIRE(p->rake_mask && p->f0 && p->voiced_flag && p->voiced_prob && p->rms, "aegis_note_events: inputs missing");
+    AEGIS_REQUIRE(p->events && p->n_events, "aegis_note_events: outputs missing");
+    AEGIS_REQUIRE(p->rms_clip_stride >= p->n_frames && p->hop > 0 && p->sr > 0, "aegis_note_events: bad rms stride / hop / sr");
+    AEGIS_REQUIRE((p->note_lut == nullptr) == (p->pitch_index == nullptr), "aegis_note_events: note_lut and pitch_index go together");
+    if (p->n_clips == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // scratch: rms_max [n_clips] f32, rms_db [n_clips*T] f32, note [n_clips*T] i16 -- carved from the events buffer? No:
+    // the library never allocates, so the scratch lives behind the event records (see the size query below)
+    const long long frames = static_cast<long long>(p->n_clips) * p->n_frames;
+    unsigned char* scratch = reinterpret_cast<unsigned char*>(p->events + static_cast<long long>(p->n_clips) * p->max_events);
+    float* rms_max = reinterpret_cast<float*>(scratch);
+    float* rms_db = rms_max + ((p->n_clips + 3) / 4) * 4;
+    short* note = reinterpret_cast<short*>(rms_db + frames);
+    if (p->n_frames > 0) {
+        notes_rms_max_kernel<<<p->n_clips, NT_THREADS, 0, st>>>(*p, rms_max);
+        if (int rc = check_launch("aegis_note_events(rms max)")) return rc;
+        notes_frames_kernel<<<dim3((p->n_frames + NT_THREADS - 1) / NT_THREADS, p->n_clips), NT_THREADS, 0, st>>>(*p, rms_max, rms_db, note);
+        if (int rc = check_launch("aegis_note_events(frames)")) return rc;
+    }
+    notes_events_kernel<<<(p->n_clips + 63) / 64, 64, 0, st>>>(*p, rms_db, note);
+    return check_launch("aegis_note_events(events)");
+}
+
+// bytes the caller must provide behind `events`: the records plus the per-frame scratch
+extern "C" long long aegis_note_events_bytes(int n_clips, int n_frames, int max_events) {
+    const long long frames = static_cast<long long>(n_clips) * n_frames;
+    return static_cast<long long>(n_clips) * max_events * static_cast<long long>(sizeof(aegis_note_event)) +
+           ((n_clips + 3) / 4) * 4 * 4LL + frames * 4 + frames * 2 + 16;
+}

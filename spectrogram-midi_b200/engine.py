@@ -72,6 +72,17 @@ class AegisEngine:
         seams); here the frame-parallel stages already use every SM, so the exact full-clip result is returned."""
         return self._pyin(np.asarray(y, dtype=np.float32))
 
+    # -- aegis_engine.py:88-96: the note-event list extract_events builds before it writes the MIDI file
+    def note_events(self, raw_data, **kwargs):
+        """``get_midi_events`` on a perception result (same keyword arguments as ``extract_events``:
+        ``confidence_threshold``, ``noise_gate_db``, ``sustain_ms``, ``min_note_duration_ms``), on the GPU (kernel K7)."""
+        from .midi_logic import get_midi_events
+
+        n = min(len(raw_data["f0"]), len(raw_data["rms"]), len(raw_data["rake_mask"]))   # aegis_engine.py:82-83
+        return get_midi_events(raw_data["rake_mask"][:n], raw_data["f0"][:n], raw_data["voiced_flag"][:n],
+                               raw_data["voiced_probs"][:n], raw_data["rms"][:n], self.sr, self.hop_length,
+                               kwargs.pop("confidence_threshold", 0.70), **kwargs)
+
     # -- aegis_engine.py:77-181: unchanged consumer
     def extract_events(self, raw_data, output_mid, **kwargs):
         try:

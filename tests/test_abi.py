@@ -19,6 +19,7 @@ STRUCTS = {
     "aegis_peaks_params": _native.PeaksParams, "aegis_yin_params": _native.YinParams,
     "aegis_viterbi_params": _native.ViterbiParams, "aegis_trend_params": _native.TrendParams,
     "aegis_synth_params": _native.SynthParams, "aegis_guitar_params": _native.GuitarParams,
+    "aegis_note_event": _native.NoteEvent, "aegis_notes_params": _native.NotesParams,
 }
 
 
@@ -77,7 +78,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
     declared = set(re.findall(r"\b(aegis_[a-z0-9_]+)\s*\(", text))
     assert {"aegis_stft_fused", "aegis_mel_post", "aegis_onset_peaks", "aegis_yin_candidates", "aegis_viterbi",
-            "aegis_trend_filters", "aegis_synth_ks", "aegis_guitar_filters", "aegis_guitar_blocks", "aegis_abi_version",
+            "aegis_trend_filters", "aegis_synth_ks", "aegis_guitar_filters", "aegis_guitar_blocks", "aegis_note_events", "aegis_note_events_bytes", "aegis_abi_version",
             "aegis_last_error"} <= declared
     lib = ctypes.CDLL(lib_path)
     for name in declared:

@@ -438,6 +438,118 @@ def test_filter_classes_mirror_reference_api(dev, golden):
     assert (conf == 1).all()
 
 
+# ---------------------------------------------------------------------------------- K7 note events
+TECH = {None: 0, "vibrato": 1, "bend": 2, "slide": 3, "hammer_on": 4, "pull_off": 5}
+
+
+def _event_rows(ev):
+    ints = np.array([[e["note"], e["start"], e["end"], e["velocity"], int(e["track"] == "main"), TECH[e.get("technique")]] for e in ev],
+                    dtype=np.int64).reshape(-1, 6)
+    flt = np.array([[e["confidence"], e["rms_energy"], e.get("slope", 0.0)] for e in ev], dtype=np.float64).reshape(-1, 3)
+    return ints, flt
+
+
+def test_note_events_match_reference_golden(dev, golden):
+    """aegis_note_events on the golden INPUT arrays == the events the REAL aegis_engine_core/midi_logic.py produced
+    from them (integers exact; confidence exact, rms dB and slope to rounding)."""
+    from spectrogram_midi_b200 import midi_logic as M
+
+    total = 0
+    for name in ("track22050", "track44100", "clip7"):
+        k = f"midi/{name}"
+        sr = int(golden[f"{k}/sr"][0])
+        ev = M.get_midi_events(rake_mask=golden[f"{k}/rake_mask"], f0=golden[f"{k}/f0"], voiced_flag=golden[f"{k}/voiced_flag"],
+                               active_probs=golden[f"{k}/voiced_prob"], rms=golden[f"{k}/rms"], sr=sr, hop_length=512,
+                               confidence_threshold=0.70)
+        ints, flt = _event_rows(ev)
+        np.testing.assert_array_equal(ints, golden[f"{k}/events"], err_msg=name)
+        want = golden[f"{k}/event_float"]
+        np.testing.assert_array_equal(flt[:, 0], want[:, 0])
+        np.testing.assert_allclose(flt[:, 1], want[:, 1], rtol=0, atol=4e-6)
+        np.testing.assert_allclose(flt[:, 2], want[:, 2], rtol=1e-9, atol=1e-12)
+        assert all(isinstance(e["note"], int) and e["track"] in ("main", "safe") for e in ev)
+        total += len(ev)
+    assert total >= 10
+
+
+def test_note_events_random_frames_equal_oracle(dev):
+    """Adversarial frame arrays (short runs, rake holes, quiet frames, merges, hammer-ons, an exact quarter-tone tie)
+    for a batch of clips at several rates: integer fields identical to the pinned restatement of midi_logic.py.
+
+    Pitch drifts are continuous (random cents), not on pYIN's 10-cent grid: on the grid a 3-frame event that rises by
+    one bin has a least-squares slope of EXACTLY the reference's 0.05 "bend" threshold, and which side np.polyfit
+    (LAPACK gelsd) lands on is its own rounding noise (2.6 % of random grid events differ between np.polyfit and the
+    closed form evaluated in the same float64) -- no implementation other than that LAPACK build can match it."""
+    rng = np.random.default_rng(5)
+    from spectrogram_midi_b200 import midi_logic as M
+
+    E2hz = 82.4068892282175
+    seen = set()
+    for sr, hop, T in ((22050, 512, 700), (44100, 512, 900), (44100, 256, 600)):
+        n = 6
+        f0 = np.zeros((n, T))
+        vf = np.zeros((n, T), bool)
+        rms = np.full((n, T), 1e-4, np.float32)
+        for c in range(n):
+            t = 0
+            while t < T:
+                ln = int(rng.integers(1, 30))
+                m = max(0, min(ln, T - t))
+                if rng.random() < 0.8 and m:
+                    base = 100.0 * rng.integers(0, 44) + rng.uniform(-12, 12)   # cents above E2, near a semitone centre
+                    kind = rng.integers(0, 4)
+                    x = np.arange(m)
+                    if kind == 0:
+                        cents = base + np.cumsum(rng.normal(0, 1.0, m))          # steady
+                    elif kind == 1:
+                        cents = base - 30 + 61.7 * x / max(m - 1, 1)            # bend up inside the note (never exactly 0.05 / frame)
+                    elif kind == 2:
+                        cents = base + 25 - 3.0 * x                               # slow slide down
+                    else:
+                        cents = base + 22.0 * np.sin(x * 1.3)                    # vibrato
+                    f0[c, t:t + m] = E2hz * 2.0 ** (cents / 1200.0)
+                    vf[c, t:t + m] = True
+                    rms[c, t:t + m] = 10 ** rng.uniform(-2.3, -0.5) * rng.uniform(0.7, 1.0, m)
+                t += ln + int(rng.integers(0, 3))
+        f0[:, 5:9] = E2hz * 2.0 ** (5 / 120.0)   # exact quarter-tone tie: hz_to_midi == 40.5 up to rounding (constant pitch)
+        vf[:, 5:9] = True
+        f0[:, 9:12] = 0.0
+        rms[:, 5:9] = 0.2
+        vp = rng.uniform(0.4, 1.0, (n, T))
+        rake = rng.random((n, T)) < 0.03
+        rake[:, 4:10] = False
+        for c in range(n):
+            got = M.get_midi_events(rake[c], f0[c], vf[c], vp[c], rms[c], sr, hop, 0.7)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref = R.get_midi_events(rake[c], f0[c], vf[c], vp[c], rms[c], sr, hop, 0.7)
+            gi, gf = _event_rows(got)
+            ri, rf = _event_rows(ref)
+            np.testing.assert_array_equal(gi, ri, err_msg=f"{sr}/{hop}/{c}")
+            np.testing.assert_allclose(gf[:, 2], rf[:, 2], rtol=1e-8, atol=1e-11)
+            assert len(got) > 10
+            seen |= {int(v) for v in ri[:, 5]}
+    assert seen >= {0, 1, 2, 3, 4, 5}   # none, vibrato, bend, slide, hammer_on, pull_off all occur
+
+
+def test_note_events_batch_from_states(dev):
+    """batch.note_events_batch (notes from the Viterbi states) == the numpy drop-in on each clip's host arrays."""
+    from spectrogram_midi_b200 import midi_logic as M
+
+    clips = corpus.clip_batch(3, 8.0, 22050, first_seed=40)
+    res = P.batch.analyze_batch(_dev(clips, dev), sr=22050)
+    ev = P.batch.note_events_batch(res, sr=22050, confidence_threshold=0.7)
+    for c in range(3):
+        host = P.batch.to_host(res, c)
+        want = M.get_midi_events(host["rake_mask"], host["f0"], host["voiced_flag"], host["voiced_probs"], host["rms"], 22050, 512, 0.7)
+        got = P.core.note_events_to_list(ev["events"], ev["n_events"], c)
+        assert _event_rows(got)[0].tolist() == _event_rows(want)[0].tolist()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = R.get_midi_events(host["rake_mask"], host["f0"], host["voiced_flag"], host["voiced_probs"], host["rms"], 22050, 512, 0.7)
+        assert _event_rows(got)[0].tolist() == _event_rows(ref)[0].tolist()
+
+
 # ---------------------------------------------------------------------------------- K6 guitar filters
 def test_guitar_filters_match_reference_golden(dev, guitar_golden):
     """aegis_guitar_filters against the outputs of the real aegis_engine_core_v2/guitar_specific.py (bit-exact)."""
