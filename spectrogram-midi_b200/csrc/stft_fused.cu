@@ -353,16 +353,17 @@ __device__ __forceinline__ void mel_partials(const aegis_stft_params& p, const S
 #pragma unroll
             for (int i = 0; i < NB; ++i) acc(m[i], w[i], r, fl);
         }
-        if (k < k1) {   // up to NB - 1 bins left: clamped loads, zero weights
+        if (k < k1) {   // up to NB - 1 bins left: predicated loads (an inactive lane costs no shared-memory wavefront)
             float4 m[NB - 1];
             float2 w[NB - 1];
 #pragma unroll
             for (int i = 0; i < NB - 1; ++i) {
-                const bool in = k + i < k1;
-                const int kk = in ? k + i : k;
-                m[i] = ld(kk);
-                w[i] = s.mel_rf[kk];
-                if (!in) w[i] = make_float2(0.f, 0.f);
+                m[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                w[i] = make_float2(0.f, 0.f);
+                if (k + i < k1) {
+                    m[i] = ld(k + i);
+                    w[i] = s.mel_rf[k + i];
+                }
             }
 #pragma unroll
             for (int i = 0; i < NB - 1; ++i) acc(m[i], w[i], r, fl);

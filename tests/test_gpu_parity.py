@@ -707,3 +707,41 @@ def test_long_clip_windows_equal_the_full_clip_result(dev, sr, mode):
         np.testing.assert_array_equal(np.nan_to_num(res["f0"]), ref["f0"])
     else:
         assert (res["voiced_flag"] == ref["voiced_flag"]).mean() >= 0.99
+
+
+def test_one_hour_clip_at_baseline_cfg4_size(dev):
+    """BASELINE cfg4 at full size on one GPU: a 3600 s, 44.1 kHz recording (158 760 000 samples, T = 310 079 frames)
+    tiled from seeded cfg2-style segments, analysed as 8 overlapping windows (the per-rank windows of an 8-GPU run,
+    processed in turn).  Too long to compare with the oracle, so size-independent properties are checked:
+    frame count, frame-local outputs identical between the two stitching modes, windowed decode (2 s burn-in) against the
+    exact single-chain decode, and spot windows against a direct analysis of the same audio."""
+    import time
+
+    from spectrogram_midi_b200 import distributed as D
+
+    sr, seg_s, n_seg = 44100, 30.0, 120
+    plan = corpus.plan_events(n_seg, seg_s, sr, first_seed=7000)
+    y = P.core.synth_events(n_seg, int(seg_s * sr), plan, dev).reshape(-1).cpu().numpy()
+    assert y.shape[0] == 158_760_000
+    t0 = time.time()
+    ex = D.analyze_long_clip(y, sr=sr, mode="exact", windows_per_rank=8)
+    t1 = time.time()
+    wi = D.analyze_long_clip(y, sr=sr, mode="windowed", windows_per_rank=8, burn_seconds=2.0)
+    t2 = time.time()
+    T = 1 + y.shape[0] // 512
+    assert T == 310_079 and all(len(ex[k]) == T for k in ("rake_mask", "f0", "voiced_flag", "voiced_probs", "rms"))
+    for k in ("rake_mask", "voiced_probs", "rms"):
+        np.testing.assert_array_equal(ex[k], wi[k])
+    agree = float((ex["voiced_flag"] == wi["voiced_flag"]).mean())
+    both = ex["voiced_flag"] & wi["voiced_flag"]
+    f0_same = float((ex["f0"][both] == wi["f0"][both]).mean())
+    print(f"cfg4 full size: exact {t1 - t0:.1f} s, windowed {t2 - t1:.1f} s ({3600 / (t2 - t1):.0f} x realtime on one GPU), "
+          f"voiced agreement {agree:.6f}, f0 identical on {f0_same:.6f} of common voiced frames, voiced {ex['voiced_flag'].mean():.3f}")
+    assert agree >= 0.9995 and f0_same >= 0.9995
+    assert 0.2 < ex["voiced_flag"].mean() < 0.99
+    # a window from the middle analysed directly: frame-local outputs are identical (8-frame aligned start)
+    f_lo = 8 * 20000
+    s_lo = f_lo * 512
+    seg = y[s_lo - 1024 : s_lo - 1024 + 512 * 400 + 2048]
+    direct = P.core.stft_features(_dev(seg, dev), sr=sr, want_mag=False, want_rms=True, center=False)
+    np.testing.assert_array_equal(direct["rms"][0].cpu().numpy()[:400], ex["rms"][f_lo : f_lo + 400])
