@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libaegis_b200.so")
+LIB_PATH = os.environ.get("AEGIS_B200_LIB") or os.path.join(PKG_DIR, "libaegis_b200.so")  # the override is for kernel A/B experiments
 ABI_VERSION = 1
 
 _f32p = C.c_void_p

@@ -13,16 +13,16 @@
 //     in registers;
 //   * window, twiddles and mel weights are read once per frame PAIR; with hop 512 the two frames
 //     share 3/4 of their sample loads;
-//   * warp specialisation: one persistent CTA of 512 threads per SM = two COMPUTE groups (4 warps each, 184
-//     registers, one 8-frame tile of one clip at a time) + two STORE groups (4 warps each, 72 registers), one per
+//   * warp specialisation: one persistent CTA of 512 threads per SM = two COMPUTE groups (4 warps each, 200
+//     registers, one 8-frame tile of one clip at a time) + two STORE groups (4 warps each, 56 registers), one per
 //     compute group.  A compute group leaves |X| of its tile in a shared-memory stage laid out as a TMA box
 //     (CU_TENSOR_MAP_SWIZZLE_32B) and goes on with its next tile; its store group has the TMA unit write the stage
 //     into librosa's [1025, T] layout (cp.async.bulk.tensor, one thread, no LSU traffic) and meanwhile reduces |X|^2
 //     over the mel triangles (each bin read once: rise / fall partial sums per band-edge segment).  Producer /
 //     consumer hand-over with named barriers (bar.arrive / bar.sync), registers rebalanced with setmaxnreg.
-//   * the hot loop is ~3000 instructions; the two compute groups are kept in step (one barrier per tile) and the two
-//     32-point passes share one copy of the butterfly code, because the instruction cache (32 KB L1.5) was the
-//     limiter once the arithmetic was packed (ncu: stall_no_instruction).
+//   * the hot loop is ~2800 straight-line instructions (45 KB) against a 32 KB L1.5 instruction cache: the two
+//     compute groups are kept in step (one barrier per tile) so that they fetch the same code at the same time
+//     (ncu: stall_no_instruction was the top stall when they drifted apart; 4.3 ms without the barrier, 3.7 with).
 // What bounds it now (ncu, profiles/): the FP32 pipe during the transform phases (both compute warps of an SM
 // sub-partition in step), shared-memory latency in the store groups.
 // HBM traffic per frame: hop*4 B read (+ halo, L2-served) and 1025*4 B written.
@@ -45,7 +45,7 @@ constexpr int SAMPLES_MAX = (TILE_F - 1) * MAX_HOP + RF_N;  // 5632
 constexpr int MEL_MAX = 128;
 constexpr int MEL_PART = (MEL_MAX + 1) * TILE_F;            // floats per rise / fall partial array
 constexpr int REGS_LAUNCH = 65536 / STFT_THREADS;            // 128: what __launch_bounds__(512, 1) gives every thread
-constexpr int REGS_COMPUTE = 184, REGS_STORE = 72;
+constexpr int REGS_COMPUTE = 200, REGS_STORE = 2 * REGS_LAUNCH - REGS_COMPUTE;   // 200 / 56 (A/B timed: 176..216 within 5 %)
 static_assert(COMPUTE_THREADS * (REGS_COMPUTE + REGS_STORE) <= STFT_THREADS * REGS_LAUNCH,
               "setmaxnreg trades registers inside the pool the CTA was launched with");
 
@@ -259,26 +259,21 @@ __device__ __forceinline__ void compute_group(const aegis_stft_params& p, StftSm
         if (!do_fft) continue;  // RMS-only call (librosa.feature.rms)
 
         // ---- two real 2048-point transforms, inside the warp; the exchange in two rounds (re, im)
-        // (the two 32-point passes share one copy of the butterfly code: the hot loop has to fit the 32 KB L1.5
-        // instruction cache together with the store group's loop, ncu: stall_no_instruction)
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            fft32(v);
-            if (pass == 0) {
-                rfft_twiddle1(lane, v, s.tw1);
-                rfft_xstore<false>(lane, v, xbuf);
-                __syncwarp();
-                p2 nre[32];
-                rfft_xload(lane, xbuf, nre);
-                __syncwarp();
-                rfft_xstore<true>(lane, v, xbuf);
-                __syncwarp();
-                p2 nim[32];
-                rfft_xload(lane, xbuf, nim);
+        fft32(v);
+        rfft_twiddle1(lane, v, s.tw1);
+        rfft_xstore<false>(lane, v, xbuf);
+        __syncwarp();
+        {
+            p2 nre[32], nim[32];
+            rfft_xload(lane, xbuf, nre);
+            __syncwarp();
+            rfft_xstore<true>(lane, v, xbuf);
+            __syncwarp();
+            rfft_xload(lane, xbuf, nim);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = c2{nre[j], nim[j]};
-            }
+            for (int j = 0; j < 32; ++j) v[j] = c2{nre[j], nim[j]};
         }
+        fft32(v);
         // the store group must have consumed the previous tile's magnitudes before they are overwritten
         if (handed_over) named_barrier(BAR_EMPTY + g, 2 * GROUP_THREADS);
         {   // this thread's frame is f = 2 wg + (lane >> 4); bins k = q + 32c and 1024 - k (rfft_split_emit): the swizzle
@@ -337,7 +332,7 @@ __device__ __forceinline__ void mel_partials(const aegis_stft_params& p, const S
         fl.b = pfma(pb, w.y, fl.b);
     };
     auto ld = [&](int k) { return *reinterpret_cast<const float4*>(st + stage_word(k, 4 * h)); };
-    constexpr int NB = 8;   // bins per round: all loads of a round are issued before the first use
+    constexpr int NB = 8;   // bins per round: all loads of a round are issued before the first use (4, 6, 8 time alike)
     for (int j = slot; j <= p.n_mels; j += GROUP_THREADS / 2) {
         int k = s.mel_seg[j];
         const int k1 = s.mel_seg[j + 1];
