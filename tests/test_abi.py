@@ -125,3 +125,26 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_native.AegisNativeError):
         _native.load()
+
+
+def test_host_side_frame_limits_and_note_table():
+    """Host logic of the K6 / K7 bindings (no device work): the frame limits use the reference's expressions and the
+    note table maps every distinct f0 value with int(round(hz_to_midi(f)))."""
+    import numpy as np
+
+    from spectrogram_midi_b200 import core, midi_logic, tables
+
+    assert core.guitar_frame_limits(512, 22050) == (2, 1)        # int(50 / 23.2), int(30 / 23.2)
+    assert core.guitar_frame_limits(512, 44100) == (4, 2)
+    assert core.note_frame_limits(22050, 512) == (2, 2)          # int(0.05 * 22050 / 512) twice
+    assert core.note_frame_limits(44100, 512) == (4, 4)
+    assert core.NOTE_EVENT_DTYPE.itemsize == ctypes.sizeof(_native.NoteEvent) == 40
+    for name in ("note", "start", "end", "velocity", "rms_energy", "track", "technique", "confidence", "slope"):
+        assert core.NOTE_EVENT_DTYPE.fields[name][1] == getattr(_native.NoteEvent, name).offset, name
+    f0 = np.array([0.0, 110.0, 110.0, np.nan, 440.0, 82.4068892282175 * 2 ** (5 / 120.0), -3.0])
+    idx, lut = midi_logic._note_lut(f0)
+    assert idx.dtype == np.uint16 and lut.dtype == np.int16 and len(lut) == 3
+    pos = f0 > 0
+    assert (idx[~pos] == 65535).all()
+    want = np.array([int(round(float(tables.hz_to_midi(v)))) for v in f0[pos]])
+    assert np.array_equal(lut[idx[pos]], want) and set(want) >= {45, 69}
