@@ -43,6 +43,8 @@ struct VitSmem {
     double lt[VT_SMEM_VARIANTS][2][VT_MAX_W];      // interior transition variants [variant][same|switch][offset]
     double ubr[2][VT_MAX_W + VT_CHUNK];            // [same|switch][q]: max over the shared-memory (interior) row
                                                    // variants and over offsets q-7..q; other rows add their own dub
+    double M4[2][2][VT_N_CHUNKS / 4];              // max of M over each aligned group of 4 chunks (= one warp of bins)
+    double ubr4[2][VT_MAX_W + 5 * VT_CHUNK];       // [same|switch][q]: max of ubr over q, q-8, q-16, q-24
     double seg_val[2][2][VT_MAX_WARPS];            // per-warp leftmost max of V
     short seg_arg[2][2][VT_MAX_WARPS];
     unsigned char rowvar[VT_MAX_BINS + 2 * VT_HALO];
@@ -85,6 +87,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
     constexpr int hw = HW, W = 2 * HW + 1;
     constexpr int NCH = (W + 2 * (VT_CHUNK - 1) + VT_CHUNK - 1) / VT_CHUNK;  // chunks that can touch a band
     static_assert(HW + VT_CHUNK <= VT_HALO, "halo too small");
+    static_assert(VT_CHUNK_PAD % 4 == 0 && VT_N_CHUNKS % 4 == 0, "chunk groups must align with the padding");
     const int n = p.n_pitch_bins, T = p.n_frames;
     const int n_warps = (n + 31) >> 5;
     const int nsv = min(p.n_interior_variants, VT_SMEM_VARIANTS);
@@ -96,6 +99,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
     // ---- one-time shared set-up
     for (int i = b; i < 2 * 2 * (VT_MAX_BINS + 2 * VT_HALO); i += blockDim.x) (&s.V[0][0][0])[i] = NEG_INF;
     for (int i = b; i < 2 * 2 * VT_N_CHUNKS; i += blockDim.x) (&s.M[0][0][0])[i] = NEG_INF;
+    for (int i = b; i < 2 * 2 * (VT_N_CHUNKS / 4); i += blockDim.x) (&s.M4[0][0][0])[i] = NEG_INF;
     for (int i = b; i < 2 * VT_MAX_BINS; i += blockDim.x) (&s.obs_lp[0][0])[i] = LOGTINY;
     for (int i = b; i < VT_MAX_BINS + 2 * VT_HALO; i += blockDim.x) {
         const int src = i - VT_HALO;
@@ -119,6 +123,17 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
             for (int var = 0; var < nsv; ++var) m = fmax(m, s.lt[var][sel][o]);
         }
         s.ubr[sel][q] = m;
+    }
+    __syncthreads();
+    // bound of a group of 4 chunks whose FIRST chunk has offset q: the chunks sit at offsets q, q-8, q-16, q-24
+    for (int i = b; i < 2 * (W + 5 * VT_CHUNK); i += blockDim.x) {
+        const int sel = i / (W + 5 * VT_CHUNK), q = i - sel * (W + 5 * VT_CHUNK);
+        double m = NEG_INF;
+        for (int j = 0; j < 4; ++j) {
+            const int qq = q - VT_CHUNK * j;
+            if (qq >= 0 && qq < W + VT_CHUNK) m = fmax(m, s.ubr[sel][qq]);
+        }
+        s.ubr4[sel][q] = m;
     }
     double dub = 0.0;
     if (live) {
@@ -214,6 +229,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                 double best0 = NEG_INF, best1 = NEG_INF;
                 int arg0 = 0, arg1 = 0;
                 const int cfirst = ((b - hw + 8 * VT_CHUNK_PAD) >> 3) - VT_CHUNK_PAD;  // floor((b - hw) / 8)
+                const int c_int_lo = (hw + VT_CHUNK - 1) / VT_CHUNK, c_int_hi = (n - hw - VT_CHUNK) / VT_CHUNK;  // chunks of untruncated rows
 #pragma unroll
                 for (int sv = 0; sv < 2; ++sv) {          // source block: 0 voiced, 1 unvoiced
                     const double* Vc = sv == 0 ? Vc0 : Vc1;
@@ -225,13 +241,31 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                         if (oob > best0) { best0 = oob; arg0 = kbase + gmax[sv].a; }
                         if (oob > best1) { best1 = oob; arg1 = kbase + gmax[sv].a; }
                     }
+                    // Groups of 4 chunks (32 bins, one warp of sources) are tested first with their own exact bound: a typical
+                    // destination rejects 10 of its 13 chunks per block with 4 group tests.
+                    const int cend = cfirst + NCH;
+                    int c = cfirst;
 #pragma unroll 1
-                    for (int ci = 0; ci < NCH; ++ci) {
-                        const int c = cfirst + ci;
+                    while (c < cend) {
+                        const int gs = (c + VT_CHUNK_PAD) >> 2;                    // group index (shifted by the padding)
+                        const int c0 = (gs << 2) - VT_CHUNK_PAD;                   // its first chunk
+                        const int gnext = min(c0 + 4, cend);
+                        {
+                            const int q4 = b + hw - VT_CHUNK * c0;                 // offset of the group's first chunk
+                            if (q4 < 0) break;                                     // the whole group lies above the band
+                            const double m4 = s.M4[cur][sv][gs];
+                            const double g0 = m4 + s.ubr4[sel0][q4], g1 = m4 + s.ubr4[sel1][q4];
+                            if (!((g0 >= L0 && g0 > best0) || (g1 >= L1 && g1 > best1))) {
+                                c = gnext;
+                                continue;
+                            }
+                        }
+#pragma unroll 1
+                        for (; c < gnext; ++c) {
                         const int ohi = b + hw - VT_CHUNK * c;   // offset of the chunk's first source
-                        if (ohi < 0) break;
+                        if (ohi < 0) { c = cend; break; }
                         const double m = s.M[cur][sv][c + VT_CHUNK_PAD];
-                        const int kind = (VT_CHUNK * c >= hw && VT_CHUNK * c + VT_CHUNK - 1 < n - hw) ? 0 : 1;  // all 8 source rows untruncated?
+                        const int kind = (c >= c_int_lo && c <= c_int_hi) ? 0 : 1;  // all 8 source rows untruncated?
                         const double bd0 = m + s.ubr[sel0][ohi], bd1 = m + s.ubr[sel1][ohi];
                         const bool need0 = (bd0 >= L0) && (bd0 > best0);
                         const bool need1 = (bd1 >= L1) && (bd1 > best1);
@@ -280,6 +314,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                                 }
                             }
                         }
+                        }
                     }
                     if (g_high) {  // higher indices than the band
                         if (oob > best0) { best0 = oob; arg0 = kbase + gmax[sv].a; }
@@ -310,6 +345,9 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                 cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
                 cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 4));
                 if ((lane & 7) == 0) s.M[nxt][v][(b >> 3) + VT_CHUNK_PAD] = cm;
+                cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
+                cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 16));
+                if (lane == 0) s.M4[nxt][v][(b >> 5) + VT_CHUNK_PAD / 4] = cm;
             }
             x = butterfly_leftmost(x, 1);
             x = butterfly_leftmost(x, 2);
