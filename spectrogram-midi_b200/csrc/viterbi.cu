@@ -295,6 +295,35 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                                         if (cc > best1) { best1 = cc; arg1 = kbase + b0 + j; }
                                     }
                                 }
+                            } else if (ohi >= VT_CHUNK - 1 && ohi < W) {
+                                // all 8 sources inside the band, some of them truncated edge rows (their tables live in
+                                // global memory, L1 resident): same unrolled form, the row pointer is selected per source.
+                                // Sources outside [0, n) carry V = -inf (halo) and never win.  (Keeping the edge rows'
+                                // central window in shared memory as well was tried: 108 ms instead of 79 ms per 1024
+                                // clips -- the extra 55 KB per CTA costs more L1 than it saves.)
+                                double x[VT_CHUNK];
+#pragma unroll
+                                for (int j = 0; j < VT_CHUNK; j += 2) {
+                                    const double2 xx = *reinterpret_cast<const double2*>(&Vc[b0 + j]);
+                                    x[j] = xx.x;
+                                    x[j + 1] = xx.y;
+                                }
+                                const unsigned long long vars = *reinterpret_cast<const unsigned long long*>(&rvc[b0]);
+#pragma unroll
+                                for (int j = 0; j < VT_CHUNK; ++j) {
+                                    const int var = static_cast<int>((vars >> (8 * j)) & 0xff);
+                                    const bool in_smem = var < nsv;
+                                    const double* row = in_smem ? &s.lt[var][0][ohi - j] : p.lt_variants + static_cast<long long>(var) * 2 * W + (ohi - j);
+                                    const int pitch = in_smem ? VT_MAX_W : W;
+                                    if (need0) {
+                                        const double cc = x[j] + row[sel0 * pitch];
+                                        if (cc > best0) { best0 = cc; arg0 = kbase + b0 + j; }
+                                    }
+                                    if (need1) {
+                                        const double cc = x[j] + row[sel1 * pitch];
+                                        if (cc > best1) { best1 = cc; arg1 = kbase + b0 + j; }
+                                    }
+                                }
                             } else {
 #pragma unroll
                                 for (int j = 0; j < VT_CHUNK; ++j) {
