@@ -217,52 +217,56 @@ AEGIS_HD void rfft_split_pair(float kr, float ki, float nr, float ni, cf32 w, fl
     pow_n = br * br + bi * bi;
 }
 
-// After fft32 of pass 2: emit |2X|^2 of every bin this thread owns through `emit(k, power)`.
-//   general lanes (q >= 1): k = q + 32c pairs with 1024 - k                          (64 bins)
-//   q == 0 lanes: column 0 (k = 32c, partner 32(32-c)), column 16 (k = 16 + 32i, partner 16 + 32(31-i)), k = 512
-// The q == 0 lanes pick different registers through selects so the warp stays converged.
+// Twiddles of the packed split: for iteration c (0..15) and column pair q (0..15) the two lanes handle
+//   lo: k = q + 32c                      hi: k = (32 - q) + 32c      (q = 0: lo k = 32c, hi k = 16 + 32c)
+struct alignas(16) tw4 {
+    float wr_lo, wr_hi, wi_lo, wi_hi;   // (cos, -sin)(2 pi k / 2048) of the lo / hi lane
+};
+AEGIS_HD constexpr int rfft_split_klo(int q, int c) { return q + 32 * c; }
+AEGIS_HD constexpr int rfft_split_khi(int q, int c) { return (q ? 32 - q : 16) + 32 * c; }
+
+// After fft32 of pass 2: emit |2X|^2 of every bin this thread owns through `emit(bin, power, is_k)`
+// (is_k: the bin is congruent to q modulo 32, else to -q; the caller's swizzle offset depends only on that).
+// Packed form: the lo lane splits the pair (Z[k], Z[1024 - k]) with k = q + 32c from lo(V[c]) and hi(V[31 - c]);
+// the hi lane at the same time splits (Z[k'], Z[1024 - k']) with k' = (32 - q) + 32c from hi(V[c]) and
+// lo(V[31 - c]): swapping the halves of V[31 - c] lines both pairs up lane by lane, so the sixteen operations of a
+// split run as packed instructions on two bins at once.  The q == 0 lanes hold the self-conjugate columns 0 and 16:
+// their partners are lo(V[32 - c]) and hi(V[31 - c]), picked with selects so the warp stays converged; k = 512 is
+// the one bin left over.
 template <class Emit>
-AEGIS_HD void rfft_split_emit(int lane, const c2* v, const cf32* tw2, Emit&& emit) {
+AEGIS_HD void rfft_split_emit(int lane, const c2* v, const tw4* tw2p /*[16][16]*/, cf32 tw512, Emit&& emit) {
     const int q = lane & 15;
     const bool sp = (q == 0);
-    const int koff = sp ? -496 : 0;  // q == 0, c >= 16: k = 16 + 32 (c - 16)
-    const cf32* const twl = tw2 + q;          // c < 16
-    const cf32* const twh = tw2 + q + koff;   // c >= 16
-    constexpr int AHEAD = 4;                  // twiddles are fetched AHEAD iterations before use (shared-memory latency)
-    cf32 wq[AHEAD];
+    const int klo = rfft_split_klo(q, 0), khi = rfft_split_khi(q, 0);
+    const tw4* const twp = tw2p + q;
+    constexpr int AHEAD = 4;   // twiddles are fetched AHEAD iterations before use (shared-memory latency)
+    tw4 wq[AHEAD];
 #pragma unroll
-    for (int c = 0; c < AHEAD; ++c) wq[c] = twl[32 * c];
+    for (int c = 0; c < AHEAD; ++c) wq[c] = twp[16 * c];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        const c2 a = v[rpos32(c)], b = v[rpos32(31 - c)];
-        const cf32 w = wq[c % AHEAD];
-        if (c + AHEAD < 32) wq[c % AHEAD] = (c + AHEAD < 16) ? twl[32 * (c + AHEAD)] : twh[32 * (c + AHEAD)];
-        float kr, ki, nr, ni;
-        int k;
-        if (c < 16) {
-            const c2 b0 = v[rpos32((32 - c) & 31)];
-            kr = a.re.x;
-            ki = a.im.x;
-            nr = sp ? b0.re.x : b.re.y;
-            ni = sp ? b0.im.x : b.im.y;
-            k = q + 32 * c;
-        } else {
-            const c2 a1 = v[rpos32(c - 16)], b1 = v[rpos32(47 - c)];
-            kr = sp ? a1.re.y : a.re.x;
-            ki = sp ? a1.im.y : a.im.x;
-            nr = sp ? b1.re.y : b.re.y;
-            ni = sp ? b1.im.y : b.im.y;
-            k = q + 32 * c + koff;
-        }
-        float pk, pn;
-        rfft_split_pair(kr, ki, nr, ni, w, pk, pn);
-        emit(k, pk, true);
-        emit(RF_M - k, pn, false);
+    for (int c = 0; c < 16; ++c) {
+        const c2 A = v[rpos32(c)], B = v[rpos32(31 - c)], B0 = v[rpos32((32 - c) & 31)];
+        const tw4 w = wq[c % AHEAD];
+        if (c + AHEAD < 16) wq[c % AHEAD] = twp[16 * (c + AHEAD)];
+        const p2 wre = p2{sp ? B0.re.x : B.re.y, sp ? B.re.y : B.re.x};   // Z[1024 - k] of the lo / hi lane
+        const p2 wim = p2{sp ? B0.im.x : B.im.y, sp ? B.im.y : B.im.x};
+        const p2 wr = p2{w.wr_lo, w.wr_hi}, wi = p2{w.wi_lo, w.wi_hi};
+        const p2 sr = A.re + wre, si = A.im - wim;    // S = Zk + conj Zn
+        const p2 dr = A.re - wre, di = A.im + wim;    // D = Zk - conj Zn;  O' = D / i = (di, -dr)
+        const p2 tr = pfma(di, wr, dr * wi);          // Re W O'
+        const p2 ti = pfma(di, wi, -(dr * wr));       // Im W O'
+        const p2 ar = sr + tr, ai = si + ti;          // 2 X[k]
+        const p2 br = sr - tr, bi = si - ti;          // conj(2 X[1024-k])
+        const p2 pk = pfma(ar, ar, ai * ai), pn = pfma(br, br, bi * bi);
+        emit(klo + 32 * c, pk.x, true);
+        emit(RF_M - (klo + 32 * c), pn.x, false);
+        emit(khi + 32 * c, pk.y, false);
+        emit(RF_M - (khi + 32 * c), pn.y, true);
     }
     {
         const c2 a = v[rpos32(16)];
         float pk, pn;
-        rfft_split_pair(a.re.x, a.im.x, a.re.x, a.im.x, tw2[RF_M / 2], pk, pn);
+        rfft_split_pair(a.re.x, a.im.x, a.re.x, a.im.x, tw512, pk, pn);
         if (sp) emit(RF_M / 2, pk, true);
     }
 }

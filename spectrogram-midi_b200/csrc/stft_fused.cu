@@ -75,7 +75,8 @@ struct StftSmem {
     float samples[STFT_GROUPS][SAMPLES_MAX];
     float window[RF_N];              // 0.5 * analysis window (the split produces 2 X)
     cf32 tw1[32 * 32];               // [b][lane] W1024^{lane b}
-    cf32 tw2[RF_M];                  // W2048^k
+    tw4 tw2p[16 * 16];               // twiddles of the packed split, [iteration c][column pair q]
+    cf32 tw512;                      // W2048^512
     float2 mel_rf[RF_BINS];          // (rise, fall) weight of every FFT bin
     alignas(16) float rise[STFT_GROUPS][MEL_PART];   // per store group
     alignas(16) float fall[STFT_GROUPS][MEL_PART];
@@ -281,7 +282,7 @@ __device__ __forceinline__ void compute_group(const aegis_stft_params& p, StftSm
             const int f = 2 * wg + (lane >> 4), q = lane & 15;
             float* const st = s.stage[g];
             const int off_k = stage_word(q, f) - 8 * q, off_n = stage_word(RF_M - q, f) - 8 * (RF_M - q);
-            rfft_split_emit(lane, v, s.tw2, [&](int k, float pw, bool is_k) { st[8 * k + (is_k ? off_k : off_n)] = sqrt_approx(pw); });
+            rfft_split_emit(lane, v, s.tw2p, s.tw512, [&](int k, float pw, bool is_k) { st[8 * k + (is_k ? off_k : off_n)] = sqrt_approx(pw); });
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the TMA unit (async proxy) reads these writes
         bar_arrive(BAR_FULL + g, 2 * GROUP_THREADS);
@@ -449,7 +450,11 @@ stft_fused_kernel(const aegis_stft_params p, const __grid_constant__ CUtensorMap
         const cf32* tab = reinterpret_cast<const cf32*>(p.twiddle);
         for (int i = tid; i < RF_N; i += STFT_THREADS) s.window[i] = 0.5f * p.window[i];
         for (int i = tid; i < 32 * 32; i += STFT_THREADS) s.tw1[i] = tab[(2 * (i & 31) * (i >> 5)) & (RF_N - 1)];
-        for (int i = tid; i < RF_M; i += STFT_THREADS) s.tw2[i] = tab[i];
+        for (int i = tid; i < 16 * 16; i += STFT_THREADS) {
+            const cf32 lo = tab[rfft_split_klo(i & 15, i >> 4)], hi = tab[rfft_split_khi(i & 15, i >> 4)];
+            s.tw2p[i] = tw4{lo.x, hi.x, lo.y, hi.y};
+        }
+        if (tid == 0) s.tw512 = tab[RF_M / 2];
         if (p.mel != nullptr) {
             for (int i = tid; i < RF_BINS; i += STFT_THREADS) s.mel_rf[i] = reinterpret_cast<const float2*>(p.mel_rise_fall)[i];
             for (int i = tid; i < p.n_mels + 2; i += STFT_THREADS) s.mel_seg[i] = p.mel_seg_start[i];

@@ -11,10 +11,15 @@ using namespace aegis;
 // out: [2][1025] magnitudes of the two frames' spectra (x 2, as the kernel computes before its 1/2 fold)
 extern "C" int emul_rfft2048x2(const float* frames, const float* twiddle, float* out, int reverse_order) {
     const cf32* tab = reinterpret_cast<const cf32*>(twiddle);
-    std::vector<cf32> tw1(32 * 32), tw2(1024);
+    std::vector<cf32> tw1(32 * 32);
+    std::vector<tw4> tw2p(16 * 16);
     for (int b = 0; b < 32; ++b)
         for (int j = 0; j < 32; ++j) tw1[b * 32 + j] = tab[(2 * j * b) & 2047];
-    for (int k = 0; k < 1024; ++k) tw2[k] = tab[k];
+    for (int c = 0; c < 16; ++c)
+        for (int q = 0; q < 16; ++q) {
+            const cf32 lo = tab[rfft_split_klo(q, c)], hi = tab[rfft_split_khi(q, c)];
+            tw2p[c * 16 + q] = tw4{lo.x, hi.x, lo.y, hi.y};
+        }
     std::vector<float> buf(RF_XCHG_WORDS);
     std::vector<p2> nre(32 * 32);
     std::vector<c2> regs(32 * 32);
@@ -47,7 +52,7 @@ extern "C" int emul_rfft2048x2(const float* frames, const float* twiddle, float*
         c2* v = &regs[lane * 32];
         fft32(v);
         const int h = lane >> 4;
-        rfft_split_emit(lane, v, tw2.data(), [&](int k, float pw, bool) {
+        rfft_split_emit(lane, v, tw2p.data(), tab[512], [&](int k, float pw, bool) {
             out[h * 1025 + k] = std::sqrt(pw);
             written[h * 1025 + k] += 1;
         });
