@@ -433,6 +433,7 @@ __device__ __forceinline__ void store_group(const aegis_stft_params& p, const CU
         named_barrier(BAR_FULL + g, 2 * GROUP_THREADS);
         store_tile(p, tmap, use_tma, s, g, gt, w.clip, w.tin * TILE_F);
     }
+    if (use_tma && gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every bulk store has landed before the CTA retires
 }
 
 __global__ void __launch_bounds__(STFT_THREADS, 1)
