@@ -76,6 +76,14 @@ def cpu_throughput(clips, cores, repeats=1):
     return repeats * len(clips) * CLIP_SECONDS / dt, dt
 
 
+def pooled_rate(clips, cores):
+    """clips per second of the CPU oracle with the full pool busy (a single-process probe is several times faster per
+    clip than a worker of a saturated pool, and would oversize the bounded sample)."""
+    k = min(len(clips), 2 * cores)
+    _, dt = cpu_throughput(clips[:k], cores)
+    return k / dt
+
+
 def host_sample_clips(n, seed0=0):
     import spectrogram_midi_b200 as P
 
@@ -92,17 +100,14 @@ def run_reference(args):
     import numpy as np  # noqa: F401
 
     t_probe0 = time.perf_counter()
-    probe = host_sample_clips(max(cores, 8))
-    _cpu_spectral_one(probe[0])
-    t0 = time.perf_counter()
-    _cpu_spectral_one(probe[0])
-    t_clip = time.perf_counter() - t0
-    # bounded sample: ~6 s of wall per step on all cores, whole run within a few minutes
-    n = int(min(1024, max(cores, round(6.0 * cores / max(t_clip, 1e-3)))))
+    probe = host_sample_clips(2 * max(cores, 4))
+    rate = pooled_rate(probe, cores)
+    # bounded sample: ~8 s of wall per step on all cores and the whole run within ~2.5 minutes
+    per_step_s = min(8.0, 150.0 / max(1, args.steps))
+    n = int(min(1024, max(cores, round(rate * per_step_s))))
     clips = host_sample_clips(n) if n > len(probe) else probe[:n]
-    log(f"[reference] cores={cores} t_clip={t_clip * 1e3:.1f} ms sample={n} clips (setup {time.perf_counter() - t_probe0:.1f}s)")
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_throughput(clips[: max(cores, 8)], cores)
+    log(f"[reference] cores={cores} pooled rate={rate:.1f} clips/s sample={n} clips per step (setup {time.perf_counter() - t_probe0:.1f}s)")
+    # (the pooled probe above was the warm-up: page cache, imports, FFT plans)
     t_total = 0.0
     for _ in range(args.steps):
         _, dt = cpu_throughput(clips, cores)
@@ -302,12 +307,8 @@ def run_gpu(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        probe = y[:8].cpu().numpy()
-        _cpu_spectral_one(probe[0])
-        t1 = time.perf_counter()
-        _cpu_spectral_one(probe[0])
-        t_clip = time.perf_counter() - t1
-        n = int(min(N_CLIPS, max(cores, round(15.0 * cores / max(t_clip, 1e-3)))))
+        rate = pooled_rate(y[: 2 * cores].cpu().numpy(), cores)
+        n = int(min(N_CLIPS, max(cores, round(15.0 * rate))))   # ~15 s of wall with every core busy
         sample = y[:n].cpu().numpy()
         v, dt = cpu_throughput(sample, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
