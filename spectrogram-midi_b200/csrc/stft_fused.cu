@@ -476,15 +476,13 @@ static bool make_mag_map(const aegis_stft_params* p, CUtensorMap* map) {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static encode_fn encode = nullptr;
-    static bool looked_up = false;
-    if (!looked_up) {
+    static const encode_fn encode = []() -> encode_fn {   // resolved once (thread-safe static initialisation)
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-            encode = reinterpret_cast<encode_fn>(fn);
-        looked_up = true;
-    }
+            return reinterpret_cast<encode_fn>(fn);
+        return nullptr;
+    }();
     if (encode == nullptr || p->mag == nullptr) return false;
     if ((reinterpret_cast<uintptr_t>(p->mag) & 15) || (p->mag_row_stride & 3) || (p->mag_clip_stride & 3)) return false;
     const cuuint64_t dims[3] = {static_cast<cuuint64_t>(p->n_frames), static_cast<cuuint64_t>(AEGIS_N_BINS), static_cast<cuuint64_t>(p->n_clips)};
