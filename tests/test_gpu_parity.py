@@ -99,6 +99,31 @@ def test_stft_ragged_batch_unaligned_rows_and_silence(dev):
         _assert_mag_close(o2["mag"][c].cpu().numpy(), L.stft_magnitude(view[c].cpu().numpy()))
 
 
+def test_stft_output_layouts_agree(dev):
+    """|X| through every store path of K1 -- TMA into the default pitched buffer, TMA into a dense caller buffer
+    (T % 4 == 0), the 16-byte LSU path (pitch % 4 == 0 but a misaligned base) and the scalar LSU path (odd pitch) --
+    is bit-identical, partial tiles at the clip end included; bytes outside the view are never touched."""
+    rng = np.random.default_rng(3)
+    for n_samples in (512 * 43, 512 * 44 + 100, 512 * 41 + 7):     # T = 44 (dense % 4 == 0), 45, 42
+        y = _dev(rng.normal(0, 0.2, (3, n_samples)).astype(np.float32), dev)
+        T = 1 + n_samples // 512
+        ref = P.core.stft_features(y, want_mag=True)["mag"]            # pitched view, TMA
+        assert ref.stride(1) % 8 == 0 and ref.shape == (3, 1025, T)
+        dense = torch.full((3, 1025, T), -1.0, device=dev)
+        P.core.stft_features(y, want_mag=True, mag_out=dense)
+        assert torch.equal(dense, ref)
+        big = torch.full((3, 1025, T + 6), -1.0, device=dev)
+        for off in (2, 1):                                           # base misaligned by 8 / 4 bytes
+            big.fill_(-1.0)
+            view = big[:, :, off:off + T]
+            P.core.stft_features(y, want_mag=True, mag_out=view)
+            assert torch.equal(view, ref)
+            assert bool((big[:, :, :off] == -1.0).all()) and bool((big[:, :, off + T:] == -1.0).all())
+        odd = torch.full((3, 1025, T + 1), -1.0, device=dev)          # row pitch T + 1
+        P.core.stft_features(y, want_mag=True, mag_out=odd[:, :, :T])
+        assert torch.equal(odd[:, :, :T], ref) and bool((odd[:, :, T] == -1.0).all())
+
+
 def test_stft_hop_and_uncentred(dev):
     y, sr = SIGNALS["clip3"]()
     for hop in (128, 256):
