@@ -14,6 +14,7 @@
 // Energy / cumulative sums are prefix scans in double; the trough/threshold/prior stage runs one
 // warp per frame with ballot compaction and shuffle reductions.
 #include <cfloat>
+#include <cstddef>
 #include "common.cuh"
 #include "fft2048.cuh"
 
@@ -27,12 +28,11 @@ constexpr int YIN_MAX_TROUGHS = 512;
 struct YinSmem {
     float en_part[2][4];  // per-warp partial frame energies (packing scale)
     float samples[FFT_N + YIN_MAX_HOP];
-    cf bufA[BUFA_SIZE];   // bufA+bufB are reused as YinScratchE once the transforms are done
-    cf bufB[BUFB_SIZE];
+    cf buf[BUFA_SIZE];    // the transforms' single exchange buffer (in place); buf + P1 are reused as YinScratchE
+    cf P1[FFT_N / 2 + 4]; // once the transforms are done (must follow buf directly)
     cf Z[FFT_N];          // reused as YinScratchC in the candidate phase
-    cf P1[FFT_N / 2 + 1];
 };
-struct YinScratchE {       // lives in bufA..bufB (33 920 B)
+struct YinScratchE {       // lives in buf..P1 (25 632 B)
     double yin[2][YIN_MAX_LAGS];
     float d[2][YIN_MAX_LAGS];
     double tot[2][64];
@@ -43,7 +43,8 @@ struct YinScratchC {       // lives in Z (16 384 B)
     unsigned short tk[2][YIN_MAX_TROUGHS];
     unsigned char tq[2][YIN_MAX_TROUGHS];
 };
-static_assert(sizeof(YinScratchE) <= sizeof(cf) * (BUFA_SIZE + BUFB_SIZE), "scratch E too large");
+static_assert(sizeof(YinScratchE) <= sizeof(cf) * (BUFA_SIZE + FFT_N / 2 + 4), "scratch E too large");
+static_assert(offsetof(YinSmem, P1) == offsetof(YinSmem, buf) + sizeof(cf) * BUFA_SIZE, "P1 must follow buf");
 static_assert(sizeof(YinScratchC) <= sizeof(cf) * FFT_N, "scratch C too large");
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -52,24 +53,33 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-// forward transform of x[n] = in[n] (natural order, complex) through the three passes; result in out
-__device__ __forceinline__ void fft_from_natural(int lt, const cf* in, const FftTwiddles& tw, cf* bufA, cf* bufB, cf* out) {
-    cf v[16];
-#pragma unroll
-    for (int a = 0; a < 16; ++a) v[a] = in[lt + 128 * a];
-    fft2048_pass1(lt, v, tw, bufA);
+// passes 2 and 3 of a transform whose pass 1 has been written to buf, in place (one exchange buffer: 17 KB less
+// shared memory than ping-ponging two, which is what lets a fourth CTA fit on the SM); natural-order result in out
+__device__ __forceinline__ void fft_finish_inplace(int lt, cf* v, const FftTwiddles& tw, cf* buf, cf* out) {
     __syncthreads();
-    fft2048_pass2(lt, tw, bufA, bufB);
+    fft2048_pass2_load(lt, buf, v);
     __syncthreads();
-    fft2048_pass3(lt, bufB, out);
+    fft2048_pass2_store(lt, v, tw, buf);
+    __syncthreads();
+    fft2048_pass3_load(lt, buf, v);
+    fft2048_pass3_store(lt, v, out);   // out != buf: no barrier needed between the two halves
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(YIN_THREADS, 3)
+// forward transform of x[n] = in[n] (natural order, complex); result in out (may alias in)
+__device__ __forceinline__ void fft_from_natural(int lt, const cf* in, const FftTwiddles& tw, cf* buf, cf* out) {
+    cf v[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) v[a] = in[lt + 128 * a];
+    fft2048_pass1(lt, v, tw, buf);
+    fft_finish_inplace(lt, v, tw, buf, out);
+}
+
+__global__ void __launch_bounds__(YIN_THREADS, 4)
 yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n_pairs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     YinSmem& s = *reinterpret_cast<YinSmem*>(smem_raw);
-    YinScratchE& se = *reinterpret_cast<YinScratchE*>(s.bufA);
+    YinScratchE& se = *reinterpret_cast<YinScratchE*>(s.buf);
     YinScratchC& sc = *reinterpret_cast<YinScratchC*>(s.Z);
     const int lt = threadIdx.x, lane = lt & 31, warp = lt >> 5;
     const int T = p.n_frames, hop = p.hop;
@@ -125,13 +135,9 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
                     const int n = lt + 128 * a;
                     v[a] = cf{f[n] * sc, (a < 8) ? f[FFT_N / 2 - n] * sc : 0.f};
                 }
-                fft2048_pass1(lt, v, tw, s.bufA);
+                fft2048_pass1(lt, v, tw, s.buf);
+                fft_finish_inplace(lt, v, tw, s.buf, s.Z);
             }
-            __syncthreads();
-            fft2048_pass2(lt, tw, s.bufA, s.bufB);
-            __syncthreads();
-            fft2048_pass3(lt, s.bufB, s.Z);
-            __syncthreads();
             // P = (2A)(2B) with 2A = Z[k] + conj Z[N-k], 2B = (Z[k] - conj Z[N-k]) / i
 #pragma unroll
             for (int m = 0; m < 9; ++m) {
@@ -154,7 +160,7 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
             __syncthreads();
         }
         // ---- one transform inverts both: q[n] = conj(FFT(conj Q)[n]) / N = acf1[n] + i*acf2[n]
-        fft_from_natural(lt, s.Z, tw, s.bufA, s.bufB, s.Z);
+        fft_from_natural(lt, s.Z, tw, s.buf, s.Z);
 
         // ---- phase E: energies, difference function, cumulative mean, CMND (64 threads / frame)
         {
@@ -361,7 +367,7 @@ extern "C" int aegis_yin_candidates(const aegis_yin_params* p, void* stream) {
         set_error("aegis_yin_candidates: cannot reserve %zu B shared memory: %s", sizeof(YinSmem), cudaGetErrorString(e));
         return 2;
     }
-    const long long max_grid = static_cast<long long>(sm_count()) * 3;
+    const long long max_grid = static_cast<long long>(sm_count()) * 4;
     const int grid = static_cast<int>(n_pairs < max_grid ? n_pairs : max_grid);
     yin_kernel<<<grid, YIN_THREADS, sizeof(YinSmem), static_cast<cudaStream_t>(stream)>>>(*p, pairs_per_clip, n_pairs);
     return check_launch("aegis_yin_candidates");
