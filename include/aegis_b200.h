@@ -322,6 +322,72 @@ int aegis_note_events(const aegis_notes_params* p, void* stream);
 long long aegis_note_events_bytes(int n_clips, int n_frames, int max_events);
 
 /* ---------------------------------------------------------------------------------------------
+ * K8  v2 ("financial") logic filter: frames -> note events, with the RSI ghost-note filter and the key /
+ *     out-of-scale / chord-context pass
+ * replaces: get_midi_events_financial with use_financial=True (aegis_engine_core_v2/midi_logic_financial.py:117-388,
+ *           called from aegis_engine_financial.py:160-171), adaptive_confidence_threshold (:77-114),
+ *           FinancialPitchAnalyzer.{detect_articulation_bollinger,detect_slides_macd,rsi,filter_ghost_notes_rsi}
+ *           (aegis_engine_core_v2/financial_analysis.py:148-196,228-271,277-364) and HarmonicAnalyzer.{detect_key,
+ *           filter_out_of_scale_notes,analyze_chord_progression,adaptive_filter_by_context}
+ *           (aegis_engine_core_v2/harmonic_analysis.py:46-283).
+ * Three calls: aegis_fin_prepare writes f0_clean (f0 where voiced, else NaN), its MIDI-number series and the rms dB
+ * scratch; the caller runs aegis_trend_filters on f0_clean (consensus, Bollinger bands window 10 / 2 sigma) and on
+ * the semitone series (MACD 5/20/9); aegis_fin_events turns the frames into events.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t note;              /* MIDI note number */
+    int32_t start;             /* first frame */
+    int32_t end;               /* last frame (inclusive) */
+    int32_t velocity;          /* 0..127 */
+    uint8_t track;             /* 1 = main (confidence >= threshold), 0 = safe */
+    uint8_t technique;         /* = financial_artic: 0 None, 1 normal, 2 bend, 3 vibrato, 4 noise */
+    uint8_t slide;             /* financial_slide at the start frame: 0 None, 1 normal, 2 slide_up, 3 slide_down */
+    int8_t harmonic_valid;     /* -1 key absent (nothing was out of scale), 1 True */
+    uint8_t _pad[4];
+    double confidence;         /* 0.5 voiced_prob + 0.5 Bollinger confidence at the start frame, after the context pass */
+} aegis_fin_event;
+
+typedef struct {
+    const uint8_t* rake_mask;  /* [n_clips][n_frames] */
+    const double* f0;          /* [n_clips][n_frames] Hz, NaN = no pitch */
+    const uint8_t* voiced_flag;/* [n_clips][n_frames] */
+    const double* voiced_prob; /* [n_clips][n_frames] */
+    const float* rms;          /* [n_clips][rms_clip_stride] */
+    int64_t rms_clip_stride;
+    int32_t n_clips;
+    int32_t n_frames;
+    int32_t hop;
+    int32_t _reserved0;
+    double sr;
+    double* f0_clean;          /* [n_clips][n_frames] written by aegis_fin_prepare */
+    double* semitones;         /* [n_clips][n_frames] written by aegis_fin_prepare */
+    const double* trend;       /* consensus of aegis_trend_filters(f0_clean) */
+    const double* boll_upper;  /* bands of aegis_trend_filters(f0_clean), window 10, 2 sigma */
+    const double* boll_lower;
+    const double* macd_line;   /* aegis_trend_filters(semitones), 5 / 20 / 9 */
+    const double* macd_hist;
+    double confidence_threshold; /* NaN = adaptive: clip(mean - std of the positive confidences, 0.3, 0.8) */
+    double slide_threshold;    /* 0.3 in the reference */
+    double rsi_threshold;      /* 70 in the reference */
+    float noise_gate_db;       /* -40 in the reference */
+    int32_t min_note_frames;   /* int(min_note_duration_ms / 1000 * sr / hop) */
+    int32_t sustain_frames;    /* int(sustain_ms / 1000 * sr / hop) */
+    int32_t use_harmonic_filter;
+    int32_t harmonic_tolerance;/* semitones a note may lie off the detected scale (reference default 1) */
+    int32_t max_events;        /* capacity per clip; n_frames / (min_note_frames + 1) + 1 always suffices */
+    aegis_fin_event* events;   /* [n_clips][max_events] */
+    int32_t* n_events;         /* [n_clips]; a value > max_events means the clip overflowed and its records are invalid */
+    double* threshold_out;     /* [n_clips] threshold in force, or NULL */
+    int32_t* key_out;          /* [n_clips] root | mode << 8 (mode 0 major, 1 minor, 2 blues) when notes were removed, else -1; or NULL */
+    double* key_confidence_out;/* [n_clips] or NULL */
+    void* scratch;             /* aegis_fin_scratch_bytes(n_clips, n_frames) bytes; shared by the two calls */
+} aegis_fin_params;
+
+int aegis_fin_prepare(const aegis_fin_params* p, void* stream);
+int aegis_fin_events(const aegis_fin_params* p, void* stream);
+long long aegis_fin_scratch_bytes(int n_clips, int n_frames);
+
+/* ---------------------------------------------------------------------------------------------
  * Corpus synthesis on device (Karplus-Strong plucks + noise rakes, generate_test_signal.py:5-53)
  * One event per note/rake; events of a clip do not overlap.  out must be zero-filled.
  * ------------------------------------------------------------------------------------------- */

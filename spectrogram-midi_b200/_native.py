@@ -127,6 +127,27 @@ class NotesParams(C.Structure):
     ]
 
 
+class FinEvent(C.Structure):
+    _fields_ = [
+        ("note", i32), ("start", i32), ("end", i32), ("velocity", i32),
+        ("track", C.c_uint8), ("technique", C.c_uint8), ("slide", C.c_uint8), ("harmonic_valid", C.c_int8),
+        ("_pad", C.c_uint8 * 4), ("confidence", f64),
+    ]
+
+
+class FinParams(C.Structure):
+    _fields_ = [
+        ("rake_mask", _ptr), ("f0", _ptr), ("voiced_flag", _ptr), ("voiced_prob", _ptr),
+        ("rms", _ptr), ("rms_clip_stride", i64), ("n_clips", i32), ("n_frames", i32), ("hop", i32), ("_reserved0", i32),
+        ("sr", f64), ("f0_clean", _ptr), ("semitones", _ptr), ("trend", _ptr), ("boll_upper", _ptr), ("boll_lower", _ptr),
+        ("macd_line", _ptr), ("macd_hist", _ptr), ("confidence_threshold", f64), ("slide_threshold", f64),
+        ("rsi_threshold", f64), ("noise_gate_db", f32), ("min_note_frames", i32), ("sustain_frames", i32),
+        ("use_harmonic_filter", i32), ("harmonic_tolerance", i32), ("max_events", i32),
+        ("events", _ptr), ("n_events", _ptr), ("threshold_out", _ptr), ("key_out", _ptr), ("key_confidence_out", _ptr),
+        ("scratch", _ptr),
+    ]
+
+
 ENTRY_POINTS = {
     "aegis_stft_fused": StftParams,
     "aegis_mel_post": MelPostParams,
@@ -137,6 +158,8 @@ ENTRY_POINTS = {
     "aegis_synth_ks": SynthParams,
     "aegis_guitar_filters": GuitarParams,
     "aegis_note_events": NotesParams,
+    "aegis_fin_prepare": FinParams,
+    "aegis_fin_events": FinParams,
 }
 
 _lib = None
@@ -161,6 +184,8 @@ def load() -> C.CDLL:
     lib.aegis_device_sm_count.restype = C.c_int
     lib.aegis_note_events_bytes.restype = C.c_longlong
     lib.aegis_note_events_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.aegis_fin_scratch_bytes.restype = C.c_longlong
+    lib.aegis_fin_scratch_bytes.argtypes = [C.c_int, C.c_int]
     lib.aegis_guitar_blocks.restype = C.c_int
     lib.aegis_guitar_blocks.argtypes = [C.c_int]
     for name, struct in ENTRY_POINTS.items():

@@ -106,6 +106,17 @@ def note_events_batch(result: dict, *, sr: float, hop_length: int = 512, fmin: f
                             pitch_index=result["states"], note_lut=torch.from_numpy(lut).to(dev), **kwargs)
 
 
+def note_events_financial_batch(result: dict, *, sr: float, hop_length: int = 512, confidence_threshold=None, **kwargs) -> dict:
+    """v2 logic-filter phase for a whole batch on the device: ``get_midi_events_financial``
+    (midi_logic_financial.py:117-388) applied to an ``analyze_batch(nan_to_num=False)`` result; palm-muted frames
+    (``with_guitar=True``) are removed from the voiced flags first, as aegis_engine_financial.py:147 does."""
+    voiced = result["voiced_flag"].to(torch.uint8)
+    if "mute_mask" in result:
+        voiced = voiced & (result["mute_mask"].to(torch.uint8) ^ 1)
+    return core.note_events_financial(result["rake_mask"], result["f0"], voiced, result["voiced_probs"], result["rms"],
+                                      sr=sr, hop_length=hop_length, confidence_threshold=confidence_threshold, **kwargs)
+
+
 def to_host(result: dict, clip: int, y: Optional[np.ndarray] = None) -> dict:
     """One clip of a batch result as the reference's perception dict (numpy, aegis_engine.py:72-75)."""
     host = {

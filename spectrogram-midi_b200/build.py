@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-        extra = ["-fmad=false"] if os.path.basename(src) == "trend.cu" else []  # keep the reference's IEEE op order
+        extra = ["-fmad=false"] if os.path.basename(src) in ("trend.cu", "notes_fin.cu") else []  # keep the reference's IEEE op order
         cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

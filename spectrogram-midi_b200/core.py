@@ -497,6 +497,103 @@ def note_events_to_list(events: torch.Tensor, n_events: torch.Tensor, clip: int)
 
 
 # ----------------------------------------------------------------------------------------------
+# K8
+# ----------------------------------------------------------------------------------------------
+FIN_EVENT_DTYPE = np.dtype([("note", "<i4"), ("start", "<i4"), ("end", "<i4"), ("velocity", "<i4"), ("track", "u1"),
+                            ("technique", "u1"), ("slide", "u1"), ("harmonic_valid", "i1"), ("_pad", "u1", (4,)),
+                            ("confidence", "<f8")])
+FIN_ARTICULATIONS = (None, "normal", "bend", "vibrato", "noise")        # detect_articulation_bollinger's labels
+FIN_SLIDES = (None, "normal", "slide_up", "slide_down")                 # detect_slides_macd's labels
+KEY_NAMES = ("C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B")
+KEY_MODES = ("major", "minor", "blues")
+
+
+def note_events_financial(rake_mask: torch.Tensor, f0: torch.Tensor, voiced_flag: torch.Tensor, voiced_prob: torch.Tensor,
+                          rms: torch.Tensor, *, sr: float, hop_length: int = 512, confidence_threshold: Optional[float] = None,
+                          noise_gate_db: float = -40, sustain_ms: float = 50, min_note_duration_ms: float = 50,
+                          use_harmonic_filter: bool = True, harmonic_tolerance: int = 1, slide_threshold: float = 0.3,
+                          rsi_threshold: float = 70, max_events: Optional[int] = None) -> dict:
+    """``get_midi_events_financial(use_financial=True)`` for a batch
+    (aegis_engine_core_v2/midi_logic_financial.py:117-388): frame arrays [n_clips, T] in (``f0`` in Hz with NaN where
+    unvoiced, as pYIN returns it), ``events`` (uint8 [n_clips, max_events, 32], records of ``FIN_EVENT_DTYPE``),
+    ``n_events`` int32, ``threshold`` f64, ``key`` int32 (root | mode << 8, -1 when no note was out of scale) and
+    ``key_confidence`` f64 out, all [n_clips].  Launches K8 prepare, K5 twice (f0 series, semitone series), K8 events.
+    """
+    if not f0.is_cuda:
+        raise nat.AegisNativeError("expected CUDA tensors: the Aegis B200 path has no CPU implementation")
+    f0 = f0.to(torch.float64).contiguous()
+    n_clips, T = f0.shape
+    dev = f0.device
+    rake_mask = rake_mask.to(torch.uint8).contiguous()
+    voiced_flag = voiced_flag.to(torch.uint8).contiguous()
+    voiced_prob = voiced_prob.to(torch.float64).contiguous()
+    if rms.dtype != torch.float32 or rms.stride(-1) != 1:
+        rms = rms.float().contiguous()
+    for name, t in (("rake_mask", rake_mask), ("voiced_flag", voiced_flag), ("voiced_prob", voiced_prob), ("rms", rms)):
+        if tuple(t.shape) != (n_clips, T):
+            raise ValueError(f"{name} must be [n_clips, T] like f0")
+    min_frames, sustain_frames = note_frame_limits(sr, hop_length, sustain_ms, min_note_duration_ms)
+    if max_events is None:   # an event that survives the duration filter spans min_frames + 1 frames
+        max_events = T // (min_frames + 1) + 1
+    P = nat.FinParams()
+    P.rake_mask, P.f0, P.voiced_flag, P.voiced_prob = rake_mask.data_ptr(), f0.data_ptr(), voiced_flag.data_ptr(), voiced_prob.data_ptr()
+    P.rms, P.rms_clip_stride = rms.data_ptr(), rms.stride(0)
+    P.n_clips, P.n_frames, P.hop, P.sr = n_clips, T, hop_length, float(sr)
+    f0_clean = torch.empty_like(f0)
+    semitones = torch.empty_like(f0)
+    scratch = torch.empty((int(nat.load().aegis_fin_scratch_bytes(n_clips, T)),), dtype=torch.uint8, device=dev)
+    P.f0_clean, P.semitones, P.scratch = f0_clean.data_ptr(), semitones.data_ptr(), scratch.data_ptr()
+    nat.call("aegis_fin_prepare", P, _stream())
+    events = torch.zeros((n_clips, max_events, FIN_EVENT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    n_events = torch.zeros((n_clips,), dtype=torch.int32, device=dev)
+    threshold = torch.empty((n_clips,), dtype=torch.float64, device=dev)
+    key = torch.empty((n_clips,), dtype=torch.int32, device=dev)
+    key_conf = torch.empty((n_clips,), dtype=torch.float64, device=dev)
+    if T > 0 and n_clips > 0:
+        a = trend_filters(f0_clean, want=("consensus", "boll_upper", "boll_lower"), boll_window=10, boll_num_std=2.0)
+        m = trend_filters(semitones, want=("macd_line", "macd_hist"), macd_fast=5, macd_slow=20, macd_signal=9)
+        P.trend, P.boll_upper, P.boll_lower = a["consensus"].data_ptr(), a["boll_upper"].data_ptr(), a["boll_lower"].data_ptr()
+        P.macd_line, P.macd_hist = m["macd_line"].data_ptr(), m["macd_hist"].data_ptr()
+        P.confidence_threshold = float("nan") if confidence_threshold is None else float(confidence_threshold)
+        P.slide_threshold, P.rsi_threshold, P.noise_gate_db = float(slide_threshold), float(rsi_threshold), float(noise_gate_db)
+        P.min_note_frames, P.sustain_frames, P.max_events = min_frames, sustain_frames, max_events
+        P.use_harmonic_filter, P.harmonic_tolerance = int(bool(use_harmonic_filter)), int(harmonic_tolerance)
+        P.events, P.n_events = events.data_ptr(), n_events.data_ptr()
+        P.threshold_out, P.key_out, P.key_confidence_out = threshold.data_ptr(), key.data_ptr(), key_conf.data_ptr()
+        nat.call("aegis_fin_events", P, _stream())
+    else:
+        threshold.fill_(0.5 if confidence_threshold is None else float(confidence_threshold))
+        key.fill_(-1)
+        key_conf.zero_()
+    return {"events": events, "n_events": n_events, "max_events": max_events, "threshold": threshold, "key": key,
+            "key_confidence": key_conf}
+
+
+def fin_events_to_list(res: dict, clip: int) -> list:
+    """One clip's records as the reference's list of dicts (keys of midi_logic_financial.py:222-231,361-384)."""
+    events, n = res["events"], int(res["n_events"][clip])
+    if n > events.shape[1]:
+        raise nat.AegisNativeError(f"clip {clip}: {n} note events exceed the buffer of {events.shape[1]}")
+    key = int(res["key"][clip])
+    if key >= 0 and n == 0:
+        raise IndexError("list index out of range")   # the reference indexes events[0] after removing every note
+    rec = events[clip, :n].cpu().numpy().reshape(-1).view(FIN_EVENT_DTYPE) if n else np.zeros(0, FIN_EVENT_DTYPE)
+    out = []
+    for r in rec:
+        art = FIN_ARTICULATIONS[int(r["technique"])]
+        e = {"note": int(r["note"]), "start": int(r["start"]), "end": int(r["end"]), "confidence": float(r["confidence"]),
+             "velocity": int(r["velocity"]), "track": "main" if r["track"] else "safe", "financial_artic": art,
+             "financial_slide": FIN_SLIDES[int(r["slide"])], "technique": art}
+        if r["harmonic_valid"] >= 0:
+            e["harmonic_valid"] = bool(r["harmonic_valid"])
+        out.append(e)
+    if key >= 0 and out:
+        out[0]["key_info"] = {"key": KEY_NAMES[key & 0xFF], "mode": KEY_MODES[key >> 8],
+                              "confidence": float(res["key_confidence"][clip])}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # corpus synthesis
 # ----------------------------------------------------------------------------------------------
 def synth_events(n_clips: int, n_samples: int, events: dict, device, decay: float = 0.996) -> torch.Tensor:

@@ -20,29 +20,27 @@ constexpr int GF_THREADS = 256;
 constexpr int GF_HALO = 32;
 constexpr int GF_OWN = GF_THREADS - 2 * GF_HALO;  // 192
 
-// numpy's float32 add.reduce over a contiguous 1-D slice a[0..n): a[0] + pairwise_sum(a[1..n))
+// numpy's float32 add.reduce over a contiguous 1-D slice a[0..n), n <= 128: pairwise_sum's leaf (eight running
+// sums combined as a tree, the remainder added one by one; fewer than eight elements are added in order)
 __device__ __forceinline__ float numpy_sum_f32(const float* a, int n) {
-    if (n <= 0) return 0.f;
-    const float* r = a + 1;
-    const int m = n - 1;
     float res;
-    if (m < 8) {
+    if (n < 8) {
         res = 0.f;
-        for (int i = 0; i < m; ++i) res = __fadd_rn(res, r[i]);
-    } else {   // m <= 128 here (rake_frames <= 30)
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+    } else {
         float acc[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = r[j];
+        for (int j = 0; j < 8; ++j) acc[j] = a[j];
         int i = 8;
-        for (; i < m - (m % 8); i += 8) {
+        for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], r[i + j]);
+            for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], a[i + j]);
         }
         res = __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), __fadd_rn(acc[2], acc[3])),
                         __fadd_rn(__fadd_rn(acc[4], acc[5]), __fadd_rn(acc[6], acc[7])));
-        for (; i < m; ++i) res = __fadd_rn(res, r[i]);
+        for (; i < n; ++i) res = __fadd_rn(res, a[i]);
     }
-    return __fadd_rn(a[0], res);
+    return res;
 }
 
 __global__ void __launch_bounds__(GF_THREADS)

@@ -16,33 +16,11 @@
 #include <cfloat>
 #include <cmath>
 #include "common.cuh"
+#include "notes_common.cuh"
 
 namespace aegis {
 
 constexpr int NT_THREADS = 256;
-
-__device__ __forceinline__ float db10_f32(float power, float amin) {
-    // 10.0 * np.log10(np.maximum(amin, power)) in float32
-    const float v = fmaxf(amin, power);
-    return __fmul_rn(10.0f, static_cast<float>(log10(static_cast<double>(v))));
-}
-
-// per clip: max of |rms| (the reference of amplitude_to_db)
-__global__ void __launch_bounds__(NT_THREADS)
-notes_rms_max_kernel(const aegis_notes_params p, float* __restrict__ rms_max) {
-    __shared__ float red[NT_THREADS / 32];
-    const int clip = blockIdx.x;
-    const float* r = p.rms + static_cast<long long>(clip) * p.rms_clip_stride;
-    float m = 0.f;
-    for (int t = threadIdx.x; t < p.n_frames; t += NT_THREADS) m = fmaxf(m, fabsf(r[t]));
-    m = warp_max(m);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < NT_THREADS / 32; ++w) m = fmaxf(m, red[w]);
-        rms_max[clip] = m;
-    }
-}
 
 // per frame: rms dB and MIDI note (or -1)
 __global__ void __launch_bounds__(NT_THREADS)
@@ -51,14 +29,7 @@ notes_frames_kernel(const aegis_notes_params p, const float* __restrict__ rms_ma
     const int t = blockIdx.x * NT_THREADS + threadIdx.x;
     if (t >= p.n_frames) return;
     const long long i = static_cast<long long>(clip) * p.n_frames + t;
-    // amplitude_to_db(rms, ref=np.max): power_to_db(rms**2, ref=max**2, amin=1e-10, top_db=80) (librosa, float32)
-    const float amin = 1e-10f;
-    const float mag = fabsf(p.rms[static_cast<long long>(clip) * p.rms_clip_stride + t]);
-    const float ref = rms_max[clip];
-    float e = __fadd_rn(db10_f32(__fmul_rn(mag, mag), amin), -db10_f32(__fmul_rn(ref, ref), amin));
-    // top_db: max(log_spec, log_spec.max() - 80); the maximum is the reference frame itself
-    const float top = __fadd_rn(__fadd_rn(db10_f32(__fmul_rn(ref, ref), amin), -db10_f32(__fmul_rn(ref, ref), amin)), -80.0f);
-    e = fmaxf(e, top);
+    const float e = rms_db_f32(p.rms[static_cast<long long>(clip) * p.rms_clip_stride + t], rms_max[clip]);
     rms_db[i] = e;
     const double f = p.f0[i];
     const bool active = p.voiced_flag[i] != 0 && !(e < p.noise_gate_db) && f > 0.0 && p.rake_mask[i] == 0;
@@ -179,7 +150,7 @@ notes_events_kernel(const aegis_notes_params p, const float* __restrict__ rms_db
                 cur.start = t;
                 cur.energy = energy;
                 cur.confidence = conf;
-                cur.velocity = static_cast<int>(fminf(fmaxf(__fmul_rn(__fadd_rn(energy, 80.0f), 1.5f), 0.0f), 127.0f));
+                cur.velocity = velocity_from_db(energy);
                 cur.track = conf >= p.confidence_threshold ? 1 : 0;
                 sy = 0.0;
                 sxy = 0.0;
@@ -215,7 +186,7 @@ extern "C" int aegis_note_events(const aegis_notes_params* p, void* stream) {
     float* rms_db = rms_max + ((p->n_clips + 3) / 4) * 4;
     short* note = reinterpret_cast<short*>(rms_db + frames);
     if (p->n_frames > 0) {
-        notes_rms_max_kernel<<<p->n_clips, NT_THREADS, 0, st>>>(*p, rms_max);
+        rms_max_kernel<NT_THREADS><<<p->n_clips, NT_THREADS, 0, st>>>(p->rms, p->rms_clip_stride, p->n_frames, rms_max);
         if (int rc = check_launch("aegis_note_events(rms max)")) return rc;
         notes_frames_kernel<<<dim3((p->n_frames + NT_THREADS - 1) / NT_THREADS, p->n_clips), NT_THREADS, 0, st>>>(*p, rms_max, rms_db, note);
         if (int rc = check_launch("aegis_note_events(frames)")) return rc;

@@ -58,6 +58,30 @@ __device__ void holt_series(const double* __restrict__ x, double* __restrict__ o
     }
 }
 
+constexpr int BOLL_MAX_WINDOW = 128;
+
+// numpy's float64 add.reduce over a contiguous 1-D array of n <= 128 elements (pairwise_sum's leaf: eight running
+// sums combined as a tree, the remainder added one by one; fewer than eight elements are added in order)
+__device__ __forceinline__ double numpy_sum_f64(const double* a, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
+        return res;
+    }
+    double acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = __dadd_rn(acc[j], a[i + j]);
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(acc[0], acc[1]), __dadd_rn(acc[2], acc[3])),
+                           __dadd_rn(__dadd_rn(acc[4], acc[5]), __dadd_rn(acc[6], acc[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
 struct EmaState {
     double alpha, one_m_alpha, prev;
     __device__ EmaState(int span) : alpha(2.0 / static_cast<double>(span + 1)), prev(nan64()) { one_m_alpha = 1.0 - alpha; }
@@ -141,9 +165,10 @@ trend_kernel(const aegis_trend_params p) {
             if (!isnan(x[i])) {
                 double acc = 0.0;
                 const int lo = i - w / 2, hi = i + (w - 1) / 2;
+                // numpy's correlate is a dot product per output: ascending index, product rounded before the add
                 for (int k = max(lo, 0); k <= min(hi, n - 1); ++k) {
                     const double v = x[k];
-                    acc += (isnan(v) ? 0.0 : v) * kv;
+                    acc = __dadd_rn(acc, __dmul_rn(isnan(v) ? 0.0 : v, kv));
                 }
                 r = acc;
             }
@@ -168,16 +193,16 @@ trend_kernel(const aegis_trend_params p) {
     if (p.boll_upper || p.boll_lower) {
         const int w = p.boll_window;
         for (int i = tid; i < n; i += TR_THREADS) {
+            // np.std of the window's valid points, with numpy's summation order (bit-exact: on a steady pitch the
+            // band is a few ulps wide and the consumers compare f0 against it)
+            double v[BOLL_MAX_WINDOW];
             int cnt = 0;
-            double sum = 0.0;
-            const int lo = max(0, i - w + 1);
-            for (int k = lo; k <= i; ++k) { const double v = x[k]; if (!isnan(v)) { sum += v; ++cnt; } }
+            for (int k = max(0, i - w + 1); k <= i; ++k) { const double xv = x[k]; if (!isnan(xv)) v[cnt++] = xv; }
             double sd = nan64();
             if (cnt > 1) {
-                const double mean = sum / static_cast<double>(cnt);
-                double sq = 0.0;
-                for (int k = lo; k <= i; ++k) { const double v = x[k]; if (!isnan(v)) { const double d = v - mean; sq += d * d; } }
-                sd = sqrt(sq / static_cast<double>(cnt));
+                const double mean = numpy_sum_f64(v, cnt) / static_cast<double>(cnt);
+                for (int k = 0; k < cnt; ++k) { const double d = __dsub_rn(v[k], mean); v[k] = __dmul_rn(d, d); }
+                sd = sqrt(numpy_sum_f64(v, cnt) / static_cast<double>(cnt));
             }
             const double ma = p.boll_ma[off + i];
             const double dev = p.boll_num_std * sd;
@@ -232,7 +257,7 @@ extern "C" int aegis_trend_filters(const aegis_trend_params* p, void* stream) {
     }
     if (p->consensus || p->consensus_conf)
         AEGIS_REQUIRE(p->savgol && p->kalman && p->holt, "aegis_trend_filters: consensus needs savgol, kalman and holt outputs");
-    if (p->boll_upper || p->boll_lower) AEGIS_REQUIRE(p->boll_ma && p->boll_window >= 1, "aegis_trend_filters: bands need boll_ma");
+    if (p->boll_upper || p->boll_lower) AEGIS_REQUIRE(p->boll_ma && p->boll_window >= 1 && p->boll_window <= BOLL_MAX_WINDOW, "aegis_trend_filters: bands need boll_ma and 1 <= boll_window <= 128");
     if (p->sma) AEGIS_REQUIRE(p->sma_window >= 1, "aegis_trend_filters: bad sma_window");
     if (p->macd_sig || p->macd_hist) AEGIS_REQUIRE(p->macd_line != nullptr, "aegis_trend_filters: MACD signal/hist need macd_line");
     if (p->n_series == 0 || p->n == 0) return 0;

@@ -128,3 +128,17 @@ class AegisFinancialEngine:
         host = batch.to_host(res, 0, y=y)
         host["sr"], host["hop_length"] = self.sr, self.hop_length  # financial_app_realtime.py:224-233
         return host
+
+    def note_events(self, raw_data, confidence_threshold=None, **kwargs):
+        """Phase 4 of ``audio_to_midi_financial`` (:150-171): the financial logic filter on a ``perception`` result;
+        palm-muted frames are taken out of the voiced flags first (:147)."""
+        from .midi_logic_financial import get_midi_events_financial
+        voiced = np.asarray(raw_data["voiced_flag"], dtype=bool)
+        if "mute_mask" in raw_data:
+            voiced = voiced & ~np.asarray(raw_data["mute_mask"], dtype=bool)
+        skip = ("confidence_threshold", "rake_sensitivity", "use_financial", "use_guitar_filters", "start_time", "end_time")
+        return get_midi_events_financial(
+            rake_mask=raw_data["rake_mask"], f0=raw_data["f0"], voiced_flag=voiced, active_probs=raw_data["voiced_probs"],
+            rms=raw_data["rms"], sr=self.sr, hop_length=self.hop_length, confidence_threshold=confidence_threshold,
+            use_financial=kwargs.get("use_financial", True), **{k: v for k, v in kwargs.items() if k not in skip})
+

@@ -28,3 +28,13 @@ def guitar_golden():
     path = os.path.join(ROOT, "tests", "golden", "guitar_golden.npz")
     with np.load(path, allow_pickle=False) as z:
         return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def fin_golden():
+    import numpy as np
+
+    path = os.path.join(ROOT, "tests", "golden", "fin_events_golden.npz")
+    with np.load(path, allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}
+

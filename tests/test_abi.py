@@ -20,6 +20,7 @@ STRUCTS = {
     "aegis_viterbi_params": _native.ViterbiParams, "aegis_trend_params": _native.TrendParams,
     "aegis_synth_params": _native.SynthParams, "aegis_guitar_params": _native.GuitarParams,
     "aegis_note_event": _native.NoteEvent, "aegis_notes_params": _native.NotesParams,
+    "aegis_fin_event": _native.FinEvent, "aegis_fin_params": _native.FinParams,
 }
 
 
@@ -141,6 +142,9 @@ def test_host_side_frame_limits_and_note_table():
     assert core.NOTE_EVENT_DTYPE.itemsize == ctypes.sizeof(_native.NoteEvent) == 40
     for name in ("note", "start", "end", "velocity", "rms_energy", "track", "technique", "confidence", "slope"):
         assert core.NOTE_EVENT_DTYPE.fields[name][1] == getattr(_native.NoteEvent, name).offset, name
+    assert core.FIN_EVENT_DTYPE.itemsize == ctypes.sizeof(_native.FinEvent) == 32
+    for name in ("note", "start", "end", "velocity", "track", "technique", "slide", "harmonic_valid", "confidence"):
+        assert core.FIN_EVENT_DTYPE.fields[name][1] == getattr(_native.FinEvent, name).offset, name
     f0 = np.array([0.0, 110.0, 110.0, np.nan, 440.0, 82.4068892282175 * 2 ** (5 / 120.0), -3.0])
     idx, lut = midi_logic._note_lut(f0)
     assert idx.dtype == np.uint16 and lut.dtype == np.int16 and len(lut) == 3

@@ -575,6 +575,119 @@ def test_note_events_batch_from_states(dev):
         assert _event_rows(got)[0].tolist() == _event_rows(ref)[0].tolist()
 
 
+# ---------------------------------------------------------------------------------- K8 v2 logic filter
+def _fin_frames(seed, n, steady_grid=False):
+    """Frame series of a made-up performance (see tests/golden/make_golden_financial_events.py): notes with jitter,
+    vibrato, bends, slides and outliers, unvoiced gaps, rake frames, an energy envelope crossing the noise gate."""
+    r = np.random.default_rng(seed)
+    f0 = np.full(n, np.nan)
+    voiced = np.zeros(n, bool)
+    rms = np.full(n, 1e-4, dtype=np.float32)
+    t = int(r.integers(0, 6))
+    scale = np.array([40, 43, 45, 46, 47, 50, 52, 55, 57, 58, 59, 62, 64, 66, 69])
+    while t < n:
+        dur = int(r.integers(3, 60))
+        m = float(r.choice(scale)) + 0.37 * float(r.random() < 0.15)
+        k = np.arange(dur)
+        kind = r.integers(0, 6)
+        cents = np.zeros(dur) if (steady_grid and kind in (0, 5)) else r.normal(0, 4.0, dur)   # pYIN-like flat stretches
+        if kind == 1:
+            cents += 45.0 * np.sin(2 * np.pi * k / r.uniform(5, 9))
+        elif kind == 2:
+            cents += np.minimum(k * r.uniform(4, 14), 190.0)
+        elif kind == 3:
+            cents += k * r.uniform(-25, 25)
+        elif kind == 4:
+            cents[r.integers(0, dur, size=max(1, dur // 8))] += r.choice([-1, 1]) * r.uniform(60, 300)
+        e = min(n, t + dur)
+        f0[t:e] = 440.0 * 2.0 ** ((m - 69.0 + cents[: e - t] / 100.0) / 12.0)
+        voiced[t:e] = True
+        rms[t:e] = (r.uniform(0.004, 0.4) * np.exp(-k[: e - t] / r.uniform(15, 80))).astype(np.float32)
+        t = e + int(r.choice([0, 0, 1, 2, 3, 6, 12]))
+    voiced &= ~(r.random(n) < 0.03)
+    probs = np.where(voiced, r.uniform(0.25, 1.0, n), r.uniform(0.0, 0.3, n))
+    return r.random(n) < 0.02, np.where(voiced, f0, np.nan), voiced, probs, rms
+
+
+def test_financial_note_events_match_reference_golden(dev, fin_golden):
+    """aegis_fin_prepare / aegis_trend_filters / aegis_fin_events on the golden INPUT arrays == the events the REAL
+    aegis_engine_core_v2/midi_logic_financial.py produced from them: every integer field (note, frames, velocity,
+    track, articulation and slide labels, harmonic flag, key), confidences to 1e-12."""
+    from oracle import financial_events as FE
+    from spectrogram_midi_b200 import midi_logic_financial as MF
+
+    g = fin_golden
+    total = 0
+    for n in [str(v) for v in g["fin/names"]]:
+        (rake, f0, vf, vp, rms), sr, kw = FE.golden_case(g, n)
+        ev = MF.get_midi_events_financial(rake_mask=rake, f0=f0, voiced_flag=vf, active_probs=vp, rms=rms, sr=sr, hop_length=512,
+                                          use_financial=True, **kw)
+        ints, conf, key = FE.events_rows(ev)
+        np.testing.assert_array_equal(ints, g[f"fin/{n}/events"], err_msg=n)
+        np.testing.assert_allclose(conf, g[f"fin/{n}/confidence"], rtol=1e-12, atol=0, err_msg=n)
+        want_key = g[f"fin/{n}/key"]
+        if want_key[0] < 0:
+            assert key is None, n
+        else:
+            assert key is not None and key[:2] == (int(want_key[0]), int(want_key[1])), n
+            assert abs(key[2] - want_key[2]) < 1e-12
+        assert all(isinstance(e["note"], int) and e["track"] in ("main", "safe") for e in ev)
+        total += len(ev)
+    assert total > 200
+    with pytest.raises(NotImplementedError):
+        MF.get_midi_events_financial(rake, f0, vf, vp, rms, sr, 512, use_financial=False)
+    assert MF.get_midi_events_financial([], [], [], [], [], 22050, 512) == []
+
+
+@pytest.mark.parametrize("kw", [
+    {}, {"harmonic_tolerance": 0}, {"confidence_threshold": 0.55, "harmonic_tolerance": 0},
+    {"min_note_duration_ms": 0, "sustain_ms": 150, "use_harmonic_filter": False}, {"noise_gate_db": -22},
+])
+def test_financial_note_events_batch_equals_oracle(dev, kw):
+    """A batch of clips through core.note_events_financial (one launch sequence for all clips) == the pinned
+    restatement clip by clip, including the adaptive threshold, flat pYIN-like pitch stretches (bands a few ulps
+    wide) and a silent clip."""
+    from oracle import financial_events as FE
+
+    for sr, T in ((22050, 700), (44100, 1300)):
+        clips = [_fin_frames(100 + 7 * i + T, T, steady_grid=(i % 2 == 1)) for i in range(7)]
+        clips.append((np.zeros(T, bool), np.full(T, np.nan), np.zeros(T, bool), np.zeros(T), np.full(T, 1e-3, np.float32)))
+        stack = [torch.from_numpy(np.stack([c[j] for c in clips])).to(dev) for j in range(5)]
+        res = P.core.note_events_financial(*stack, sr=sr, hop_length=512, **kw)
+        thr = res["threshold"].cpu().numpy()
+        events = 0
+        for c, (rake, f0, vf, vp, rms) in enumerate(clips):
+            want = FE.get_midi_events_financial(rake, f0, vf, vp, rms, sr, 512, **kw)
+            got = P.core.fin_events_to_list(res, c)
+            wi, wc, wk = FE.events_rows(want)
+            gi, gc, gk = FE.events_rows(got)
+            np.testing.assert_array_equal(gi, wi, err_msg=f"clip {c} sr {sr}")
+            np.testing.assert_allclose(gc, wc, rtol=1e-12, atol=0)
+            assert (gk is None) == (wk is None) and (gk is None or (gk[:2] == wk[:2] and abs(gk[2] - wk[2]) < 1e-12))
+            if "confidence_threshold" not in kw:
+                S = FE.frame_series(f0, vf, vp)
+                np.testing.assert_allclose(thr[c], FE.adaptive_confidence_threshold(S["combined"]), rtol=1e-13)
+            events += len(want)
+        assert events > 20
+
+
+def test_financial_engine_note_events(dev):
+    """AegisFinancialEngine.perception -> note_events (K1..K6, K5, K8) == the restatement on the same host arrays."""
+    from oracle import financial_events as FE
+
+    y = corpus.random_clip(21, 14.0, 22050)
+    eng = P.engine.AegisFinancialEngine(sample_rate=22050)
+    raw = eng.perception(y)
+    got = eng.note_events(raw)
+    voiced = raw["voiced_flag"] & ~raw["mute_mask"]
+    want = FE.get_midi_events_financial(raw["rake_mask"], raw["f0"], voiced, raw["voiced_probs"], raw["rms"], 22050, 512)
+    assert len(want) >= 3
+    np.testing.assert_array_equal(FE.events_rows(got)[0], FE.events_rows(want)[0])
+    res = P.batch.analyze_batch(_dev(y[None], dev), sr=22050, nan_to_num=False, with_guitar=True)
+    ev = P.batch.note_events_financial_batch(res, sr=22050)
+    np.testing.assert_array_equal(FE.events_rows(P.core.fin_events_to_list(ev, 0))[0], FE.events_rows(want)[0])
+
+
 # ---------------------------------------------------------------------------------- K6 guitar filters
 def test_guitar_filters_match_reference_golden(dev, guitar_golden):
     """aegis_guitar_filters against the outputs of the real aegis_engine_core_v2/guitar_specific.py (bit-exact)."""

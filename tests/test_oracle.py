@@ -52,6 +52,29 @@ def test_guitar_filters_match_reference(guitar_golden):
     assert mute > 0 and added > 0 and seen == {0, 1, 2}  # every branch is exercised
 
 
+def test_financial_logic_filter_matches_reference(fin_golden):
+    """oracle restatement of aegis_engine_core_v2/midi_logic_financial.py (+ financial_analysis / harmonic_analysis)
+    against the real files' events: every integer field, the confidences bit for bit, and the key"""
+    from oracle import financial_events as FE
+
+    g = fin_golden
+    names = [str(n) for n in g["fin/names"]]
+    assert len(names) >= 15
+    total = keys = 0
+    labels = set()
+    for n in names:
+        frames, sr, kw = FE.golden_case(g, n)
+        ev = FE.get_midi_events_financial(*frames, sr, 512, **kw)
+        ints, conf, key = FE.events_rows(ev)
+        np.testing.assert_array_equal(ints, g[f"fin/{n}/events"], err_msg=n)
+        np.testing.assert_array_equal(conf, g[f"fin/{n}/confidence"], err_msg=n)
+        np.testing.assert_array_equal(np.array([-1.0, -1.0, 0.0] if key is None else key), g[f"fin/{n}/key"], err_msg=n)
+        total += len(ev)
+        keys += key is not None
+        labels |= set(ints[:, 5].tolist())
+    assert total > 200 and keys >= 4 and labels >= {1, 2, 3, 4}   # events, key detections and every label occur
+
+
 @pytest.mark.parametrize("key,fn", [
     ("savgol", lambda f: R.savitzky_golay(f)),
     ("kalman", lambda f: R.kalman_filter(f)),
