@@ -388,6 +388,33 @@ int aegis_fin_events(const aegis_fin_params* p, void* stream);
 long long aegis_fin_scratch_bytes(int n_clips, int n_frames);
 
 /* ---------------------------------------------------------------------------------------------
+ * K9  audio ingest: PCM -> float32, channel mix-down, polyphase rate conversion
+ * replaces: librosa.load(path, sr=engine rate) after the file read (aegis_engine.py:24, aegis_engine_financial.py:45):
+ *           soundfile's int16 -> float32 / 32768, librosa.to_mono, librosa.resample(res_type='polyphase')
+ *           = scipy.signal.resample_poly(y, up, down).  `taps` is scipy.signal.firwin(2 * 10 * max(up, down) + 1,
+ *           1 / max(up, down), window=('kaiser', 5.0)) in float32 times `up`; n_pre_pad = down - half_len % down,
+ *           n_pre_remove = (half_len + n_pre_pad) / down, n_out = ceil(n_in * up / down)  (scipy/signal/_signaltools.py).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* x;             /* [n_clips][in_clip_stride] float32 or int16, channels interleaved */
+    int64_t in_clip_stride;    /* elements */
+    int64_t n_in;              /* sample frames per clip */
+    int32_t in_format;         /* 0 float32, 1 int16 (scaled by 1 / 32768) */
+    int32_t n_channels;        /* 1..8, averaged */
+    int32_t n_clips;
+    int32_t up, down;          /* reduced ratio: target_sr / gcd, orig_sr / gcd */
+    int32_t n_taps;
+    const float* taps;         /* [n_taps] */
+    int32_t n_pre_pad;
+    int32_t n_pre_remove;
+    float* out;                /* [n_clips][out_clip_stride] */
+    int64_t out_clip_stride;
+    int64_t n_out;
+} aegis_resample_params;
+
+int aegis_resample_poly(const aegis_resample_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Corpus synthesis on device (Karplus-Strong plucks + noise rakes, generate_test_signal.py:5-53)
  * One event per note/rake; events of a clip do not overlap.  out must be zero-filled.
  * ------------------------------------------------------------------------------------------- */

@@ -510,3 +510,50 @@ def onset_detect(y=None, sr=22050, onset_envelope=None, hop_length=512, normaliz
         onset_envelope = onset_envelope - np.min(onset_envelope)
         onset_envelope = onset_envelope / (np.max(onset_envelope) + np.finfo(onset_envelope.dtype).tiny)
     return peak_pick(onset_envelope, **onset_detect_params(sr, hop_length))
+
+
+# --------------------------------------------------------------------------------------------
+# librosa.load's tail: to_mono + resample(res_type='polyphase') (aegis_engine.py:24, aegis_engine_financial.py:45)
+# Third-party: librosa.resample(res_type='polyphase') calls scipy.signal.resample_poly (scipy 1.18 here); its published
+# algorithm is restated below from first principles (zero stuffing, FIR, decimation) in float64 and pinned against
+# scipy.signal.resample_poly itself in tests/test_oracle.py.  librosa's DEFAULT res_type (soxr_hq, libsoxr) is absent
+# from this image: parity for it is unpinned and the product refuses it.
+# --------------------------------------------------------------------------------------------
+def kaiser_lowpass(up, down):
+    """scipy.signal.firwin(2 * 10 * max(up, down) + 1, 1 / max(up, down), window=('kaiser', 5.0)), written out."""
+    import scipy.special
+
+    max_rate = max(up, down)
+    half_len = 10 * max_rate
+    n = np.arange(-half_len, half_len + 1, dtype=np.float64)
+    fc = 1.0 / max_rate
+    h = fc * np.sinc(fc * n)
+    h *= scipy.special.i0(5.0 * np.sqrt(np.clip(1.0 - (n / half_len) ** 2, 0.0, None))) / scipy.special.i0(5.0)
+    return h / h.sum(), half_len
+
+
+def resample_polyphase(y, orig_sr, target_sr):
+    """librosa.resample(y, orig_sr=, target_sr=, res_type='polyphase') in float64 arithmetic, float32 result."""
+    y = np.asarray(y, dtype=np.float64)
+    g = int(np.gcd(int(orig_sr), int(target_sr)))
+    up, down = int(target_sr) // g, int(orig_sr) // g
+    if up == down == 1:
+        return y.astype(np.float32)
+    h, half_len = kaiser_lowpass(up, down)
+    h = h.astype(np.float32).astype(np.float64) * up        # scipy matches the filter's dtype to x before the gain
+    n_out = -(-len(y) * up // down)
+    stuffed = np.zeros(len(y) * up)
+    stuffed[::up] = y
+    full = np.convolve(stuffed, h)                          # full[n + half_len] is centred on stuffed sample n
+    idx = half_len + np.arange(n_out) * down
+    out = np.zeros(n_out)
+    ok = idx < len(full)
+    out[ok] = full[idx[ok]]
+    return out.astype(np.float32)
+
+
+def to_mono(y):
+    """librosa.to_mono: mean over the channel axis of [channels, n]."""
+    y = np.asarray(y)
+    return np.mean(y, axis=0) if y.ndim > 1 else y
+

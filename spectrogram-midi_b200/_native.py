@@ -148,6 +148,14 @@ class FinParams(C.Structure):
     ]
 
 
+class ResampleParams(C.Structure):
+    _fields_ = [
+        ("x", _ptr), ("in_clip_stride", i64), ("n_in", i64), ("in_format", i32), ("n_channels", i32),
+        ("n_clips", i32), ("up", i32), ("down", i32), ("n_taps", i32), ("taps", _ptr),
+        ("n_pre_pad", i32), ("n_pre_remove", i32), ("out", _ptr), ("out_clip_stride", i64), ("n_out", i64),
+    ]
+
+
 ENTRY_POINTS = {
     "aegis_stft_fused": StftParams,
     "aegis_mel_post": MelPostParams,
@@ -160,6 +168,7 @@ ENTRY_POINTS = {
     "aegis_note_events": NotesParams,
     "aegis_fin_prepare": FinParams,
     "aegis_fin_events": FinParams,
+    "aegis_resample_poly": ResampleParams,
 }
 
 _lib = None

@@ -594,6 +594,46 @@ def fin_events_to_list(res: dict, clip: int) -> list:
 
 
 # ----------------------------------------------------------------------------------------------
+# K9
+# ----------------------------------------------------------------------------------------------
+def resample_poly(x: torch.Tensor, orig_sr: int, target_sr: int, *, n_channels: int = 1) -> torch.Tensor:
+    """``librosa.resample(y, orig_sr=, target_sr=, res_type='polyphase')`` for a batch, fused with the PCM -> float
+    conversion and ``librosa.to_mono``: ``x`` is [n_clips, n_frames * n_channels] float32 or int16 (channels
+    interleaved, int16 scaled by 1/32768 as soundfile does); returns float32 [n_clips, ceil(n_frames * target / orig)],
+    bit-identical to ``scipy.signal.resample_poly`` on the float32 mono signal.  Equal rates only convert and mix."""
+    if not x.is_cuda:
+        raise nat.AegisNativeError("expected a CUDA tensor: the Aegis B200 path has no CPU implementation")
+    if int(orig_sr) != orig_sr or int(target_sr) != target_sr or orig_sr <= 0 or target_sr <= 0:
+        raise ValueError("polyphase resampling needs positive integer sample rates")   # as librosa.resample does
+    if x.dtype not in (torch.float32, torch.int16):
+        raise ValueError("x must be float32 or int16")
+    if x.dim() == 1:
+        x = x[None]
+    x = x.contiguous()
+    n_clips, width = x.shape
+    if n_channels < 1 or width % n_channels:
+        raise ValueError("row length must be a multiple of n_channels")
+    n_in = width // n_channels
+    g = int(np.gcd(int(orig_sr), int(target_sr)))
+    up, down = int(target_sr) // g, int(orig_sr) // g
+    n_out = -(-n_in * up // down)
+    out = torch.empty((n_clips, n_out), dtype=torch.float32, device=x.device)
+    if up == down == 1:     # identity filter: one tap of weight 1 at the output sample
+        taps, n_pre_pad, n_pre_remove = np.ones(1, np.float32), 0, 0
+    else:
+        taps, n_pre_pad, n_pre_remove = tables.resample_poly_design(up, down)
+    taps_d = _dev_tensor(("resample", up, down), x.device, lambda: taps)
+    P = nat.ResampleParams()
+    P.x, P.in_clip_stride, P.n_in = x.data_ptr(), x.stride(0), n_in
+    P.in_format, P.n_channels, P.n_clips = (1 if x.dtype == torch.int16 else 0), n_channels, n_clips
+    P.up, P.down, P.n_taps, P.taps = up, down, int(taps_d.numel()), taps_d.data_ptr()
+    P.n_pre_pad, P.n_pre_remove = n_pre_pad, n_pre_remove
+    P.out, P.out_clip_stride, P.n_out = out.data_ptr(), out.stride(0), n_out
+    nat.call("aegis_resample_poly", P, _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # corpus synthesis
 # ----------------------------------------------------------------------------------------------
 def synth_events(n_clips: int, n_samples: int, events: dict, device, decay: float = 0.996) -> torch.Tensor:

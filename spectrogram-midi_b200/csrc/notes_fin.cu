@@ -59,8 +59,9 @@ inline FinScratch carve_scratch(void* base, int n_clips, int n_frames) {
 
 __global__ void __launch_bounds__(NF_THREADS)
 fin_prepare_kernel(const aegis_fin_params p, const float* __restrict__ rms_max, float* __restrict__ rms_db) {
-    const int clip = blockIdx.y;
-    const int t = blockIdx.x * NF_THREADS + threadIdx.x;
+    const int blocks_per_clip = (p.n_frames + NF_THREADS - 1) / NF_THREADS;
+    const int clip = blockIdx.x / blocks_per_clip;
+    const int t = (blockIdx.x - clip * blocks_per_clip) * NF_THREADS + threadIdx.x;
     if (t >= p.n_frames) return;
     const long long i = static_cast<long long>(clip) * p.n_frames + t;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -73,8 +74,9 @@ fin_prepare_kernel(const aegis_fin_params p, const float* __restrict__ rms_max, 
 
 __global__ void __launch_bounds__(NF_THREADS)
 fin_frames_kernel(const aegis_fin_params p, const float* __restrict__ rms_db, FinFrame* __restrict__ frames) {
-    const int clip = blockIdx.y;
-    const int t = blockIdx.x * NF_THREADS + threadIdx.x;
+    const int blocks_per_clip = (p.n_frames + NF_THREADS - 1) / NF_THREADS;
+    const int clip = blockIdx.x / blocks_per_clip;
+    const int t = (blockIdx.x - clip * blocks_per_clip) * NF_THREADS + threadIdx.x;
     if (t >= p.n_frames) return;
     const long long i = static_cast<long long>(clip) * p.n_frames + t;
     const double f = p.f0_clean[i];
@@ -429,6 +431,10 @@ fin_events_kernel(const aegis_fin_params p, const FinFrame* __restrict__ frames,
 
 }  // namespace aegis
 
+static unsigned frame_blocks(const aegis_fin_params* p) {
+    return static_cast<unsigned>(static_cast<long long>((p->n_frames + aegis::NF_THREADS - 1) / aegis::NF_THREADS) * p->n_clips);
+}
+
 static int fin_check_common(const aegis_fin_params* p, const char* who) {
     using namespace aegis;
     AEGIS_REQUIRE(p != nullptr, "%s: null params", who);
@@ -436,6 +442,7 @@ static int fin_check_common(const aegis_fin_params* p, const char* who) {
     AEGIS_REQUIRE(p->rake_mask && p->f0 && p->voiced_flag && p->voiced_prob && p->rms, "%s: inputs missing", who);
     AEGIS_REQUIRE(p->rms_clip_stride >= p->n_frames && p->hop > 0 && p->sr > 0, "%s: bad rms stride / hop / sr", who);
     AEGIS_REQUIRE(p->f0_clean && p->semitones && p->scratch, "%s: f0_clean / semitones / scratch missing", who);
+    AEGIS_REQUIRE(static_cast<long long>((p->n_frames + aegis::NF_THREADS - 1) / aegis::NF_THREADS) * p->n_clips < (1LL << 31), "%s: too many frames for one launch", who);
     return 0;
 }
 
@@ -447,7 +454,7 @@ extern "C" int aegis_fin_prepare(const aegis_fin_params* p, void* stream) {
     const FinScratch s = carve_scratch(p->scratch, p->n_clips, p->n_frames);
     rms_max_kernel<NF_THREADS><<<p->n_clips, NF_THREADS, 0, st>>>(p->rms, p->rms_clip_stride, p->n_frames, s.rms_max);
     if (int rc = check_launch("aegis_fin_prepare(rms max)")) return rc;
-    fin_prepare_kernel<<<dim3((p->n_frames + NF_THREADS - 1) / NF_THREADS, p->n_clips), NF_THREADS, 0, st>>>(*p, s.rms_max, s.rms_db);
+    fin_prepare_kernel<<<frame_blocks(p), NF_THREADS, 0, st>>>(*p, s.rms_max, s.rms_db);
     return check_launch("aegis_fin_prepare(frames)");
 }
 
@@ -462,7 +469,7 @@ extern "C" int aegis_fin_events(const aegis_fin_params* p, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const FinScratch s = carve_scratch(p->scratch, p->n_clips, p->n_frames);
     if (p->n_frames > 0) {
-        fin_frames_kernel<<<dim3((p->n_frames + NF_THREADS - 1) / NF_THREADS, p->n_clips), NF_THREADS, 0, st>>>(*p, s.rms_db, s.frames);
+        fin_frames_kernel<<<frame_blocks(p), NF_THREADS, 0, st>>>(*p, s.rms_db, s.frames);
         if (int rc = check_launch("aegis_fin_events(frames)")) return rc;
     }
     fin_events_kernel<<<(p->n_clips + 63) / 64, 64, 0, st>>>(*p, s.frames, s.compact);

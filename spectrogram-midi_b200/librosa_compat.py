@@ -213,17 +213,51 @@ onset = types.SimpleNamespace(onset_strength=onset_strength, onset_detect=onset_
 util = types.SimpleNamespace(softmask=_softmask)
 
 
-def load(path, *, sr=22050, mono=True, offset=0.0, duration=None):
-    """Minimal ``librosa.load`` for PCM/float WAV files already at the requested rate.
+def resample(y, *, orig_sr, target_sr, res_type="polyphase", fix=True, scale=False, axis=-1, **kwargs):
+    """``librosa.resample`` for ``res_type='polyphase'`` (= ``scipy.signal.resample_poly``) on the GPU (kernel K9),
+    bit-identical to it for float32 input.  librosa's default ``soxr_hq`` lives in libsoxr, which this image does not
+    have and whose arithmetic cannot be pinned: any other ``res_type`` raises."""
+    if res_type != "polyphase":
+        raise NotImplementedError(f"res_type={res_type!r}: only 'polyphase' (scipy.signal.resample_poly) is built on the B200 path")
+    y = np.asarray(y)
+    if y.ndim != 1 or axis not in (-1, 0):
+        raise NotImplementedError("mono signals only")
+    if orig_sr == target_sr:
+        return y
+    ratio = float(target_sr) / orig_sr
+    n_samples = int(np.ceil(y.shape[-1] * ratio))
+    if n_samples < 1:
+        raise ValueError(f"Input signal length={y.shape[-1]} is too small to resample from {orig_sr}->{target_sr}")
+    out = core.resample_poly(torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).to(_device()), orig_sr, target_sr)[0]
+    y_hat = out.cpu().numpy()
+    if fix and len(y_hat) != n_samples:
+        y_hat = np.pad(y_hat[:n_samples], (0, max(0, n_samples - len(y_hat))))
+    if scale:
+        y_hat = y_hat / np.sqrt(ratio)
+    return np.asarray(y_hat, dtype=y.dtype if np.issubdtype(y.dtype, np.floating) else np.float32)
 
-    Decoding and resampling are host I/O outside the hot path: this reads RIFF
-    WAV with the standard library and refuses to resample.
+
+def load(path, *, sr=22050, mono=True, offset=0.0, duration=None, res_type="polyphase"):
+    """``librosa.load`` for RIFF WAV files (read with the standard library): PCM -> float32, channel mix-down and --
+    when the file's rate differs from ``sr`` -- rate conversion.  16-bit files that need converting go to the GPU as
+    int16 and are scaled, mixed and resampled there in one pass (K9, ``res_type='polyphase'`` only, see ``resample``).
     """
     import wave
 
     with wave.open(path, "rb") as w:
         file_sr, n_ch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
         raw = w.readframes(n)
+    start = int(round(offset * file_sr))
+    stop = None if duration is None else start + int(round(duration * file_sr))
+    need_resample = sr is not None and int(sr) != file_sr
+    if need_resample and res_type != "polyphase":
+        raise NotImplementedError(f"file is {file_sr} Hz, engine wants {sr} Hz and res_type={res_type!r}: only 'polyphase' is built")
+    if need_resample and mono and width == 2:
+        pcm = np.frombuffer(raw, dtype="<i2").reshape(-1, n_ch)[start:stop]
+        if pcm.shape[0] == 0:
+            return np.zeros(0, np.float32), int(sr)
+        dev_pcm = torch.from_numpy(np.array(pcm, dtype=np.int16).reshape(1, -1)).to(_device())   # frombuffer views are read-only
+        return core.resample_poly(dev_pcm, file_sr, int(sr), n_channels=n_ch)[0].cpu().numpy(), int(sr)
     if width == 2:
         data = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
     elif width == 4:
@@ -235,8 +269,9 @@ def load(path, *, sr=22050, mono=True, offset=0.0, duration=None):
     if n_ch > 1:
         data = data.reshape(-1, n_ch)
         data = data.mean(axis=1) if mono else data.T
-    if sr is not None and int(sr) != file_sr:
-        raise NotImplementedError(f"file is {file_sr} Hz, engine wants {sr} Hz: resample upstream (out of scope here)")
-    start = int(round(offset * file_sr))
-    stop = None if duration is None else start + int(round(duration * file_sr))
-    return np.ascontiguousarray(data[..., start:stop], dtype=np.float32), file_sr
+    data = np.ascontiguousarray(data[..., start:stop], dtype=np.float32)
+    if not need_resample:
+        return data, file_sr
+    if data.ndim != 1:
+        raise NotImplementedError("resampling multi-channel output (mono=False)")
+    return resample(data, orig_sr=file_sr, target_sr=int(sr), res_type=res_type), int(sr)

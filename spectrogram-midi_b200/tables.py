@@ -358,3 +358,18 @@ def rake_frame_limits(hop_length: int, sr: float) -> tuple:
 def savgol_coeffs(window: int = 11, polyorder: int = 3) -> np.ndarray:
     """Correlation weights used by ``scipy.signal.savgol_filter`` (financial_filters.py:46-51)."""
     return np.ascontiguousarray(scipy.signal.savgol_coeffs(window, polyorder)[::-1])
+
+
+@functools.lru_cache(maxsize=16)
+def resample_poly_design(up: int, down: int):
+    """(taps float32 incl. the `* up` gain, n_pre_pad, n_pre_remove) of scipy.signal.resample_poly(x_float32, up, down)
+    for a reduced ratio: Kaiser(5.0) windowed sinc of 2 * 10 * max(up, down) + 1 taps with cutoff 1 / max(up, down),
+    zero-padded in front so that output sample 0 sits at the filter centre (scipy/signal/_signaltools.py)."""
+    max_rate = max(up, down)
+    half_len = 10 * max_rate
+    h = scipy.signal.firwin(2 * half_len + 1, 1.0 / max_rate, window=("kaiser", 5.0)).astype(np.float32)
+    h *= up
+    n_pre_pad = down - half_len % down
+    n_pre_remove = (half_len + n_pre_pad) // down
+    return h, int(n_pre_pad), int(n_pre_remove)
+

@@ -688,6 +688,73 @@ def test_financial_engine_note_events(dev):
     np.testing.assert_array_equal(FE.events_rows(P.core.fin_events_to_list(ev, 0))[0], FE.events_rows(want)[0])
 
 
+# ---------------------------------------------------------------------------------- K9 ingest / resampler
+@pytest.mark.parametrize("orig,target", [(44100, 22050), (48000, 22050), (22050, 44100), (16000, 22050), (48000, 44100), (22050, 22050)])
+def test_resample_poly_is_bit_identical_to_scipy(dev, orig, target):
+    """aegis_resample_poly == scipy.signal.resample_poly (librosa's res_type='polyphase') bit for bit on float32 audio:
+    clip lengths that end mid-tile, a one-sample clip, a batch with a padded row stride."""
+    import scipy.signal
+
+    g = int(np.gcd(orig, target))
+    up, down = target // g, orig // g
+    rng = np.random.default_rng(orig + target)
+    for n in (1, 777, 40000):
+        y = rng.uniform(-1, 1, (3, n)).astype(np.float32)
+        y[1] = corpus.random_clip(3, 2.0, 22050)[:n] if n <= 44100 else y[1]
+        got = P.core.resample_poly(_dev(y, dev), orig, target).cpu().numpy()
+        for c in range(3):
+            ref = scipy.signal.resample_poly(y[c], up, down) if up != down else y[c]
+            assert got[c].shape == ref.shape
+            np.testing.assert_array_equal(got[c], ref, err_msg=f"{orig}->{target} n={n} clip {c}")
+    wide = torch.zeros((2, 5000 + 13), dtype=torch.float32, device=dev)
+    y = rng.uniform(-1, 1, (2, 5000)).astype(np.float32)
+    wide[:, :5000] = torch.from_numpy(y).to(dev)
+    got = P.core.resample_poly(wide[:, :5000], orig, target).cpu().numpy()
+    np.testing.assert_array_equal(got[1], scipy.signal.resample_poly(y[1], up, down) if up != down else y[1])
+    np.testing.assert_allclose(got[0], L.resample_polyphase(y[0], orig, target), rtol=0, atol=2e-6)   # and the oracle
+
+
+def test_pcm_ingest_and_load(dev, tmp_path):
+    """int16 stereo PCM -> float / 32768 -> channel mean -> 44.1 kHz to 22.05 kHz in one kernel == the same steps in
+    numpy + scipy; librosa_compat.load does it for a WAV file; other res_types are refused, equal rates pass through."""
+    import wave
+
+    import scipy.signal
+
+    lib = P.librosa_compat
+    rng = np.random.default_rng(9)
+    n = 30000
+    pcm = rng.integers(-32768, 32768, size=(n, 2), dtype=np.int16)
+    mono = (pcm.astype(np.float32) / 32768.0)
+    mono = L.to_mono(mono.T).astype(np.float32)
+    ref = scipy.signal.resample_poly(mono, 1, 2)
+    got = P.core.resample_poly(torch.from_numpy(pcm.reshape(1, -1)).to(dev), 44100, 22050, n_channels=2)[0].cpu().numpy()
+    np.testing.assert_array_equal(got, ref)
+    path = str(tmp_path / "stereo44k.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(2)
+        w.setframerate(44100)
+        w.writeframes(pcm.tobytes())
+    y, sr = lib.load(path, sr=22050)
+    assert sr == 22050 and y.dtype == np.float32
+    np.testing.assert_array_equal(y, ref)
+    y_off, _ = lib.load(path, sr=22050, offset=0.1, duration=0.25)
+    a = int(round(0.1 * 44100))
+    np.testing.assert_array_equal(y_off, scipy.signal.resample_poly(mono[a:a + int(round(0.25 * 44100))], 1, 2))
+    y_native, sr_native = lib.load(path, sr=None)
+    assert sr_native == 44100
+    np.testing.assert_array_equal(y_native, mono)
+    with pytest.raises(NotImplementedError):
+        lib.load(path, sr=22050, res_type="soxr_hq")
+    with pytest.raises(NotImplementedError):
+        lib.resample(mono, orig_sr=44100, target_sr=22050, res_type="kaiser_best")
+    np.testing.assert_array_equal(lib.resample(mono, orig_sr=44100, target_sr=22050), ref)
+    assert lib.resample(mono, orig_sr=22050, target_sr=22050) is mono
+    with pytest.raises(ValueError):
+        P.core.resample_poly(torch.zeros((1, 8), device=dev), 44100.5, 22050)
+
+
 # ---------------------------------------------------------------------------------- K6 guitar filters
 def test_guitar_filters_match_reference_golden(dev, guitar_golden):
     """aegis_guitar_filters against the outputs of the real aegis_engine_core_v2/guitar_specific.py (bit-exact)."""

@@ -225,3 +225,32 @@ def test_onset_detect_finds_the_plucks():
     starts = np.array([0.2, 1.4, 2.6 + 0.025 + 1000 / 22050]) * 22050 / 512  # E2, A2 .. pluck times
     assert all(np.min(np.abs(on - s)) <= 2 for s in starts[:2])
     assert L.onset_detect(onset_envelope=np.zeros(50, np.float32), sr=22050).size == 0
+
+
+def test_polyphase_resampler_restatement_matches_scipy():
+    """librosa.resample(res_type='polyphase') is scipy.signal.resample_poly (scipy is the pinned third-party
+    dependency here; libsoxr, librosa's default, is absent): the float64 restatement agrees with it to float32
+    rounding, its filter equals scipy.signal.firwin, and the product's design table carries scipy's centring."""
+    import scipy.signal
+
+    from spectrogram_midi_b200 import tables
+
+    rng = np.random.default_rng(0)
+    for orig, target, n in [(44100, 22050, 5000), (48000, 22050, 7000), (22050, 44100, 3001), (16000, 22050, 4000),
+                            (44100, 22050, 1), (48000, 44100, 2500), (22050, 22050, 100)]:
+        y = rng.uniform(-1, 1, n).astype(np.float32)
+        g = int(np.gcd(orig, target))
+        up, down = target // g, orig // g
+        ref = scipy.signal.resample_poly(y, up, down)
+        got = L.resample_polyphase(y, orig, target)
+        assert got.dtype == np.float32 and got.shape == ref.shape == (-(-n * up // down),)
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-6)
+        if up != down:
+            h, half_len = L.kaiser_lowpass(up, down)
+            np.testing.assert_allclose(h, scipy.signal.firwin(2 * half_len + 1, 1.0 / max(up, down), window=("kaiser", 5.0)), rtol=1e-12, atol=1e-18)
+            taps, n_pre_pad, n_pre_remove = tables.resample_poly_design(up, down)
+            assert taps.dtype == np.float32 and len(taps) == 2 * half_len + 1
+            assert (n_pre_remove * down - n_pre_pad) == half_len     # output 0 sits on the filter centre
+    stereo = rng.uniform(-1, 1, (2, 50)).astype(np.float32)
+    np.testing.assert_array_equal(L.to_mono(stereo), (stereo[0] + stereo[1]) / 2)
+
