@@ -415,6 +415,28 @@ typedef struct {
 int aegis_resample_poly(const aegis_resample_params* p, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Event serialisation (HOST code, HOST pointers): Standard MIDI File bytes and tablature positions
+ * replaces: the MIDI writer of AegisEngine.extract_events (aegis_engine.py:98-179, mido.MidiFile.save), the MIDI
+ *           writer of AegisFinancialEngine.audio_to_midi_financial (aegis_engine_financial.py:185-246) and
+ *           generate_tabs (aegis_engine_core/tabs.py:1-40).
+ * The writers return the file size in bytes (and fill `out` when `capacity` suffices), or -1 on error.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t hop;
+    int32_t midi_program;      /* v1: program change sent on both tracks (reference default 27) */
+    double sr;
+    double vibrato_rate;       /* v1: Hz, reference default 5.0 */
+    double vibrato_depth;      /* v1: fraction of the pitch-wheel range, reference default 0.3 */
+} aegis_smf_options;
+
+long long aegis_smf_write_v1(const aegis_note_event* events, int32_t n_events, const aegis_smf_options* opt,
+                             uint8_t* out, long long capacity);
+long long aegis_smf_write_v2(const aegis_fin_event* events, int32_t n_events, const aegis_smf_options* opt,
+                             uint8_t* out, long long capacity);
+/* string_out[i] in 1..6 (0: no string can play the note, the reference skips it), fret_out[i] in 0..24 */
+int aegis_tabs(const int32_t* notes, int32_t n, int32_t* string_out, int32_t* fret_out);
+
+/* ---------------------------------------------------------------------------------------------
  * Corpus synthesis on device (Karplus-Strong plucks + noise rakes, generate_test_signal.py:5-53)
  * One event per note/rake; events of a clip do not overlap.  out must be zero-filled.
  * ------------------------------------------------------------------------------------------- */

@@ -14,7 +14,7 @@ def __getattr__(name):  # torch / the CUDA library load lazily so `import` works
     import importlib
 
     if name in {"core", "batch", "engine", "librosa_compat", "vision", "worker", "financial_filters",
-                "financial_analysis", "guitar_specific", "midi_logic", "midi_logic_financial", "distributed", "build", "_native"}:
+                "financial_analysis", "guitar_specific", "midi_logic", "midi_logic_financial", "midi_writer", "tabs", "distributed", "build", "_native"}:
         return importlib.import_module(f"{__name__}.{name}")
     if name in {"AegisEngine", "AegisFinancialEngine"}:
         return getattr(importlib.import_module(f"{__name__}.engine"), name)

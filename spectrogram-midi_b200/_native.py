@@ -156,6 +156,10 @@ class ResampleParams(C.Structure):
     ]
 
 
+class SmfOptions(C.Structure):
+    _fields_ = [("hop", i32), ("midi_program", i32), ("sr", f64), ("vibrato_rate", f64), ("vibrato_depth", f64)]
+
+
 ENTRY_POINTS = {
     "aegis_stft_fused": StftParams,
     "aegis_mel_post": MelPostParams,
@@ -195,6 +199,12 @@ def load() -> C.CDLL:
     lib.aegis_note_events_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.aegis_fin_scratch_bytes.restype = C.c_longlong
     lib.aegis_fin_scratch_bytes.argtypes = [C.c_int, C.c_int]
+    for name in ("aegis_smf_write_v1", "aegis_smf_write_v2"):
+        fn = getattr(lib, name)
+        fn.restype = C.c_longlong
+        fn.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SmfOptions), C.c_void_p, C.c_longlong]
+    lib.aegis_tabs.restype = C.c_int
+    lib.aegis_tabs.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.aegis_guitar_blocks.restype = C.c_int
     lib.aegis_guitar_blocks.argtypes = [C.c_int]
     for name, struct in ENTRY_POINTS.items():

@@ -2,9 +2,9 @@
 
 ``AegisEngine`` mirrors ``aegis_engine.py:16-75,183-216`` (perception phase) and
 ``AegisFinancialEngine`` mirrors ``aegis_engine_financial.py:36-71``: same constructor arguments,
-method names, keyword names/defaults, returned dict keys and dtypes.  The logic-filter phase
-(``extract_events``: note state machine, MIDI writing) is the reference's unchanged consumer; it is
-delegated to the reference's own ``aegis_engine_core.midi_logic`` when that package is importable.
+method names, keyword names/defaults, returned dict keys and dtypes.  The logic-filter phases
+(``extract_events`` / ``audio_to_midi_financial``: note events, MIDI file) run on the GPU kernels K7 / K8 and the
+library's own MIDI writer; ``generate_tabs`` / ``export_musicxml`` mirror ``aegis_engine_core/tabs.py``.
 """
 from __future__ import annotations
 
@@ -83,16 +83,29 @@ class AegisEngine:
                                raw_data["voiced_probs"][:n], raw_data["rms"][:n], self.sr, self.hop_length,
                                kwargs.pop("confidence_threshold", 0.70), **kwargs)
 
-    # -- aegis_engine.py:77-181: unchanged consumer
+    # -- aegis_engine.py:77-181
     def extract_events(self, raw_data, output_mid, **kwargs):
-        try:
-            from aegis_engine import AegisEngine as _Ref  # the reference checkout, if it is on sys.path
-        except Exception as e:  # pragma: no cover - depends on the user's environment
-            raise RuntimeError(
-                "extract_events is the reference's unchanged logic-filter phase (aegis_engine.py:77-181); "
-                "put the reference checkout on sys.path to use it with these perception outputs") from e
-        ref = _Ref(self.sr, self.hop_length, self.n_fft)
-        return ref.extract_events(raw_data, output_mid, **kwargs)
+        """Logic-filter phase: ``get_midi_events`` (K7) and, when ``output_mid`` is a path or a file-like object, the
+        two-track MIDI file with bend / vibrato pitch-wheel curves (native writer, no mido)."""
+        from . import midi_writer
+
+        logic = {k: v for k, v in kwargs.items()
+                 if k not in ("start_time", "end_time", "turbo_mode", "rake_sensitivity", "vibrato_rate", "vibrato_depth")}
+        events = self.note_events(raw_data, **logic)
+        if output_mid:
+            midi_writer.write_midi(events, output_mid, self.sr, self.hop_length, **kwargs)
+        return events
+
+    # -- aegis_engine.py:32-36
+    def generate_tabs(self, events):
+        from .tabs import generate_tabs
+
+        return generate_tabs(events)
+
+    def export_musicxml(self, tab_data, xml_path):
+        from .tabs import export_musicxml
+
+        return export_musicxml(tab_data, xml_path)
 
 
 class AegisFinancialEngine:
@@ -141,4 +154,20 @@ class AegisFinancialEngine:
             rake_mask=raw_data["rake_mask"], f0=raw_data["f0"], voiced_flag=voiced, active_probs=raw_data["voiced_probs"],
             rms=raw_data["rms"], sr=self.sr, hop_length=self.hop_length, confidence_threshold=confidence_threshold,
             use_financial=kwargs.get("use_financial", True), **{k: v for k, v in kwargs.items() if k not in skip})
+
+    # -- aegis_engine_financial.py:73-246
+    def audio_to_midi_financial(self, input_wav, output_mid, confidence_threshold=None, rake_sensitivity=0.6,
+                                use_financial=True, **kwargs):
+        """Whole v2 pipeline: perception (K1..K6), financial logic filter (K5 + K8), two-track MIDI file.  Returns
+        ``output_mid``, or ``None`` when the audio is empty or no note is found, as the reference does."""
+        from . import midi_writer
+
+        raw = self.perception(input_wav, rake_sensitivity=rake_sensitivity, **kwargs)
+        if raw is None:
+            return None
+        events = self.note_events(raw, confidence_threshold=confidence_threshold, use_financial=use_financial, **kwargs)
+        if not events:
+            return None
+        midi_writer.write_midi_financial(events, output_mid, self.sr, self.hop_length)
+        return output_mid
 

@@ -21,7 +21,7 @@ STRUCTS = {
     "aegis_synth_params": _native.SynthParams, "aegis_guitar_params": _native.GuitarParams,
     "aegis_note_event": _native.NoteEvent, "aegis_notes_params": _native.NotesParams,
     "aegis_fin_event": _native.FinEvent, "aegis_fin_params": _native.FinParams,
-    "aegis_resample_params": _native.ResampleParams,
+    "aegis_resample_params": _native.ResampleParams, "aegis_smf_options": _native.SmfOptions,
 }
 
 

@@ -5,6 +5,7 @@ Tolerances (BASELINE.json north_star): spectrogram rtol 1e-4 (+ atol 1e-5 * fram
 RMS rtol 1e-5, f0 within 1 cent on voiced frames; integer outputs (voiced flags, Viterbi states on
 identical observations, rake mask, onset frames, MIDI note events) bit-exact.
 """
+import os
 import warnings
 
 import numpy as np
@@ -686,6 +687,45 @@ def test_financial_engine_note_events(dev):
     res = P.batch.analyze_batch(_dev(y[None], dev), sr=22050, nan_to_num=False, with_guitar=True)
     ev = P.batch.note_events_financial_batch(res, sr=22050)
     np.testing.assert_array_equal(FE.events_rows(P.core.fin_events_to_list(ev, 0))[0], FE.events_rows(want)[0])
+
+
+# ---------------------------------------------------------------------------------- whole engines, audio -> MIDI file
+def test_engines_write_midi_files(dev, tmp_path):
+    """AegisEngine.audio_to_midi -> extract_events (K7 + native writer) and AegisFinancialEngine.audio_to_midi_financial
+    (K1..K6, K5 + K8, native writer) on one clip: the files decode to the messages the reference would hand to mido."""
+    import io
+    import warnings
+
+    from oracle import financial_events as FE
+    from oracle import midi_messages as MM
+
+    sr = 22050
+    y = corpus.random_clip(33, 12.0, sr)
+    eng = P.engine.AegisEngine(sr)
+    raw = eng.audio_to_midi(y, None)
+    buf = io.BytesIO()
+    events = eng.extract_events(raw, buf, confidence_threshold=0.7, vibrato_rate=6.0, midi_program=29)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = R.get_midi_events(raw["rake_mask"], raw["f0"], raw["voiced_flag"], raw["voiced_probs"], raw["rms"], sr, 512, 0.7)
+    assert R.events_key(events) == R.events_key(want) and len(events) >= 3
+    fmt, tpb, tracks = MM.read_smf(buf.getvalue())
+    assert (fmt, tpb) == (1, 480) and tracks == MM.v1_tracks(events, sr, 512, midi_program=29, vibrato_rate=6.0)
+    assert eng.extract_events(raw, None) is not None          # no file requested
+    tab = eng.generate_tabs(events)
+    assert len(tab) == sum(40 <= e["note"] <= 88 for e in events)
+    assert os.path.getsize(eng.export_musicxml(tab, str(tmp_path / "clip.xml"))) > 400
+
+    fin = P.engine.AegisFinancialEngine(sr)
+    out = str(tmp_path / "fin.mid")
+    assert fin.audio_to_midi_financial(y, out) == out
+    rawf = fin.perception(y)
+    voiced = rawf["voiced_flag"] & ~rawf["mute_mask"]
+    wantf = FE.get_midi_events_financial(rawf["rake_mask"], rawf["f0"], voiced, rawf["voiced_probs"], rawf["rms"], sr, 512)
+    _, _, tracks = MM.read_smf(open(out, "rb").read())
+    assert tracks == MM.v2_tracks(wantf, sr, 512)
+    assert fin.audio_to_midi_financial(np.zeros(0, np.float32), out) is None
+    assert fin.audio_to_midi_financial(np.zeros(30000, np.float32), out) is None      # silence: no notes
 
 
 # ---------------------------------------------------------------------------------- K9 ingest / resampler
