@@ -729,7 +729,7 @@ def test_engines_write_midi_files(dev, tmp_path):
 
 
 # ---------------------------------------------------------------------------------- K9 ingest / resampler
-@pytest.mark.parametrize("orig,target", [(44100, 22050), (48000, 22050), (22050, 44100), (16000, 22050), (48000, 44100), (22050, 22050)])
+@pytest.mark.parametrize("orig,target", [(44100, 22050), (88200, 22050), (48000, 22050), (22050, 44100), (16000, 22050), (48000, 44100), (22050, 22050)])
 def test_resample_poly_is_bit_identical_to_scipy(dev, orig, target):
     """aegis_resample_poly == scipy.signal.resample_poly (librosa's res_type='polyphase') bit for bit on float32 audio:
     clip lengths that end mid-tile, a one-sample clip, a batch with a padded row stride."""

@@ -10,7 +10,7 @@ import spectrogram_midi_b200 as P
 n_clips = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 secs = float(sys.argv[2]) if len(sys.argv) > 2 else 30.0
 dev = torch.device("cuda:0")
-for orig, target, dtype, ch in [(44100, 22050, torch.float32, 1), (44100, 22050, torch.int16, 1), (44100, 22050, torch.int16, 2),
+for orig, target, dtype, ch in [(44100, 22050, torch.float32, 1), (88200, 22050, torch.int16, 1), (44100, 22050, torch.int16, 1), (44100, 22050, torch.int16, 2),
                                 (48000, 22050, torch.float32, 1), (22050, 22050, torch.int16, 1)]:
     n_in = int(secs * orig)
     if dtype == torch.int16:
