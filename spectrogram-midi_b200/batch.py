@@ -146,15 +146,33 @@ class HostPipeline:
     stream while chunk i runs through the kernels (double-buffered device input), and the small
     per-frame results (RMS, onset envelope, onset flags) are copied back as each chunk finishes.
     |X| is produced in HBM per chunk (it is the input of the onset path) and not copied to the host.
+
+    With ``pcm_rate`` the host batch is 16-bit PCM as it sits in a WAV file (int16 ``[n_clips, n_source_frames *
+    pcm_channels]``, channels interleaved, at ``pcm_rate`` Hz): half the PCIe bytes of float32, and the ingest kernel
+    K9 does what ``librosa.load`` does after the file read (scale, mix down, resample to ``sr``) on the device.
+    ``n_samples`` stays the clip length at the engine rate.
     """
 
-    def __init__(self, n_clips: int, n_samples: int, *, sr: float, hop_length: int = 512, device=None, chunk_clips: int = 128):
+    def __init__(self, n_clips: int, n_samples: int, *, sr: float, hop_length: int = 512, device=None, chunk_clips: int = 128,
+                 pcm_rate: Optional[int] = None, pcm_channels: int = 1):
         self.sr, self.hop = sr, hop_length
         self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.n_clips, self.n_samples = n_clips, n_samples
         self.chunk = min(chunk_clips, n_clips)
         self.T = core.frame_count(n_samples, hop_length)
-        self.inbuf = [torch.empty((self.chunk, n_samples), dtype=torch.float32, device=self.dev) for _ in range(2)]
+        self.pcm_rate, self.pcm_channels = pcm_rate, pcm_channels
+        if pcm_rate is None:
+            self.in_shape, in_dtype = (n_clips, n_samples), torch.float32
+        else:
+            g = int(np.gcd(int(pcm_rate), int(sr)))
+            up, down = int(sr) // g, int(pcm_rate) // g
+            n_src = -(-n_samples * down // up)                 # fewest source frames whose resampled length reaches n_samples
+            while -(-n_src * up // down) > n_samples:
+                n_src -= 1
+            if -(-n_src * up // down) != n_samples:
+                raise ValueError(f"no source length at {pcm_rate} Hz resamples to exactly {n_samples} samples at {sr} Hz")
+            self.in_shape, in_dtype = (n_clips, n_src * pcm_channels), torch.int16
+        self.inbuf = [torch.empty((self.chunk, self.in_shape[1]), dtype=in_dtype, device=self.dev) for _ in range(2)]
         self.mag = core.alloc_frames((self.chunk, core.N_BINS), self.T, self.dev)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.in_ready = [torch.cuda.Event() for _ in range(2)]
@@ -162,12 +180,12 @@ class HostPipeline:
         self.rms = torch.empty((n_clips, self.T), dtype=torch.float32, pin_memory=True)
         self.env = torch.empty((n_clips, self.T), dtype=torch.float32, pin_memory=True)
         self.peaks = torch.empty((n_clips, self.T), dtype=torch.uint8, pin_memory=True)
-        self.h2d_bytes = n_clips * n_samples * 4
+        self.h2d_bytes = n_clips * self.in_shape[1] * (4 if pcm_rate is None else 2)
         self.d2h_bytes = n_clips * self.T * (4 + 4 + 1)
 
     def run(self, y_host: torch.Tensor) -> dict:
-        if y_host.is_cuda or y_host.shape != (self.n_clips, self.n_samples):
-            raise ValueError("expected a host tensor [n_clips, n_samples]")
+        if y_host.is_cuda or tuple(y_host.shape) != self.in_shape or y_host.dtype != self.inbuf[0].dtype:
+            raise ValueError(f"expected a host {self.inbuf[0].dtype} tensor {self.in_shape}")
         main = torch.cuda.current_stream(self.dev)
         starts = list(range(0, self.n_clips, self.chunk))
         for b in range(2):
@@ -181,6 +199,8 @@ class HostPipeline:
                 self.in_ready[b].record(self.copy_stream)
             main.wait_event(self.in_ready[b])
             yb = self.inbuf[b][:n]
+            if self.pcm_rate is not None:
+                yb = core.resample_poly(yb, self.pcm_rate, int(self.sr), n_channels=self.pcm_channels)
             feat = core.stft_features(yb, sr=self.sr, hop_length=self.hop, want_mag=True, want_mel=True, want_rms=True,
                                       mag_out=self.mag[:n])
             post = core.mel_post(feat["mel"], feat["mel_max"], sr=self.sr, hop_length=self.hop, want_sdb=False,

@@ -795,6 +795,36 @@ def test_pcm_ingest_and_load(dev, tmp_path):
         P.core.resample_poly(torch.zeros((1, 8), device=dev), 44100.5, 22050)
 
 
+def test_host_pipeline_pcm_ingest(dev):
+    """HostPipeline fed with int16 PCM (same rate, and stereo 44.1 kHz) == HostPipeline fed with the float32 audio
+    that numpy / scipy make of that PCM: the ingest kernel sits in front of an unchanged path."""
+    import scipy.signal
+
+    sr, n_clips, n = 22050, 5, 22050 * 2
+    rng = np.random.default_rng(12)
+    clips = corpus.clip_batch(n_clips, 2.0, sr, first_seed=70)
+    pcm = np.round(clips * 32767.0).astype(np.int16)
+    ref_pipe = P.batch.HostPipeline(n_clips, n, sr=sr, device=dev, chunk_clips=2)
+    want = {k: v.clone() for k, v in ref_pipe.run(torch.from_numpy(pcm.astype(np.float32) / 32768.0).pin_memory()).items()}
+    pipe = P.batch.HostPipeline(n_clips, n, sr=sr, device=dev, chunk_clips=2, pcm_rate=sr)
+    got = pipe.run(torch.from_numpy(pcm).pin_memory())
+    assert pipe.h2d_bytes * 2 == ref_pipe.h2d_bytes
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    # stereo 44.1 kHz source
+    n_src = n * 2
+    stereo = rng.integers(-20000, 20000, size=(n_clips, n_src, 2), dtype=np.int16)
+    mono = ((stereo[..., 0].astype(np.float32) / 32768.0) + (stereo[..., 1].astype(np.float32) / 32768.0)) / np.float32(2)
+    y = np.stack([scipy.signal.resample_poly(m, 1, 2) for m in mono])
+    want = {k: v.clone() for k, v in ref_pipe.run(torch.from_numpy(y).pin_memory()).items()}
+    pipe2 = P.batch.HostPipeline(n_clips, n, sr=sr, device=dev, chunk_clips=2, pcm_rate=44100, pcm_channels=2)
+    got = pipe2.run(torch.from_numpy(stereo.reshape(n_clips, -1)).pin_memory())
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    with pytest.raises(ValueError):
+        pipe2.run(torch.from_numpy(pcm).pin_memory())
+
+
 # ---------------------------------------------------------------------------------- K6 guitar filters
 def test_guitar_filters_match_reference_golden(dev, guitar_golden):
     """aegis_guitar_filters against the outputs of the real aegis_engine_core_v2/guitar_specific.py (bit-exact)."""
