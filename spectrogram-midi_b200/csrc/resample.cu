@@ -102,16 +102,19 @@ decimate_kernel(const aegis_resample_params p, int span, int tiles_per_clip) {
     for (int j = tid; j < J; j += RS_THREADS) taps[j] = p.taps[j];
     const unsigned char* in_base = static_cast<const unsigned char*>(p.x) +
                                    static_cast<long long>(clip) * p.in_clip_stride * (p.in_format == 1 ? 2 : 4);
+    // the tile is stored in groups of 16 floats padded to 20: thread windows start 80 B apart, so the float4 loads of
+    // a quarter warp fall in eight different 16-byte bank groups
     for (int s = tid; s < span; s += RS_THREADS) {
         const long long k = k_lo + s;
-        xs[s] = (k >= 0 && k < p.n_in) ? load_mono(p, in_base, k) : 0.f;
+        xs[s + (s >> 4) * 4] = (k >= 0 && k < p.n_in) ? load_mono(p, in_base, k) : 0.f;
     }
     __syncthreads();
+    static_assert((R * DOWN) % 16 == 0, "a thread's window must start on a group of 16");
     float xw[W4 * 4];
-    const float4* src = reinterpret_cast<const float4*>(xs + tid * (R * DOWN));   // R * DOWN is a multiple of 4
+    const float* src = xs + tid * (R * DOWN / 16) * 20;
 #pragma unroll
     for (int v = 0; v < W4; ++v) {
-        const float4 q = src[v];
+        const float4 q = *reinterpret_cast<const float4*>(src + (v / 4) * 20 + (v % 4) * 4);
         xw[4 * v] = q.x; xw[4 * v + 1] = q.y; xw[4 * v + 2] = q.z; xw[4 * v + 3] = q.w;
     }
     float acc[R];
@@ -124,8 +127,10 @@ decimate_kernel(const aegis_resample_params p, int span, int tiles_per_clip) {
         for (int r = 0; r < R; ++r) acc[r] = __fadd_rn(acc[r], __fmul_rn(xw[(J - 1 - j) + r * DOWN], h));
     }
     __syncthreads();                                           // every window is in registers: reuse xs for the outputs
+    static_assert(R % 4 == 0, "outputs are staged as float4");
 #pragma unroll
-    for (int r = 0; r < R; ++r) xs[tid * R + r] = acc[r];
+    for (int r = 0; r < R; r += 4)
+        *reinterpret_cast<float4*>(xs + tid * R + r) = make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
     __syncthreads();
     float* out = p.out + static_cast<long long>(clip) * p.out_clip_stride;
     for (int i = tid; i < TILE; i += RS_THREADS) {
@@ -134,28 +139,12 @@ decimate_kernel(const aegis_resample_params p, int span, int tiles_per_clip) {
     }
 }
 
-// equal rates: conversion and mix-down only
-__global__ void __launch_bounds__(RS_THREADS)
-convert_kernel(const aegis_resample_params p, int blocks_per_clip) {
-    const int clip = blockIdx.x / blocks_per_clip;
-    const unsigned char* in_base = static_cast<const unsigned char*>(p.x) +
-                                   static_cast<long long>(clip) * p.in_clip_stride * (p.in_format == 1 ? 2 : 4);
-    float* out = p.out + static_cast<long long>(clip) * p.out_clip_stride;
-    const float gain = p.taps[0];
-    const long long m0 = static_cast<long long>(blockIdx.x - clip * blocks_per_clip) * RS_TILE + threadIdx.x;
-#pragma unroll
-    for (int r = 0; r < RS_PER_THREAD; ++r) {
-        const long long m = m0 + r * RS_THREADS;
-        if (m < p.n_out) out[m] = __fadd_rn(0.f, __fmul_rn(m < p.n_in ? load_mono(p, in_base, m) : 0.f, gain));
-    }
-}
-
 template <int DOWN, int R>
 int launch_decimate(const aegis_resample_params* p, cudaStream_t st) {
     constexpr int J = 20 * DOWN + 1;
     constexpr int TILE = RS_THREADS * R;
-    const int span = ((TILE - 1) * DOWN + J + 2 + 3 + 3) & ~3;   // + the float4 overshoot of the last window
-    const size_t smem = (((J + 3) & ~3) + span) * sizeof(float);
+    const int span = ((TILE - 1) * DOWN + J + 2 + 3 + 15) & ~15;   // + the float4 overshoot of the last window
+    const size_t smem = (((J + 3) & ~3) + span / 16 * 20) * sizeof(float);   // groups of 16 padded to 20
     cudaError_t e = cudaFuncSetAttribute(decimate_kernel<DOWN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
         set_error("aegis_resample_poly: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
