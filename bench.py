@@ -76,6 +76,27 @@ def cpu_throughput(clips, cores, repeats=1):
     return repeats * len(clips) * CLIP_SECONDS / dt, dt
 
 
+def serial_throughput(clips):
+    """audio-s/s of the CPU oracle on ONE core, in this process (SURVEY.md §8d asks for serial next to the pool)."""
+    from threadpoolctl import threadpool_limits
+
+    with threadpool_limits(limits=1):   # BLAS is already loaded in this process: the environment variables come too late
+        _cpu_spectral_one(clips[0])     # warm caches / FFT plans
+        t0 = time.perf_counter()
+        for c in clips:
+            _cpu_spectral_one(c)
+        return len(clips) * CLIP_SECONDS / (time.perf_counter() - t0)
+
+
+def library_versions():
+    import platform
+
+    import numpy
+    import scipy
+
+    return {"python": platform.python_version(), "numpy": numpy.__version__, "scipy": scipy.__version__, "librosa": None}
+
+
 def pooled_rate(clips, cores):
     """clips per second of the CPU oracle with the full pool busy (a single-process probe is several times faster per
     clip than a worker of a saturated pool, and would oversize the bounded sample)."""
@@ -329,7 +350,9 @@ def run_gpu(args):
         v, dt = cpu_throughput(sample, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {n} clips of the batch ({n * CLIP_SECONDS:.0f} audio-s), Pool({cores}) by clip, {dt:.1f} s wall; "
-                         "numpy/scipy oracle port of the librosa path (librosa not installable here)"}
+                         "numpy/scipy oracle port of the librosa path (librosa not installable here)",
+               "serial_value": serial_throughput(sample[:6]), "serial_sample": "6 clips on one core, same process",
+               "versions": library_versions()}
 
     if rank == 0:
         line = {
