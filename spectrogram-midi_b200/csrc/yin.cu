@@ -66,15 +66,6 @@ __device__ __forceinline__ void fft_finish_inplace(int lt, cf* v, const FftTwidd
     __syncthreads();
 }
 
-// forward transform of x[n] = in[n] (natural order, complex); result in out (may alias in)
-__device__ __forceinline__ void fft_from_natural(int lt, const cf* in, const FftTwiddles& tw, cf* buf, cf* out) {
-    cf v[16];
-#pragma unroll
-    for (int a = 0; a < 16; ++a) v[a] = in[lt + 128 * a];
-    fft2048_pass1(lt, v, tw, buf);
-    fft_finish_inplace(lt, v, tw, buf, out);
-}
-
 __global__ void __launch_bounds__(YIN_THREADS, 4)
 yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n_pairs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -123,21 +114,30 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
             fzero[fr] = !(en > 0.f);  // digital silence: acf must be exactly 0, not the partner's noise
         }
 
-        // ---- spectra: Z = FFT(frame + i*rev), rev[n] = frame[1024-n] (n < 1024), 0 otherwise
+        // ---- three transforms through ONE copy of the FFT code (the kernel is far larger than the instruction cache;
+        // a second inlined copy for the inverse transform cost more in instruction fetch than the branches here):
+        // it = 0, 1: spectra Z = FFT(frame + i*rev), rev[n] = frame[1024-n] (n < 1024), 0 otherwise, then the products;
+        // it = 2:    one transform inverts both products: q[n] = conj(FFT(conj Q)[n]) / N = acf1[n] + i*acf2[n]
 #pragma unroll 1
-        for (int fr = 0; fr < 2; ++fr) {
-            const float* f = s.samples + fr * hop;
+        for (int it = 0; it < 3; ++it) {
             {
-                const float sc = ldexpf(1.0f, -fexp[fr]);
                 cf v[16];
+                if (it < 2) {
+                    const float* f = s.samples + it * hop;
+                    const float sc = ldexpf(1.0f, -fexp[it]);
 #pragma unroll
-                for (int a = 0; a < 16; ++a) {
-                    const int n = lt + 128 * a;
-                    v[a] = cf{f[n] * sc, (a < 8) ? f[FFT_N / 2 - n] * sc : 0.f};
+                    for (int a = 0; a < 16; ++a) {
+                        const int n = lt + 128 * a;
+                        v[a] = cf{f[n] * sc, (a < 8) ? f[FFT_N / 2 - n] * sc : 0.f};
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < 16; ++a) v[a] = s.Z[lt + 128 * a];
                 }
                 fft2048_pass1(lt, v, tw, s.buf);
                 fft_finish_inplace(lt, v, tw, s.buf, s.Z);
             }
+            if (it == 2) break;
             // P = (2A)(2B) with 2A = Z[k] + conj Z[N-k], 2B = (Z[k] - conj Z[N-k]) / i
 #pragma unroll
             for (int m = 0; m < 9; ++m) {
@@ -148,7 +148,7 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
                     const cf A2 = cf{zk.x + zn.x, zk.y - zn.y};
                     const cf B2 = cf{zk.y + zn.y, zn.x - zk.x};
                     const cf P = cmul(A2, B2);
-                    if (fr == 0) {
+                    if (it == 0) {
                         s.P1[k] = P;
                     } else {  // conj(Q), Q = P1 + i*P2 extended Hermitian-wise; in place over Z
                         const cf p1 = s.P1[k];
@@ -159,8 +159,6 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
             }
             __syncthreads();
         }
-        // ---- one transform inverts both: q[n] = conj(FFT(conj Q)[n]) / N = acf1[n] + i*acf2[n]
-        fft_from_natural(lt, s.Z, tw, s.buf, s.Z);
 
         // ---- phase E: energies, difference function, cumulative mean, CMND (64 threads / frame)
         {
