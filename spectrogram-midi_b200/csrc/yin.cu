@@ -297,34 +297,47 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
                         if (lane == 0) tp[i] = c;
                     }
                     __syncwarp();
-                    // 5. emit in ascending-bin order (= descending lag); equal bins: the larger lag wins
+                    // 5. every lane turns its troughs' lags into pitch bins (parabolic refinement, log2: the expensive
+                    //    part, in parallel; tk[] is overwritten with the bin, 0xffff = not a candidate) ...
+                    if (lane == 0) tp[best_i] += p.no_trough_prob * __ldg(p.beta_cumsum + tq[best_i]);
+                    __syncwarp();
+                    {
+                        const double scale = 12.0 * p.bins_per_semitone;
+                        for (int i = lane; i < nt; i += 32) {
+                            unsigned short bin16 = 0xffffu;
+                            if (tp[i] != 0.0) {
+                                const int k = tk[i];
+                                double shift = 0.0;
+                                if (k > 0 && k < L - 1) {
+                                    const double a = yv[k + 1] + yv[k - 1] - 2.0 * yv[k];
+                                    const double b = (yv[k + 1] - yv[k - 1]) / 2.0;
+                                    if (!(fabs(b) >= fabs(a))) shift = -b / a;
+                                }
+                                const double period = static_cast<double>(minp + k) + shift;
+                                const double f0 = p.sr / period;
+                                double bf = rint(scale * log2(f0 / p.fmin));
+                                bf = fmin(fmax(bf, 0.0), static_cast<double>(p.n_pitch_bins));
+                                const int bin = static_cast<int>(bf);
+                                if (bin < p.n_pitch_bins) bin16 = static_cast<unsigned short>(bin);   // else: unvoiced rows, overwritten
+                            }
+                            tk[i] = bin16;
+                        }
+                    }
+                    __syncwarp();
+                    //    ... and lane 0 emits them in ascending-bin order (= descending lag); equal bins: the larger lag wins
                     if (lane == 0) {
-                        tp[best_i] += p.no_trough_prob * __ldg(p.beta_cumsum + tq[best_i]);
                         unsigned short* ob = p.cand_bin + fidx * p.max_cand;
                         double* op = p.cand_prob + fidx * p.max_cand;
-                        const double scale = 12.0 * p.bins_per_semitone;
                         int last_bin = -1;
                         bool over = false;
                         for (int i = nt - 1; i >= 0; --i) {
-                            const double pr = tp[i];
-                            if (pr == 0.0) continue;
-                            const int k = tk[i];
-                            double shift = 0.0;
-                            if (k > 0 && k < L - 1) {
-                                const double a = yv[k + 1] + yv[k - 1] - 2.0 * yv[k];
-                                const double b = (yv[k + 1] - yv[k - 1]) / 2.0;
-                                if (!(fabs(b) >= fabs(a))) shift = -b / a;
-                            }
-                            const double period = static_cast<double>(minp + k) + shift;
-                            const double f0 = p.sr / period;
-                            double bf = rint(scale * log2(f0 / p.fmin));
-                            bf = fmin(fmax(bf, 0.0), static_cast<double>(p.n_pitch_bins));
-                            const int bin = static_cast<int>(bf);
-                            if (bin >= p.n_pitch_bins) continue;  // lands in the unvoiced rows: overwritten
+                            const int bin = tk[i];
+                            if (bin == 0xffff) continue;
                             if (bin == last_bin) continue;        // overwritten by the later (larger-lag) write
                             last_bin = bin;
                             if (count < p.max_cand) {
                                 ob[count] = static_cast<unsigned short>(bin);
+                                const double pr = tp[i];
                                 op[count] = pr;
                                 vsum += pr;
                                 ++count;
