@@ -139,6 +139,22 @@ decimate_kernel(const aegis_resample_params p, int span, int tiles_per_clip) {
     }
 }
 
+// equal rates: conversion and mix-down only
+__global__ void __launch_bounds__(RS_THREADS)
+convert_kernel(const aegis_resample_params p, int blocks_per_clip) {
+    const int clip = blockIdx.x / blocks_per_clip;
+    const unsigned char* in_base = static_cast<const unsigned char*>(p.x) +
+                                   static_cast<long long>(clip) * p.in_clip_stride * (p.in_format == 1 ? 2 : 4);
+    float* out = p.out + static_cast<long long>(clip) * p.out_clip_stride;
+    const float gain = p.taps[0];
+    const long long m0 = static_cast<long long>(blockIdx.x - clip * blocks_per_clip) * RS_TILE + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < RS_PER_THREAD; ++r) {
+        const long long m = m0 + r * RS_THREADS;
+        if (m < p.n_out) out[m] = __fadd_rn(0.f, __fmul_rn(m < p.n_in ? load_mono(p, in_base, m) : 0.f, gain));
+    }
+}
+
 template <int DOWN, int R>
 int launch_decimate(const aegis_resample_params* p, cudaStream_t st) {
     constexpr int J = 20 * DOWN + 1;
