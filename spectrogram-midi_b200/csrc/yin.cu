@@ -86,6 +86,7 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
         const float* __restrict__ yc = p.y + static_cast<long long>(clip) * p.clip_stride;
         const long long g0 = static_cast<long long>(t0) * hop - p.pad;
         __syncthreads();
+        #pragma unroll 4
         for (int i = lt; i < FFT_N + hop; i += YIN_THREADS) {
             const long long gi = g0 + i;
             s.samples[i] = (gi >= 0 && gi < N) ? __ldg(yc + gi) : 0.f;
@@ -165,24 +166,28 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
             const int fr = lt >> 6, u = lt & 63;
             const float* f = s.samples + fr * hop;
             double acc = 0.0;
+            #pragma unroll 2
             for (int j = 1 + u; j <= FFT_N / 2; j += 64) acc += static_cast<double>(f[j] * f[j]);
             acc = warp_sum_d(acc);
             if (lane == 0) se.e0[fr][warp & 1] = acc;
             const int chunk = (maxp + 63) / 64;
             const int lo = 1 + u * chunk, hi = min(lo + chunk, maxp + 1);
             double run = 0.0;
+            #pragma unroll 1
             for (int tau = lo; tau < hi; ++tau)
                 run += static_cast<double>(f[FFT_N / 2 + tau] * f[FFT_N / 2 + tau]) - static_cast<double>(f[tau] * f[tau]);
             se.tot[fr][u] = run;
             __syncthreads();
             const double e0 = se.e0[fr][0] + se.e0[fr][1];
             double base = e0;
+            #pragma unroll 2
             for (int v = 0; v < u; ++v) base += se.tot[fr][v];
             float e0f = static_cast<float>(e0);
             if (fabsf(e0f) < 1e-6f) e0f = 0.f;
             const float acf_scale = ldexpf(1.0f / (4.0f * FFT_N), 2 * fexp[fr]);
             run = 0.0;
             double dsum = 0.0;
+            #pragma unroll 1
             for (int tau = lo; tau < hi; ++tau) {
                 run += static_cast<double>(f[FFT_N / 2 + tau] * f[FFT_N / 2 + tau]) - static_cast<double>(f[tau] * f[tau]);
                 float e = static_cast<float>(base + run);
@@ -198,8 +203,10 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
             se.tot[fr][u] = dsum;
             __syncthreads();
             base = 0.0;
+            #pragma unroll 2
             for (int v = 0; v < u; ++v) base += se.tot[fr][v];
             run = 0.0;
+            #pragma unroll 1
             for (int tau = lo; tau < hi; ++tau) {
                 run += static_cast<double>(se.d[fr][tau]);
                 if (tau >= minp) {
