@@ -576,6 +576,23 @@ def test_note_events_batch_from_states(dev):
         assert _event_rows(got)[0].tolist() == _event_rows(ref)[0].tolist()
 
 
+def test_onset_fast_path_equals_general_kernel(dev):
+    """The onset-only kernel (four columns per thread, 16-byte loads) and the general mel_post kernel (one column per
+    thread, used whenever the dB image or the rake mask is wanted) give bit-identical envelopes, extrema and peaks,
+    for frame counts that end anywhere inside a group of four columns."""
+    for seconds in (1.0, 1.03, 1.05, 1.07, 7.3):
+        clips = corpus.clip_batch(3, seconds, 22050, first_seed=int(seconds * 100))
+        feat = P.core.stft_features(_dev(clips, dev), sr=22050, want_mag=False, want_mel=True, want_rms=False)
+        fast = P.core.mel_post(feat["mel"], feat["mel_max"], sr=22050, want_sdb=False, want_rake=False, want_onset=True)
+        full = P.core.mel_post(feat["mel"], feat["mel_max"], sr=22050, want_sdb=True, want_rake=True, want_onset=True)
+        assert torch.equal(fast["onset_env"], full["onset_env"]), seconds
+        assert torch.equal(fast["env_minmax"], full["env_minmax"])
+        a = P.core.onset_peaks(fast["onset_env"], fast["env_minmax"], sr=22050)
+        b = P.core.onset_peaks(full["onset_env"], full["env_minmax"], sr=22050)
+        assert torch.equal(a["peaks"], b["peaks"]) and torch.equal(a["n_peaks"], b["n_peaks"])
+        assert int(a["n_peaks"].sum()) == int(a["peaks"].sum())
+
+
 # ---------------------------------------------------------------------------------- K8 v2 logic filter
 def _fin_frames(seed, n, steady_grid=False):
     """Frame series of a made-up performance (see tests/golden/make_golden_financial_events.py): notes with jitter,
