@@ -254,3 +254,34 @@ def test_polyphase_resampler_restatement_matches_scipy():
     stereo = rng.uniform(-1, 1, (2, 50)).astype(np.float32)
     np.testing.assert_array_equal(L.to_mono(stereo), (stereo[0] + stereo[1]) / 2)
 
+
+def test_resampler_kernel_arithmetic_model_equals_scipy_bitwise():
+    """The arithmetic K9 performs -- for output m the taps h[phase + j * up] against x[q - j], q = c // up,
+    phase = c % up, c = (m + n_pre_remove) * down - n_pre_pad, summed over ascending input index with a separately
+    rounded float32 product and sum -- restated in numpy float32, is bit-identical to scipy.signal.resample_poly.
+    (The GPU test checks the kernel against scipy directly; this pins the index algebra and the design table on CPU.)"""
+    import scipy.signal
+
+    from spectrogram_midi_b200 import tables
+
+    f32 = np.float32
+    rng = np.random.default_rng(5)
+    for orig, target, n in [(44100, 22050, 400), (48000, 22050, 500), (22050, 44100, 150), (16000, 22050, 260), (88200, 22050, 700)]:
+        y = rng.uniform(-1, 1, n).astype(f32)
+        g = int(np.gcd(orig, target))
+        up, down = target // g, orig // g
+        h, n_pre_pad, n_pre_remove = tables.resample_poly_design(up, down)
+        taps_per_phase = -(-len(h) // up)
+        n_out = -(-n * up // down)
+        out = np.zeros(n_out, f32)
+        for m in range(n_out):
+            c = (m + n_pre_remove) * down - n_pre_pad
+            q, phase = divmod(c, up)
+            acc = f32(0)
+            for j in range(taps_per_phase - 1, -1, -1):
+                i, k = phase + j * up, q - j
+                if i < len(h) and 0 <= k < n:
+                    acc = f32(acc + f32(y[k] * h[i]))
+            out[m] = acc
+        np.testing.assert_array_equal(out, scipy.signal.resample_poly(y, up, down), err_msg=f"{orig}->{target}")
+
