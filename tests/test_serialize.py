@@ -125,3 +125,31 @@ def test_running_status_and_varlen_layout():
     raw = P.midi_writer.smf_bytes(bend, 1024, 512)
     # fifteen consecutive wheel messages share one status byte; the closing one follows the note-off and needs its own
     assert raw[14:].count(b"\xe0") == 2
+
+
+def test_midi_files_of_the_golden_reference_events(golden, fin_golden):
+    """The note events the REAL midi_logic.py / midi_logic_financial.py produced (committed golden vectors) written by
+    the native writers: the files decode to the message lists of the restated export code."""
+    from oracle import financial_events as FE
+
+    n_v1 = n_v2 = 0
+    for name in ("track22050", "track44100", "clip7"):
+        k = f"midi/{name}"
+        sr = int(golden[f"{k}/sr"][0])
+        events = [{"note": int(r[0]), "start": int(r[1]), "end": int(r[2]), "velocity": int(r[3]), "track": "main" if r[4] else "safe",
+                   "technique": TECH[int(r[5])], "confidence": float(f[0]), "rms_energy": float(f[1]), "slope": float(f[2])}
+                  for r, f in zip(golden[f"{k}/events"], golden[f"{k}/event_float"])]
+        _, tpb, tracks = MM.read_smf(P.midi_writer.smf_bytes(events, sr, 512))
+        assert tpb == 480 and tracks == MM.v1_tracks(events, sr, 512)
+        n_v1 += len(events)
+    for name in [str(v) for v in fin_golden["fin/names"]]:
+        k = f"fin/{name}"
+        sr = int(fin_golden[f"{k}/args"][0])
+        events = [{"note": int(r[0]), "start": int(r[1]), "end": int(r[2]), "velocity": int(r[3]), "track": "main" if r[4] else "safe",
+                   "technique": FE.ARTIC[int(r[5])], "financial_slide": FE.SLIDE[int(r[6])], "confidence": float(c)}
+                  for r, c in zip(fin_golden[f"{k}/events"], fin_golden[f"{k}/confidence"])]
+        _, _, tracks = MM.read_smf(P.midi_writer.smf_bytes_financial(events, sr, 512))
+        assert tracks == MM.v2_tracks(events, sr, 512), name
+        n_v2 += len(events)
+    assert n_v1 >= 10 and n_v2 > 200
+
