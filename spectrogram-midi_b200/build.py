@@ -66,4 +66,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    try:
+        print("BUILD OK", build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    except Exception as e:   # the last line of the output always says how it went, whatever the caller pipes it through
+        print(e, file=sys.stderr)
+        print("BUILD FAILED")
+        sys.exit(1)
