@@ -618,6 +618,8 @@ def resample_poly(x: torch.Tensor, orig_sr: int, target_sr: int, *, n_channels: 
     up, down = int(target_sr) // g, int(orig_sr) // g
     n_out = -(-n_in * up // down)
     out = torch.empty((n_clips, n_out), dtype=torch.float32, device=x.device)
+    if n_clips == 0 or n_out == 0:
+        return out
     if up == down == 1:     # identity filter: one tap of weight 1 at the output sample
         taps, n_pre_pad, n_pre_remove = np.ones(1, np.float32), 0, 0
     else:
