@@ -543,7 +543,8 @@ def note_events_financial(rake_mask: torch.Tensor, f0: torch.Tensor, voiced_flag
     semitones = torch.empty_like(f0)
     scratch = torch.empty((int(nat.load().aegis_fin_scratch_bytes(n_clips, T)),), dtype=torch.uint8, device=dev)
     P.f0_clean, P.semitones, P.scratch = f0_clean.data_ptr(), semitones.data_ptr(), scratch.data_ptr()
-    nat.call("aegis_fin_prepare", P, _stream())
+    if T > 0 and n_clips > 0:
+        nat.call("aegis_fin_prepare", P, _stream())
     events = torch.zeros((n_clips, max_events, FIN_EVENT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     n_events = torch.zeros((n_clips,), dtype=torch.int32, device=dev)
     threshold = torch.empty((n_clips,), dtype=torch.float64, device=dev)
