@@ -435,6 +435,10 @@ long long aegis_smf_write_v2(const aegis_fin_event* events, int32_t n_events, co
                              uint8_t* out, long long capacity);
 /* string_out[i] in 1..6 (0: no string can play the note, the reference skips it), fret_out[i] in 0..24 */
 int aegis_tabs(const int32_t* notes, int32_t n, int32_t* string_out, int32_t* fret_out);
+/* export_musicxml (aegis_engine_core/tabs.py:42-112) as bytes: techniques 0 none, 1 vibrato, 2 bend, 3 slide (may be
+ * NULL).  Returns the document size (fills `out` when `capacity` suffices), or -1 on error. */
+long long aegis_musicxml_write(const int32_t* notes, const int32_t* strings, const int32_t* frets,
+                               const uint8_t* techniques, int32_t n, uint8_t* out, long long capacity);
 
 /* ---------------------------------------------------------------------------------------------
  * Corpus synthesis on device (Karplus-Strong plucks + noise rakes, generate_test_signal.py:5-53)

@@ -203,6 +203,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = C.c_longlong
         fn.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SmfOptions), C.c_void_p, C.c_longlong]
+    lib.aegis_musicxml_write.restype = C.c_longlong
+    lib.aegis_musicxml_write.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_longlong]
     lib.aegis_tabs.restype = C.c_int
     lib.aegis_tabs.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.aegis_guitar_blocks.restype = C.c_int

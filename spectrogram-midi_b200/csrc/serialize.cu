@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstring>
 #include <algorithm>
+#include <string>
 #include <vector>
 #include "common.cuh"
 
@@ -214,3 +215,48 @@ extern "C" int aegis_tabs(const int32_t* notes, int32_t n, int32_t* string_out, 
     }
     return 0;
 }
+
+// export_musicxml (aegis_engine_core/tabs.py:42-112): one 4/4 measure of quarter notes with string / fret technical
+// marks and bend / slide / vibrato symbols, byte for byte what xml.etree.ElementTree writes for the reference's tree
+// (declaration with single quotes, no whitespace between elements, attributes in insertion order, ` />` for empty
+// elements).  techniques: 0 none, 1 vibrato, 2 bend, 3 slide (the v1 codes; anything else adds no symbol).
+extern "C" long long aegis_musicxml_write(const int32_t* notes, const int32_t* strings, const int32_t* frets,
+                                          const uint8_t* techniques, int32_t n, uint8_t* out, long long capacity) {
+    using namespace aegis;
+    if (n < 0 || (n > 0 && (!notes || !strings || !frets))) {
+        set_error("aegis_musicxml_write: bad arguments");
+        return -1;
+    }
+    static const char* const kStep[12] = {"C", "C", "D", "D", "E", "F", "F", "G", "G", "A", "A", "B"};
+    static const bool kSharp[12] = {false, true, false, true, false, false, true, false, true, false, true, false};
+    std::string x;
+    x.reserve(512 + static_cast<size_t>(n) * 256);
+    x += "<?xml version='1.0' encoding='UTF-8'?>\n"
+         "<score-partwise version=\"3.1\"><part-list><score-part id=\"P1\"><part-name>Aegis Guitar</part-name></score-part>"
+         "</part-list><part id=\"P1\"><measure number=\"1\"><attributes><divisions>1</divisions><key><fifths>0</fifths></key>"
+         "<time><beats>4</beats><beat-type>4</beat-type></time><clef><sign>G</sign><line>2</line></clef>"
+         "<staff-details><staff-lines>6</staff-lines></staff-details></attributes>";
+    for (int i = 0; i < n; ++i) {
+        const int pitch = notes[i];
+        const int pc = ((pitch % 12) + 12) % 12;
+        // Python's floor division: (pitch // 12) - 1
+        const int octave = (pitch >= 0 ? pitch / 12 : -((-pitch + 11) / 12)) - 1;
+        x += "<note><pitch><step>";
+        x += kStep[pc];
+        x += "</step>";
+        if (kSharp[pc]) x += "<alter>1</alter>";
+        x += "<octave>" + std::to_string(octave) + "</octave></pitch><duration>1</duration><type>quarter</type><notations><technical><string>" +
+             std::to_string(strings[i]) + "</string><fret>" + std::to_string(frets[i]) + "</fret>";
+        const int tech = techniques ? techniques[i] : 0;
+        if (tech == 2) x += "<bend><bend-alter>2</bend-alter></bend></technical>";
+        else if (tech == 3) x += "</technical><slur type=\"start\" number=\"1\" />";
+        else if (tech == 1) x += "<hammer-on type=\"start\" /></technical><ornaments><wavy-line type=\"start\" number=\"1\" /></ornaments>";
+        else x += "</technical>";
+        x += "</notations></note>";
+    }
+    x += "</measure></part></score-partwise>";
+    const long long need = static_cast<long long>(x.size());
+    if (out != nullptr && capacity >= need) std::memcpy(out, x.data(), x.size());
+    return need;
+}
+
