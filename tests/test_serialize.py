@@ -5,6 +5,7 @@ mido, see oracle/midi_messages.py).  Host code only -- no GPU needed, the librar
 import io
 import os
 import sys
+import xml.etree.ElementTree as ET
 
 import numpy as np
 import pytest
@@ -39,6 +40,8 @@ def test_tabs_and_musicxml_match_reference(tabs_golden, tmp_path):
         path = str(tmp_path / f"{case}.xml")
         assert P.tabs.export_musicxml(tab, path) == path
         assert open(path, "rb").read() == g[f"{k}/xml"].tobytes(), case
+        root = ET.fromstring(P.tabs.musicxml_bytes(tab))      # and it is well-formed XML with one <note> per position
+        assert root.tag == "score-partwise" and len(root.findall("./part/measure/note")) == len(tab)
     assert skipped > 10     # unplayable notes are dropped, as in the reference
     eng = P.engine.AegisEngine(22050)
     assert eng.generate_tabs(events) == tab     # the engine methods of aegis_engine.py:32-36
