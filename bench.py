@@ -34,6 +34,7 @@ N_CLIPS = int(os.environ.get("AEGIS_BENCH_CLIPS", "1024"))
 HOP = 512
 METRIC = "audio-sec transcribed/sec (realtime factor)"
 UNIT = "audio-s/s"
+WORKLOAD = "cfg2: 1024 x 30 s clips @22050 Hz per GPU, STFT |X| + onset strength/peaks + RMS (n_fft 2048, hop 512)"
 
 
 def log(*a):
@@ -57,35 +58,91 @@ def _cpu_spectral_one(y):
     return float(S[3, 3]) + float(env.sum()) + len(peaks) + float(r.sum())
 
 
+_THREAD_VARS = ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS")
+
+
 def _pool_init():
-    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
-        os.environ[k] = "1"
+    """Worker start-up.  The workers are SPAWNED with the thread variables already set to 1 in the environment they
+    inherit (`single_threaded_env`), so their BLAS / OpenMP runtimes come up single-threaded: one process per core,
+    one thread per process, as the reference's multiprocessing pool runs (aegis_engine.py:207-210).  (Round 1 set the
+    variables here, after a fork: the parent's BLAS was already loaded with all its threads and the pool thrashed.)
+    threadpool_limits is the second line of defence for a runtime that ignores the environment."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=1)
+    except Exception:  # pragma: no cover
+        pass
 
 
-def cpu_throughput(clips, cores, repeats=1):
-    """audio-s/s of the CPU oracle over `clips` (numpy [n, N]) with a pool of `cores` processes."""
-    import multiprocessing as mp
+class single_threaded_env:
+    """Set the BLAS / OpenMP thread variables to 1 in os.environ while worker processes are started."""
 
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_pool_init) as pool:
-        pool.map(_cpu_spectral_one, [clips[i] for i in range(min(len(clips), cores))])  # warm caches / imports
+    def __enter__(self):
+        self.saved = {k: os.environ.get(k) for k in _THREAD_VARS}
+        for k in _THREAD_VARS:
+            os.environ[k] = "1"
+
+    def __exit__(self, *exc):
+        for k, v in self.saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+class CpuPool:
+    """multiprocessing.Pool(cores) of single-threaded workers, started with `spawn` (no fork of a process that holds a
+    CUDA context or a many-threaded BLAS)."""
+
+    def __init__(self, cores, fn=None):
+        import multiprocessing as mp
+
+        self.cores, self.fn = cores, fn or _cpu_spectral_one
+        with single_threaded_env():
+            self.pool = mp.get_context("spawn").Pool(cores, initializer=_pool_init)
+            self.pool.map(_worker_threads, range(cores))    # every worker is up (and its BLAS loaded) before the env is restored
+
+    def throughput(self, clips, repeats=1, warm=True):
+        """(audio-s/s, wall seconds) of the CPU oracle over `clips` (numpy [n, N]), one clip per task."""
+        if warm:
+            self.pool.map(self.fn, [clips[i] for i in range(min(len(clips), self.cores))])  # caches / imports / FFT plans
         t0 = time.perf_counter()
         for _ in range(repeats):
-            pool.map(_cpu_spectral_one, [clips[i] for i in range(len(clips))], chunksize=1)
+            self.pool.map(self.fn, [clips[i] for i in range(len(clips))], chunksize=1)
         dt = time.perf_counter() - t0
-    return repeats * len(clips) * CLIP_SECONDS / dt, dt
+        return repeats * clips.shape[0] * clips.shape[1] / SR / dt, dt
+
+    def worker_threads(self):
+        return max(self.pool.map(_worker_threads, range(self.cores)))
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
-def serial_throughput(clips):
+def _worker_threads(_):
+    """largest BLAS / OpenMP thread count of this worker (1 when the pool is set up correctly)"""
+    import numpy  # noqa: F401  (loads the BLAS)
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([int(d.get("num_threads", 1)) for d in threadpool_info()] or [1])
+    except Exception:  # pragma: no cover
+        return -1
+
+
+def serial_throughput(clips, fn=None):
     """audio-s/s of the CPU oracle on ONE core, in this process (SURVEY.md §8d asks for serial next to the pool)."""
     from threadpoolctl import threadpool_limits
 
+    fn = fn or _cpu_spectral_one
     with threadpool_limits(limits=1):   # BLAS is already loaded in this process: the environment variables come too late
-        _cpu_spectral_one(clips[0])     # warm caches / FFT plans
+        fn(clips[0])                    # warm caches / FFT plans
         t0 = time.perf_counter()
         for c in clips:
-            _cpu_spectral_one(c)
-        return len(clips) * CLIP_SECONDS / (time.perf_counter() - t0)
+            fn(c)
+        return clips.shape[0] * clips.shape[1] / SR / (time.perf_counter() - t0)
 
 
 def library_versions():
@@ -97,12 +154,29 @@ def library_versions():
     return {"python": platform.python_version(), "numpy": numpy.__version__, "scipy": scipy.__version__, "librosa": None}
 
 
-def pooled_rate(clips, cores):
-    """clips per second of the CPU oracle with the full pool busy (a single-process probe is several times faster per
-    clip than a worker of a saturated pool, and would oversize the bounded sample)."""
-    k = min(len(clips), 2 * cores)
-    _, dt = cpu_throughput(clips[:k], cores)
+def pooled_rate(pool, clips):
+    """clips per second of the CPU oracle with the full pool busy (sizes the bounded sample)."""
+    k = min(len(clips), 2 * pool.cores)
+    _, dt = pool.throughput(clips[:k])
     return k / dt
+
+
+def cpu_baseline_record(pool, sample, what, serial_clips=3):
+    """The `cpu_baseline` object: pooled throughput on `sample`, the one-core figure beside it, and a self-check that the
+    pool really used its cores (round 1's pool ran many-threaded BLAS in every worker and was ~10x slow)."""
+    v, dt = pool.throughput(sample)
+    serial = serial_throughput(sample[:serial_clips], pool.fn)
+    rec = {"value": v, "unit": UNIT, "cores": pool.cores, "kind": "port",
+           "sample": f"{what}; multiprocessing.Pool({pool.cores}) of single-threaded spawned workers, one clip per task, {dt:.1f} s wall; "
+                     "numpy/scipy oracle port of the librosa path (librosa is not installable here)",
+           "serial_value": serial, "serial_sample": f"{serial_clips} clips on one core, same process",
+           "worker_blas_threads": pool.worker_threads(), "versions": library_versions()}
+    if v < 0.5 * pool.cores * serial:
+        # expected on SMT hosts (os.cpu_count() counts hyper-threads) and when the sample is shorter than a few tasks per
+        # worker; a pool that thrashes shows up as a ratio far below this
+        rec["cpu_baseline_suspect"] = True
+    rec["pool_efficiency"] = v / (pool.cores * serial)
+    return rec
 
 
 def host_sample_clips(n, seed0=0):
@@ -113,7 +187,8 @@ def host_sample_clips(n, seed0=0):
 
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the path.  librosa cannot be installed
-    here (no network, not in the wheelhouse), so this times the oracle port with every host core."""
+    here (no network, not in the wheelhouse), so this times the oracle port with every host core: one single-threaded
+    worker process per core, sharded by clip (the generous reading of Turbo Mode, aegis_engine.py:183-216)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -121,30 +196,38 @@ def run_reference(args):
     import numpy as np  # noqa: F401
 
     t_probe0 = time.perf_counter()
+    pool = CpuPool(cores)
     probe = host_sample_clips(2 * max(cores, 4))
-    rate = pooled_rate(probe, cores)
+    rate = pooled_rate(pool, probe)
     # bounded sample: ~8 s of wall per step on all cores and the whole run within ~2.5 minutes
     per_step_s = min(8.0, 150.0 / max(1, args.steps))
     n = int(min(1024, max(cores, round(rate * per_step_s))))
     clips = host_sample_clips(n) if n > len(probe) else probe[:n]
-    log(f"[reference] cores={cores} pooled rate={rate:.1f} clips/s sample={n} clips per step (setup {time.perf_counter() - t_probe0:.1f}s)")
-    # (the pooled probe above was the warm-up: page cache, imports, FFT plans)
+    log(f"[reference] cores={cores} worker BLAS threads={pool.worker_threads()} pooled rate={rate:.1f} clips/s "
+        f"sample={n} clips per step (setup {time.perf_counter() - t_probe0:.1f}s)")
+    for _ in range(args.warmup):
+        pool.throughput(clips[: 2 * cores], warm=False)
     t_total = 0.0
     for _ in range(args.steps):
-        _, dt = cpu_throughput(clips, cores)
+        _, dt = pool.throughput(clips, warm=False)
         t_total += dt
     value = args.steps * n * CLIP_SECONDS / t_total
+    serial = serial_throughput(clips[:3])
+    pool.close()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "cfg2: 1024 x 30 s clips @22050 Hz, STFT |X| + onset strength/peaks + RMS (n_fft 2048, hop 512)",
-                   "sample_clips_per_step": n},
+        "config": {"workload": WORKLOAD, "sample_clips_per_step": n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n} clips x 30 s per step, multiprocessing.Pool({cores}) by clip, numpy/scipy oracle port"},
+                         "sample": f"{n} clips x 30 s per step, multiprocessing.Pool({cores}) of single-threaded workers by clip, "
+                                   "numpy/scipy oracle port",
+                         "serial_value": serial, "pool_efficiency": value / (cores * serial)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if value < 0.5 * cores * serial:
+        line["cpu_baseline"]["cpu_baseline_suspect"] = True
     print(json.dumps(line), flush=True)
 
 
@@ -367,22 +450,18 @@ def run_gpu(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        rate = pooled_rate(y[: 2 * cores].cpu().numpy(), cores)
+        pool = CpuPool(cores)                        # spawned, single-threaded workers (no fork of this CUDA process)
+        rate = pooled_rate(pool, y[: 2 * cores].cpu().numpy())
         n = int(min(N_CLIPS, max(cores, round(15.0 * rate))))   # ~15 s of wall with every core busy
-        sample = y[:n].cpu().numpy()
-        v, dt = cpu_throughput(sample, cores)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {n} clips of the batch ({n * CLIP_SECONDS:.0f} audio-s), Pool({cores}) by clip, {dt:.1f} s wall; "
-                         "numpy/scipy oracle port of the librosa path (librosa not installable here)",
-               "serial_value": serial_throughput(sample[:6]), "serial_sample": "6 clips on one core, same process",
-               "versions": library_versions()}
+        cpu = cpu_baseline_record(pool, y[:n].cpu().numpy(), f"first {n} clips of the batch ({n * CLIP_SECONDS:.0f} audio-s)")
+        pool.close()
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: 1024 x 30 s clips @22050 Hz per GPU, STFT |X| + onset strength/peaks + RMS (n_fft 2048, hop 512)",
+            "config": {"workload": WORKLOAD,
                        "clips_per_gpu": N_CLIPS, "clip_seconds": CLIP_SECONDS, "sr": SR, "frames_per_clip": T, "sharding": "by clip",
                        "host_affinity": None if host_cpus is None else f"rank 0 pinned to the {len(host_cpus)} CPUs next to its GPU (NVML)",
                        "l2": "inputs (2.7 GB) and outputs (5.4 GB) per step exceed the 126 MB L2; no flush needed"},
