@@ -48,7 +48,7 @@ constexpr int VT_MAX_BINS = 512;
 constexpr int VT_HALO = 64;            // V halo: sources outside [0, n) read -inf; needs half_width + 7 <= 64
 constexpr int VT_MAX_HW = 50;
 constexpr int VT_MAX_W = 2 * VT_MAX_HW + 1;
-constexpr int VT_SMEM_VARIANTS = 4;    // interior row variants kept in shared memory (librosa's tables have 3)
+constexpr int VT_SMEM_VARIANTS = 3;    // interior row variants kept in shared memory (librosa's tables have 3; more are served like edge rows)
 constexpr int VT_MAX_WIN = VT_MAX_BINS / 32;   // windows of 32 destination bins
 constexpr int VT_CHUNK = 8;            // sources are pruned in aligned chunks of 8 bins
 constexpr int VT_CHUNK_PAD = 8;        // chunk indices -8 .. (512/8 + 8)
@@ -90,9 +90,19 @@ __device__ __forceinline__ double lower_bound_from_hi(unsigned hmax) {
 __device__ __forceinline__ double upper_bound_from_hi(unsigned hmin) {
     return __hiloint2double(static_cast<int>(hmin), 0);
 }
+// max of two doubles that are never NaN (fmax's NaN handling costs two extra instructions per call)
+__device__ __forceinline__ double dmax(double a, double b) { return b > a ? b : a; }
 __device__ __forceinline__ double warp_max_d(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = dmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// Read-only tables (written once before the frame loop) are read through 32-bit shared addresses with an immediate
+// offset: one LDS per value, no address arithmetic beyond one add.  Not volatile: the contents never change.
+template <int IMM>
+__device__ __forceinline__ double lds_table(unsigned addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM));
     return v;
 }
 
@@ -134,10 +144,10 @@ __device__ __forceinline__ void viterbi_task(const VitSmem& s, const aegis_viter
     {
         const int dr = min(d, n - 1);
         const double x0 = Vc0[d], x1 = Vc0[VROW + d];
-        L = fmax(x0 + lt_row(dr, dv, hw), x1 + lt_row(dr, 1 - dv, hw));   // table (source voicing sv -> dv) = sv ^ dv
+        L = dmax(x0 + lt_row(dr, dv, hw), x1 + lt_row(dr, 1 - dv, hw));   // table (source voicing sv -> dv) = sv ^ dv
         const int pv = s.prev[dv][d];
         const int sv = pv >= n, bs = pv - sv * n, o = d - bs + hw;
-        if (o >= 0 && o < W) L = fmax(L, Vc0[sv * VROW + bs] + lt_row(bs, sv ^ dv, o));
+        if (o >= 0 && o < W) L = dmax(L, Vc0[sv * VROW + bs] + lt_row(bs, sv ^ dv, o));
     }
     const double Lmin = lower_bound_from_hi(__reduce_max_sync(0xffffffffu, live ? static_cast<unsigned>(__double2hiint(L)) : 0u));
 
@@ -183,7 +193,9 @@ __device__ __forceinline__ void viterbi_task(const VitSmem& s, const aegis_viter
             mask = __ballot_sync(0xffffffffu, (Mrow[r] + s.ubrmax[sel][r] >= Lmin) && lane < NCHW);
         }
         const double* ubr_l = &s.ubr[sel][VT_UBR_PAD + ohi0];      // this lane's bound for window chunk r: ubr_l[-8 r]
-        const char* lt_l = reinterpret_cast<const char*>(&s.lt[0][sel][VT_LT_PAD + ohi0]);   // table entry of chunk r, source j: lt_l[row offset - 64 r - 8 j]
+        // shared address of this lane's table entry for (variant 0, window chunk 0, source 0); chunk r, source j of a row
+        // with table offset `off` sits at  + off - 64 r - 8 j
+        const unsigned lt_l = static_cast<unsigned>(__cvta_generic_to_shared(&s.lt[0][sel][VT_LT_PAD + ohi0]));
         while (mask) {
             const int r = __ffs(mask) - 1;
             mask &= mask - 1;
@@ -193,30 +205,42 @@ __device__ __forceinline__ void viterbi_task(const VitSmem& s, const aegis_viter
             // the sources are real candidates, visited in ascending order)
             const int b0 = VT_CHUNK * (c_lo + r);
             const uint4 ro = *reinterpret_cast<const uint4*>(&roff[b0]);   // 8 table offsets (16 bit each), warp-uniform
-            const char* base = lt_l - 8 * VT_CHUNK * r;
-            const int ohi = ohi0 - VT_CHUNK * r;    // offset of the chunk's first source in this destination's band
-            // table value of source j of the chunk (compile-time j); an edge row's table is in global memory, range-checked
-            auto tval = [&](const unsigned off, const int j) -> double {
-                if (!(off & VT_EDGE_BIT)) return *reinterpret_cast<const double*>(base + off - 8 * j);   // warp-uniform branch
-                const int o = ohi - j;
-                const bool in = static_cast<unsigned>(o) < static_cast<unsigned>(W);
-                return in ? __ldg(p.lt_variants + (off & 0x7FFFu) + sel * W + o) : NEG_INF;
-            };
+            if (((ro.x | ro.y | ro.z | ro.w) & 0x80008000u) == 0u) {
+                // all 8 rows are interior rows: tables in shared memory, -inf padded, no range checks
+                const unsigned base = lt_l - 8 * VT_CHUNK * r;
 #pragma unroll
-            for (int h = 0; h < VT_CHUNK; h += 4) {   // half a chunk at a time: 4 candidates live
-                const double2 xa = *reinterpret_cast<const double2*>(&Vc[b0 + h]);
-                const double2 xb = *reinterpret_cast<const double2*>(&Vc[b0 + h + 2]);
-                const unsigned ra = h == 0 ? ro.x : ro.z, rb = h == 0 ? ro.y : ro.w;
-                double c0 = xa.x + tval(ra & 0xFFFFu, h);
-                double c1 = xa.y + tval(ra >> 16, h + 1);
-                double c2 = xb.x + tval(rb & 0xFFFFu, h + 2);
-                double c3 = xb.y + tval(rb >> 16, h + 3);
-                // leftmost-max tournament over the 4 candidates, then against the running best (lower indices)
-                int i0 = h, i2 = h + 2;
-                take_later(c0, i0, c1, h + 1);
-                take_later(c2, i2, c3, h + 3);
-                take_later(c0, i0, c2, i2);
-                if (c0 > best) { best = c0; arg = kbase + b0 + i0; }
+                for (int h = 0; h < VT_CHUNK; h += 4) {   // half a chunk at a time: 4 candidates live
+                    const double2 xa = *reinterpret_cast<const double2*>(&Vc[b0 + h]);
+                    const double2 xb = *reinterpret_cast<const double2*>(&Vc[b0 + h + 2]);
+                    const unsigned ra = h == 0 ? ro.x : ro.z, rb = h == 0 ? ro.y : ro.w;
+                    double c0 = xa.x + (h == 0 ? lds_table<0>(base + (ra & 0xFFFFu)) : lds_table<-32>(base + (ra & 0xFFFFu)));
+                    double c1 = xa.y + (h == 0 ? lds_table<-8>(base + (ra >> 16)) : lds_table<-40>(base + (ra >> 16)));
+                    double c2 = xb.x + (h == 0 ? lds_table<-16>(base + (rb & 0xFFFFu)) : lds_table<-48>(base + (rb & 0xFFFFu)));
+                    double c3 = xb.y + (h == 0 ? lds_table<-24>(base + (rb >> 16)) : lds_table<-56>(base + (rb >> 16)));
+                    // leftmost-max tournament over the 4 candidates, then against the running best (lower indices)
+                    int i0 = h, i2 = h + 2;
+                    take_later(c0, i0, c1, h + 1);
+                    take_later(c2, i2, c3, h + 3);
+                    take_later(c0, i0, c2, i2);
+                    if (c0 > best) { best = c0; arg = kbase + b0 + i0; }
+                }
+            } else {
+                // a chunk with truncated edge rows: their tables are in global memory (L1 resident), range-checked
+                const int ohi = ohi0 - VT_CHUNK * r;    // offset of the chunk's first source in this destination's band
+#pragma unroll 1
+                for (int j = 0; j < VT_CHUNK; ++j) {
+                    const unsigned off = roff[b0 + j];   // warp-uniform
+                    const int o = ohi - j;
+                    double tv;
+                    if (!(off & VT_EDGE_BIT)) {
+                        tv = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(&s.lt[0][sel][VT_LT_PAD + o]) + off);
+                    } else {
+                        const bool in = static_cast<unsigned>(o) < static_cast<unsigned>(W);
+                        tv = in ? __ldg(p.lt_variants + (off & 0x7FFFu) + sel * W + o) : NEG_INF;
+                    }
+                    const double v = Vc[b0 + j] + tv;
+                    if (v > best) { best = v; arg = kbase + b0 + j; }   // ascending sources, strict >
+                }
             }
         }
         if (oob_possible && ga > d + hw && oob > best) { best = oob; arg = kbase + ga; }   // higher indices than the band
@@ -227,8 +251,7 @@ __device__ __forceinline__ void viterbi_task(const VitSmem& s, const aegis_viter
 template <int HW, int NW, int MINB>
 __global__ void __launch_bounds__(32 * NW, MINB)
 viterbi_forward_kernel(const aegis_viterbi_params p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    VitSmem& s = *reinterpret_cast<VitSmem*>(smem_raw);
+    __shared__ VitSmem s;   // static (< 48 KB): every access is an LDS / STS with an immediate offset
     const int clip = blockIdx.x;
     const int b = threadIdx.x, lane = b & 31, warp = b >> 5;
     constexpr int hw = HW, W = 2 * HW + 1;
@@ -337,9 +360,9 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
         const int d = 32 * win + lane;
         if (d < n) s.V[nxt][v][VT_HALO + d] = xv;
         double cm = xv;
-        cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
-        cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
-        cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 4));
+        cm = dmax(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+        cm = dmax(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+        cm = dmax(cm, __shfl_xor_sync(0xffffffffu, cm, 4));
         const int ch = (d >> 3) + VT_CHUNK_PAD;
         if ((lane & 7) == 0) s.M[nxt][v][ch] = cm + s.cdub[ch];
         const unsigned hmin = __reduce_min_sync(0xffffffffu, static_cast<unsigned>(__double2hiint(xv)));
@@ -403,7 +426,9 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                 int win, dv;
                 if (task < n_voiced) {
                     dv = 0;
-                    win = __fns(vmask, 0, task + 1);
+                    unsigned m = vmask;   // the task-th set bit
+                    for (int k = 0; k < task; ++k) m &= m - 1;
+                    win = dense_v ? task : __ffs(m) - 1;
                 } else {
                     dv = 1;
                     const int k = task - n_voiced;
@@ -501,12 +526,8 @@ static int launch_forward(const aegis_viterbi_params* p, cudaStream_t st) {
     int nw = 0;
     if (n_win <= 14) { kern = viterbi_forward_kernel<HW, 7, 4>; nw = 7; }     // 441 bins (E2..C6): 7 warps, four clips per SM
     else { kern = viterbi_forward_kernel<HW, 8, 4>; nw = 8; }                 // up to 512 bins
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(VitSmem)));
-    if (e != cudaSuccess) {
-        set_error("aegis_viterbi: cannot reserve %zu B shared memory: %s", sizeof(VitSmem), cudaGetErrorString(e));
-        return 2;
-    }
-    kern<<<p->n_clips, 32 * nw, sizeof(VitSmem), st>>>(*p);
+    static_assert(sizeof(VitSmem) <= 48 * 1024, "VitSmem must fit static shared memory");
+    kern<<<p->n_clips, 32 * nw, 0, st>>>(*p);
     return check_launch("aegis_viterbi(forward)");
 }
 
