@@ -213,7 +213,8 @@ typedef struct {
     int32_t ema_span;
     int32_t boll_window;
     int32_t macd_fast, macd_slow, macd_signal;
-    int32_t _reserved0;
+    int32_t consensus_mask;    /* filters that vote in the consensus: bit 0 savgol, 1 kalman, 2 holt; 0 = all three
+                                  (multi_filter_consensus(data, filters=[...]), financial_filters.py:256-298) */
     double kalman_q, kalman_r;
     double holt_alpha, holt_beta;
     double boll_num_std;
@@ -389,9 +390,14 @@ long long aegis_fin_scratch_bytes(int n_clips, int n_frames);
 
 /* ---------------------------------------------------------------------------------------------
  * K9  audio ingest: PCM -> float32, channel mix-down, polyphase rate conversion
- * replaces: librosa.load(path, sr=engine rate) after the file read (aegis_engine.py:24, aegis_engine_financial.py:45):
- *           soundfile's int16 -> float32 / 32768, librosa.to_mono, librosa.resample(res_type='polyphase')
- *           = scipy.signal.resample_poly(y, up, down).  `taps` is scipy.signal.firwin(2 * 10 * max(up, down) + 1,
+ * replaces: librosa.load(path, sr=engine rate, res_type='polyphase') after the file read: soundfile's
+ *           int16 -> float32 / 32768, librosa.to_mono, librosa.resample(res_type='polyphase')
+ *           = scipy.signal.resample_poly(y, up, down).  NOTE: the reference's own call sites (aegis_engine.py:24,
+ *           aegis_engine_financial.py:45) pass no res_type, so librosa converts with its default 'soxr_hq' (libsoxr):
+ *           that resampler is NOT what this entry point computes (libsoxr is absent from the image and its
+ *           arithmetic cannot be restated); the Python layer warns (ResampleDivergenceWarning) whenever it has to
+ *           substitute.  Parity with the reference holds for files already at the engine rate, or when both sides
+ *           use res_type='polyphase'.  `taps` is scipy.signal.firwin(2 * 10 * max(up, down) + 1,
  *           1 / max(up, down), window=('kaiser', 5.0)) in float32 times `up`; n_pre_pad = down - half_len % down,
  *           n_pre_remove = (half_len + n_pre_pad) / down, n_out = ceil(n_in * up / down)  (scipy/signal/_signaltools.py).
  * ------------------------------------------------------------------------------------------- */

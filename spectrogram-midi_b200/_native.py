@@ -80,7 +80,7 @@ class TrendParams(C.Structure):
     _fields_ = [
         ("x", _ptr), ("n_series", i32), ("n", i32), ("savgol_coeffs", _ptr),
         ("savgol_window", i32), ("sma_window", i32), ("ema_span", i32), ("boll_window", i32),
-        ("macd_fast", i32), ("macd_slow", i32), ("macd_signal", i32), ("_reserved0", i32),
+        ("macd_fast", i32), ("macd_slow", i32), ("macd_signal", i32), ("consensus_mask", i32),
         ("kalman_q", f64), ("kalman_r", f64), ("holt_alpha", f64), ("holt_beta", f64),
         ("boll_num_std", f64),
         ("compact", _ptr), ("scratch", _ptr), ("savgol", _ptr), ("kalman", _ptr), ("holt", _ptr),

@@ -220,7 +220,7 @@ def yin_candidates(y: torch.Tensor, cfg: tables.PyinConfig, *, center: bool = Tr
     if max_cand is None:
         max_cand = cfg.max_troughs
     n_fr = n_clips * T
-    key = ("pyin", cfg.sr, cfg.hop_length, cfg.fmin, cfg.fmax, cfg.n_thresholds)
+    key = ("pyin",) + cfg.cache_key   # every table-determining parameter (sr/hop/fmin/fmax alone alias configs)
     P = nat.YinParams()
     P.y, P.clip_stride, P.n_samples, P.n_clips = _audio_ptr(y), y.stride(0), n_samples, n_clips
     P.hop, P.pad, P.n_frames = cfg.hop_length, ((cfg.frame_length // 2 if center else 0) if pad is None else int(pad)), T
@@ -259,7 +259,7 @@ def viterbi_decode(obs: dict, cfg: tables.PyinConfig, n_clips: int, *, fill_na: 
     T = obs["n_frames"]
     dev = obs["cand_bin"].device
     nb = cfg.n_pitch_bins
-    key = ("hmm", cfg.sr, cfg.hop_length, cfg.fmin, cfg.fmax)
+    key = ("hmm",) + cfg.cache_key
     P = nat.ViterbiParams()
     P.n_clips, P.n_frames, P.n_pitch_bins, P.half_width = n_clips, T, nb, cfg.half_width
     P.n_variants, P.n_interior_variants, P.max_cand = cfg.lt_variants.shape[0], cfg.n_interior_variants, obs["max_cand"]
@@ -315,8 +315,10 @@ TREND_OUTPUTS = ("savgol", "kalman", "holt", "consensus", "consensus_conf", "sma
 def trend_filters(x: torch.Tensor, *, want=TREND_OUTPUTS, savgol_window: int = 11, savgol_polyorder: int = 3,
                   kalman_q: float = 1e-5, kalman_r: float = 1e-1, holt_alpha: float = 0.3, holt_beta: float = 0.1,
                   sma_window: int = 5, ema_span: int = 5, boll_window: int = 20, boll_num_std: float = 2.0,
-                  macd_fast: int = 12, macd_slow: int = 26, macd_signal: int = 9) -> dict:
-    """Batched float64 trend filters over f0 series [n_series, n] (NaN = unvoiced)."""
+                  macd_fast: int = 12, macd_slow: int = 26, macd_signal: int = 9,
+                  consensus_filters=("savgol", "kalman", "holt")) -> dict:
+    """Batched float64 trend filters over f0 series [n_series, n] (NaN = unvoiced).  ``consensus_filters``: the filters
+    that vote in ``consensus`` / ``consensus_conf`` (``multi_filter_consensus(data, filters=[...])``)."""
     if not x.is_cuda:
         raise nat.AegisNativeError("expected a CUDA tensor: the Aegis B200 path has no CPU implementation")
     if x.dim() == 1:
@@ -338,7 +340,11 @@ def trend_filters(x: torch.Tensor, *, want=TREND_OUTPUTS, savgol_window: int = 1
     out = {}
     need = set(want)
     if need & {"consensus", "consensus_conf"}:
-        need |= {"savgol", "kalman", "holt"}
+        votes = [f for f in ("savgol", "kalman", "holt") if f in consensus_filters]
+        if not votes:
+            raise ValueError("consensus needs at least one of savgol / kalman / holt")
+        need |= set(votes)
+        P.consensus_mask = sum(1 << ("savgol", "kalman", "holt").index(f) for f in votes)
     if need & {"boll_upper", "boll_lower"}:
         need |= {"boll_ma"}
     if need & {"macd_sig", "macd_hist"}:

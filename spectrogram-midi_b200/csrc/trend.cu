@@ -214,8 +214,11 @@ trend_kernel(const aegis_trend_params p) {
 
     // ---- phase 4: consensus = nanmedian, confidence = 1 / (1 + nanstd) over the three filters
     if (p.consensus || p.consensus_conf) {
+        // a filter that does not vote contributes NaN, which nanmedian / nanstd skip (financial_filters.py:270-296)
+        const int votes = (p.consensus_mask & 7) ? (p.consensus_mask & 7) : 7;
         for (int i = tid; i < n; i += TR_THREADS) {
-            const double r[3] = {p.savgol[off + i], p.kalman[off + i], p.holt[off + i]};
+            const double r[3] = {(votes & 1) ? p.savgol[off + i] : nan64(), (votes & 2) ? p.kalman[off + i] : nan64(),
+                                 (votes & 4) ? p.holt[off + i] : nan64()};
             double v[3];
             int cnt = 0;
             double sum = 0.0;
@@ -255,8 +258,11 @@ extern "C" int aegis_trend_filters(const aegis_trend_params* p, void* stream) {
         AEGIS_REQUIRE(p->compact && p->scratch && p->savgol_coeffs, "aegis_trend_filters: savgol needs compact/scratch workspaces and coefficients");
         AEGIS_REQUIRE(p->savgol_window >= 1 && (p->savgol_window & 1), "aegis_trend_filters: savgol window must be odd");
     }
-    if (p->consensus || p->consensus_conf)
-        AEGIS_REQUIRE(p->savgol && p->kalman && p->holt, "aegis_trend_filters: consensus needs savgol, kalman and holt outputs");
+    if (p->consensus || p->consensus_conf) {
+        const int votes = (p->consensus_mask & 7) ? (p->consensus_mask & 7) : 7;
+        AEGIS_REQUIRE((!(votes & 1) || p->savgol) && (!(votes & 2) || p->kalman) && (!(votes & 4) || p->holt),
+                      "aegis_trend_filters: consensus needs the outputs of the filters that vote (consensus_mask=%d)", p->consensus_mask);
+    }
     if (p->boll_upper || p->boll_lower) AEGIS_REQUIRE(p->boll_ma && p->boll_window >= 1 && p->boll_window <= BOLL_MAX_WINDOW, "aegis_trend_filters: bands need boll_ma and 1 <= boll_window <= 128");
     if (p->sma) AEGIS_REQUIRE(p->sma_window >= 1, "aegis_trend_filters: bad sma_window");
     if (p->macd_sig || p->macd_hist) AEGIS_REQUIRE(p->macd_line != nullptr, "aegis_trend_filters: MACD signal/hist need macd_line");

@@ -188,9 +188,11 @@ __device__ __forceinline__ void viterbi_task(const VitSmem& s, const aegis_viter
         // ---- prefilter: lane r holds window chunk c_lo + r
         const double* Mrow = &s.M[cur][sv][c_lo + VT_CHUNK_PAD];
         unsigned mask;
+        double pb;   // lane r: bound of window chunk r that holds for all 32 destinations
         {
             const int r = lane < NCHW ? lane : 0;
-            mask = __ballot_sync(0xffffffffu, (Mrow[r] + s.ubrmax[sel][r] >= Lmin) && lane < NCHW);
+            pb = lane < NCHW ? Mrow[r] + s.ubrmax[sel][r] : NEG_INF;
+            mask = __ballot_sync(0xffffffffu, pb >= Lmin);
         }
         const double* ubr_l = &s.ubr[sel][VT_UBR_PAD + ohi0];      // this lane's bound for window chunk r: ubr_l[-8 r]
         // shared address of this lane's table entry for (variant 0, window chunk 0, source 0); chunk r, source j of a row
@@ -224,23 +226,30 @@ __device__ __forceinline__ void viterbi_task(const VitSmem& s, const aegis_viter
                     take_later(c0, i0, c2, i2);
                     if (c0 > best) { best = c0; arg = kbase + b0 + i0; }
                 }
+                if (mask) {   // chunks whose window-wide bound is <= every lane's running best cannot win (strict >) any more
+                    const double bmin = lower_bound_from_hi(__reduce_max_sync(0xffffffffu, live ? static_cast<unsigned>(__double2hiint(best)) : 0u));
+                    mask &= __ballot_sync(0xffffffffu, pb > bmin);
+                }
             } else {
                 // a chunk with truncated edge rows: their tables are in global memory (L1 resident), range-checked
                 const int ohi = ohi0 - VT_CHUNK * r;    // offset of the chunk's first source in this destination's band
-#pragma unroll 1
+                const double* gt = p.lt_variants + sel * W + ohi;
+                const unsigned base = lt_l - 8 * VT_CHUNK * r;
+                const unsigned rr[4] = {ro.x, ro.y, ro.z, ro.w};
+#pragma unroll
                 for (int j = 0; j < VT_CHUNK; ++j) {
-                    const unsigned off = roff[b0 + j];   // warp-uniform
-                    const int o = ohi - j;
+                    const unsigned off = (j & 1) ? (rr[j >> 1] >> 16) : (rr[j >> 1] & 0xFFFFu);   // warp-uniform
                     double tv;
                     if (!(off & VT_EDGE_BIT)) {
-                        tv = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(&s.lt[0][sel][VT_LT_PAD + o]) + off);
+                        tv = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(&s.lt[0][sel][VT_LT_PAD + ohi - j]) + off);
                     } else {
-                        const bool in = static_cast<unsigned>(o) < static_cast<unsigned>(W);
-                        tv = in ? __ldg(p.lt_variants + (off & 0x7FFFu) + sel * W + o) : NEG_INF;
+                        const bool in = static_cast<unsigned>(ohi - j) < static_cast<unsigned>(W);
+                        tv = in ? __ldg(gt + (off & 0x7FFFu) - j) : NEG_INF;
                     }
                     const double v = Vc[b0 + j] + tv;
                     if (v > best) { best = v; arg = kbase + b0 + j; }   // ascending sources, strict >
                 }
+                (void)base;
             }
         }
         if (oob_possible && ga > d + hw && oob > best) { best = oob; arg = kbase + ga; }   // higher indices than the band

@@ -65,6 +65,14 @@ def _world(group=None) -> tuple:
     return 0, 1
 
 
+def collective_device(group=None):
+    """Where tensors handed to a collective must live: the rank's current CUDA device under NCCL (a CPU tensor makes
+    NCCL fail on that rank while the others block), the host under gloo or without a group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return None
+
+
 def all_reduce_max(t: torch.Tensor, group=None) -> torch.Tensor:
     if _world(group)[1] > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
@@ -95,24 +103,31 @@ def all_gather_ragged(t: torch.Tensor, group=None) -> List[torch.Tensor]:
 
 
 def gather_counts(local_count: int, device=None, group=None) -> List[int]:
-    """Per-rank counts (e.g. clips analysed, events found) for reporting."""
-    t = torch.tensor([local_count], dtype=torch.int64, device=device)
+    """Per-rank counts (e.g. clips analysed, events found) for reporting.  ``device=None`` picks the device the
+    group's backend needs (a rank that owns zero clips has no tensor to borrow one from)."""
+    t = torch.tensor([local_count], dtype=torch.int64, device=device if device is not None else collective_device(group))
     return [int(x[0]) for x in all_gather_ragged(t, group)]
 
 
+# compact transport record (22 bytes, packed) for reporting; the product path gathers the kernels' own 40-byte records
 EVENT_DTYPE = np.dtype([("note", "<i2"), ("start", "<i4"), ("end", "<i4"), ("velocity", "u1"), ("track", "u1"),
                         ("technique", "u1"), ("_pad", "u1"), ("confidence", "<f4"), ("slope", "<f4")])
 
 
-def gather_note_events(events: np.ndarray, device=None, group=None) -> np.ndarray:
-    """All-gather note-event records (``EVENT_DTYPE``, 24 B each) from every rank, in rank order."""
-    events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
-    raw = torch.from_numpy(events.view(np.uint8).reshape(len(events), EVENT_DTYPE.itemsize).copy())
+def gather_note_events(events: np.ndarray, device=None, group=None, dtype=EVENT_DTYPE) -> np.ndarray:
+    """All-gather note-event records from every rank, in rank order: north_star's only cross-GPU exchange of the
+    long-clip path.  ``dtype`` is the record layout (``EVENT_DTYPE``, 22 B, or ``core.NOTE_EVENT_DTYPE``, the 40-byte
+    records kernel K7 writes); the bytes travel as uint8 rows, padded to the largest rank and trimmed."""
+    dtype = np.dtype(dtype)
+    events = np.ascontiguousarray(events, dtype=dtype)
+    raw = torch.from_numpy(events.view(np.uint8).reshape(len(events), dtype.itemsize).copy())
+    if device is None:
+        device = collective_device(group)
     if device is not None:
         raw = raw.to(device)
     parts = all_gather_ragged(raw, group)
     flat = torch.cat(parts).cpu().numpy()
-    return flat.reshape(-1).view(EVENT_DTYPE) if flat.size else np.zeros(0, EVENT_DTYPE)
+    return flat.reshape(-1).view(dtype) if flat.size else np.zeros(0, dtype)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -185,7 +200,27 @@ class CudaBackend:
         obs = dict(cand_bin=cand_bin.contiguous(), cand_prob=cand_prob.contiguous(), cand_count=cand_count.contiguous(),
                    voiced_prob=voiced_prob[None].contiguous(), n_frames=T, max_cand=mc)
         dec = core.viterbi_decode(obs, self.cfg, 1)
-        return {"f0": dec["f0"][0], "voiced_flag": dec["voiced_flag"][0]}
+        return {"f0": dec["f0"][0], "voiced_flag": dec["voiced_flag"][0], "states": dec["states"][0]}
+
+    def note_events(self, res: dict, **kwargs) -> np.ndarray:
+        """``get_midi_events`` (midi_logic.py:32-148) on full-length host arrays with kernel K7 -> records of
+        ``core.NOTE_EVENT_DTYPE`` in time order.  MIDI notes come from the Viterbi states through the host-made table."""
+        from . import core, tables
+
+        def dev(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.device)[None]
+
+        lut = np.array([int(round(float(tables.hz_to_midi(f)))) for f in self.cfg.freqs], dtype=np.int16)
+        states = res.get("states")
+        out = core.note_events(dev(res["rake_mask"], np.uint8), dev(np.nan_to_num(res["f0"]), np.float64),
+                               dev(res["voiced_flag"], np.uint8), dev(res["voiced_probs"], np.float64), dev(res["rms"], np.float32),
+                               sr=self.sr, hop_length=self.hop,
+                               pitch_index=None if states is None else dev(states, np.int16),
+                               note_lut=None if states is None else torch.from_numpy(lut).to(self.device), **kwargs)
+        n = int(out["n_events"][0])
+        if n > out["max_events"]:
+            raise RuntimeError(f"{n} note events exceed the buffer of {out['max_events']}")
+        return out["events"][0, :n].cpu().numpy().reshape(-1).view(core.NOTE_EVENT_DTYPE).copy()
 
 
 MIN_MARGIN_FRAMES = 32  # the rake run-length gate looks at up to 30 neighbouring columns
@@ -193,7 +228,8 @@ MIN_MARGIN_FRAMES = 32  # the rake run-length gate looks at up to 30 neighbourin
 
 def analyze_long_clip(y, *, sr: float, hop_length: int = 512, fmin: Optional[float] = None, fmax: Optional[float] = None,
                       rake_sensitivity: float = 0.6, mode: str = "exact", burn_seconds: float = 2.0, group=None,
-                      backend=None, windows_per_rank: int = 1) -> dict:
+                      backend=None, windows_per_rank: int = 1, return_events: bool = False,
+                      event_kwargs: Optional[dict] = None) -> dict:
     """Perception arrays of ONE long clip computed by all ranks of ``group`` (each rank can read the clip,
     or at least its own windows, from host memory).  Every rank returns the full-length result:
     ``rake_mask, f0 (NaN unvoiced), voiced_flag, voiced_probs, rms`` as numpy arrays (aegis_engine.py:72-75).
@@ -201,6 +237,13 @@ def analyze_long_clip(y, *, sr: float, hop_length: int = 512, fmin: Optional[flo
     The clip is cut into ``world * windows_per_rank`` overlapping windows; rank r owns windows
     ``r*windows_per_rank ...`` (``windows_per_rank > 1`` bounds device memory for hour-long clips and lets a
     single GPU exercise the same stitching).
+
+    ``return_events=True`` adds ``events``: the v1 note events of the whole clip (``get_midi_events``,
+    midi_logic.py:32-148; records of ``core.NOTE_EVENT_DTYPE``, keyword arguments in ``event_kwargs``), assembled with
+    the path's one event collective: the note state machine is a single sequential chain over the clip (and its
+    dB scale needs the clip-wide RMS maximum), so every rank runs it on the gathered frame arrays -- microseconds per
+    second of audio -- keeps the events that START inside its own frames, and ``gather_note_events`` puts the list
+    together (NCCL over NVLink on a GPU box).  The list equals the single-GPU one by construction.
     """
     if mode not in ("exact", "windowed"):
         raise ValueError("mode must be 'exact' or 'windowed'")
@@ -231,6 +274,8 @@ def analyze_long_clip(y, *, sr: float, hop_length: int = 512, fmin: Optional[flo
             # coupling 2, approximate: decode own frames + burn-in margin, keep the interior
             dec = backend.decode(feat["cand_bin"], feat["cand_prob"], feat["cand_count"], feat["voiced_prob"])
             own["f0"], own["voiced_flag"] = dec["f0"][a:b], dec["voiced_flag"][a:b]
+            if "states" in dec:
+                own["states"] = dec["states"][a:b]
         else:
             for k in ("cand_bin", "cand_prob", "cand_count"):
                 own[k] = feat[k][a:b]
@@ -241,11 +286,22 @@ def analyze_long_clip(y, *, sr: float, hop_length: int = 512, fmin: Optional[flo
         # coupling 2, exact: the gathered sparse observations are decoded as the single chain they are
         dec = backend.decode(full.pop("cand_bin"), full.pop("cand_prob"), full.pop("cand_count"), full["voiced_probs"])
         full["f0"], full["voiced_flag"] = dec["f0"], dec["voiced_flag"]
-    return {
+        if "states" in dec:
+            full["states"] = dec["states"]
+    res = {
         "rake_mask": full["rake_mask"].cpu().numpy().astype(bool), "f0": full["f0"].cpu().numpy(),
         "voiced_flag": full["voiced_flag"].cpu().numpy().astype(bool), "voiced_probs": full["voiced_probs"].cpu().numpy(),
         "rms": full["rms"].cpu().numpy(),
     }
+    if "states" in full:
+        res["states"] = full["states"].cpu().numpy()
+    if return_events:
+        ev = backend.note_events(res, **(event_kwargs or {}))
+        lo, hi = (mine[0].own_lo, mine[-1].own_hi) if mine else (0, 0)
+        keep = (ev["start"] >= lo) & (ev["start"] < hi)
+        res["events_local"] = int(keep.sum())
+        res["events"] = gather_note_events(ev[keep], group=group, dtype=ev.dtype)
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -263,5 +319,5 @@ def analyze_clips_sharded(load_clips: Callable[[Sequence[int]], torch.Tensor], n
     y = load_clips(list(mine))
     res = batch.analyze_batch(y, sr=sr, **analyze_kwargs) if len(mine) else {}
     res["clip_indices"] = list(mine)
-    res["clips_per_rank"] = gather_counts(len(mine), device=y.device if len(mine) else None, group=group)
+    res["clips_per_rank"] = gather_counts(len(mine), group=group)   # the device the backend needs, also on a rank without clips
     return res

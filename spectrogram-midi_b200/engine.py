@@ -17,19 +17,24 @@ from .vision import detect_rake_patterns
 from .worker import _pyin_worker  # noqa: F401  (kept importable from here like aegis_engine.py:14)
 
 
-def _as_audio(source, sr, start_time=0, end_time=None):
-    """A numpy array is taken as audio already at ``sr``; a str/path goes through ``librosa_compat.load``."""
+def _as_audio(source, sr, start_time=0, end_time=None, res_type=None):
+    """A numpy array is taken as audio already at ``sr``; a str/path goes through ``librosa_compat.load`` (which warns
+    when it has to convert the rate without an explicit ``res_type``: the reference would use soxr_hq there)."""
     if isinstance(source, (str, bytes)) or hasattr(source, "__fspath__"):
         duration = (end_time - start_time) if end_time else None
-        y, _ = librosa.load(source, sr=sr, offset=start_time, duration=duration)
+        y, _ = librosa.load(source, sr=sr, offset=start_time, duration=duration, res_type=res_type)
         return y
     y = np.asarray(source, dtype=np.float32)
-    s = int(round(start_time * sr))
-    e = None if not end_time else int(round(end_time * sr))
+    s = int(start_time * sr)
+    e = None if not end_time else s + int((end_time - start_time) * sr)
     return np.ascontiguousarray(y[s:e])
 
 
 class AegisEngine:
+    #: how files at another rate are converted to ``sample_rate``: ``None`` = warn (the reference's librosa.load uses
+    #: soxr_hq, this path 'polyphase'), ``'polyphase'`` = convert silently (set it on both sides to compare like with like)
+    res_type = None
+
     def __init__(self, sample_rate=44100, hop_length=512, n_fft=2048):
         self.sr = sample_rate
         self.hop_length = hop_length
@@ -37,7 +42,7 @@ class AegisEngine:
 
     # -- aegis_engine.py:22-27
     def load_audio(self, file_path, start_time=0, end_time=None):
-        y = _as_audio(file_path, self.sr, start_time, end_time)
+        y = _as_audio(file_path, self.sr, start_time, end_time, self.res_type)
         if len(y) == 0:
             return y, np.zeros((128, 0), dtype=np.float32)
         S = librosa.feature.melspectrogram(y=y, sr=self.sr, n_fft=self.n_fft, hop_length=self.hop_length)
@@ -57,7 +62,7 @@ class AegisEngine:
         """Perception phase.  ``output_mid`` is ignored exactly as in the reference (:41-75 never use it)."""
         start_time, end_time = kwargs.get("start_time", 0), kwargs.get("end_time", None)
         rake_sensitivity = kwargs.get("rake_sensitivity", 0.6)
-        y = _as_audio(input_wav, self.sr, start_time, end_time)
+        y = _as_audio(input_wav, self.sr, start_time, end_time, self.res_type)
         if len(y) == 0:
             return None
         # one upload, every kernel on the device, one download (turbo_mode needs no special casing:
@@ -111,13 +116,17 @@ class AegisEngine:
 class AegisFinancialEngine:
     """Perception methods of ``aegis_engine_financial.py:36-71`` (sr defaults to 22 050 there)."""
 
+    res_type = None   # see AegisEngine.res_type
+
     def __init__(self, sample_rate=22050, hop_length=512, n_fft=2048):
         self.sr = sample_rate
         self.hop_length = hop_length
         self.n_fft = n_fft
 
     def load_audio(self, file_path, start_time=0, end_time=None):
-        return AegisEngine(self.sr, self.hop_length, self.n_fft).load_audio(file_path, start_time, end_time)
+        eng = AegisEngine(self.sr, self.hop_length, self.n_fft)
+        eng.res_type = self.res_type
+        return eng.load_audio(file_path, start_time, end_time)
 
     def detect_rake_patterns(self, S_dB, sensitivity=0.6):
         return detect_rake_patterns(S_dB, self.hop_length, self.sr, sensitivity)
@@ -130,7 +139,7 @@ class AegisFinancialEngine:
         """Arrays ``audio_to_midi_financial`` hands to its note logic (:105-160): rake mask, pYIN with NaN
         f0, RMS, S_dB, plus the consensus trend of ``analyze_pitch_financial`` (financial_analysis.py:386-391).
         ``use_guitar_filters`` (default True, :128) applies ``apply_guitar_filters`` as :132-147 do."""
-        y = _as_audio(input_wav, self.sr, kwargs.get("start_time", 0), kwargs.get("end_time", None))
+        y = _as_audio(input_wav, self.sr, kwargs.get("start_time", 0), kwargs.get("end_time", None), self.res_type)
         if len(y) == 0:
             return None
         yd = torch.from_numpy(y).to(librosa._device())[None]

@@ -213,12 +213,14 @@ onset = types.SimpleNamespace(onset_strength=onset_strength, onset_detect=onset_
 util = types.SimpleNamespace(softmask=_softmask)
 
 
-def resample(y, *, orig_sr, target_sr, res_type="polyphase", fix=True, scale=False, axis=-1, **kwargs):
+def resample(y, *, orig_sr, target_sr, res_type="soxr_hq", fix=True, scale=False, axis=-1, **kwargs):
     """``librosa.resample`` for ``res_type='polyphase'`` (= ``scipy.signal.resample_poly``) on the GPU (kernel K9),
-    bit-identical to it for float32 input.  librosa's default ``soxr_hq`` lives in libsoxr, which this image does not
-    have and whose arithmetic cannot be pinned: any other ``res_type`` raises."""
+    bit-identical to it for float32 input.  The default is librosa's (``'soxr_hq'``, libsoxr), which this image does not
+    have and whose arithmetic cannot be pinned: it and every other ``res_type`` raise, so a caller must ask for
+    ``'polyphase'`` by name -- nothing is substituted silently."""
     if res_type != "polyphase":
-        raise NotImplementedError(f"res_type={res_type!r}: only 'polyphase' (scipy.signal.resample_poly) is built on the B200 path")
+        raise NotImplementedError(f"res_type={res_type!r}: only 'polyphase' (scipy.signal.resample_poly) is built on the B200 path; "
+                                  "pass res_type='polyphase' explicitly")
     y = np.asarray(y)
     if y.ndim != 1 or axis not in (-1, 0):
         raise NotImplementedError("mono signals only")
@@ -237,19 +239,38 @@ def resample(y, *, orig_sr, target_sr, res_type="polyphase", fix=True, scale=Fal
     return np.asarray(y_hat, dtype=y.dtype if np.issubdtype(y.dtype, np.floating) else np.float32)
 
 
-def load(path, *, sr=22050, mono=True, offset=0.0, duration=None, res_type="polyphase"):
+class ResampleDivergenceWarning(UserWarning):
+    """The file's sample rate differs from the requested one and no ``res_type`` was given: the reference's
+    ``librosa.load(file, sr=...)`` would convert with libsoxr's ``soxr_hq``, this path converts with ``'polyphase'``
+    (``scipy.signal.resample_poly``).  The samples -- and everything derived from them -- differ from the reference's."""
+
+
+def load(path, *, sr=22050, mono=True, offset=0.0, duration=None, res_type=None):
     """``librosa.load`` for RIFF WAV files (read with the standard library): PCM -> float32, channel mix-down and --
     when the file's rate differs from ``sr`` -- rate conversion.  16-bit files that need converting go to the GPU as
-    int16 and are scaled, mixed and resampled there in one pass (K9, ``res_type='polyphase'`` only, see ``resample``).
+    int16 and are scaled, mixed and resampled there in one pass (K9).
+
+    Rate conversion: librosa's default ``res_type`` is ``'soxr_hq'`` (libsoxr), which is not in this image and whose
+    arithmetic cannot be restated; only ``'polyphase'`` is built.  ``res_type='polyphase'`` converts silently and
+    bit-identically to librosa with that argument; any other explicit ``res_type`` raises ``NotImplementedError``; with
+    no ``res_type`` (what the reference's call sites do, aegis_engine.py:24, aegis_engine_financial.py:45) a conversion
+    that is actually needed warns with ``ResampleDivergenceWarning`` and uses ``'polyphase'`` -- never silently.
+    ``offset`` / ``duration`` truncate to whole source frames as librosa does (``int(offset * sr_native)``).
     """
+    import warnings
     import wave
 
     with wave.open(path, "rb") as w:
         file_sr, n_ch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
         raw = w.readframes(n)
-    start = int(round(offset * file_sr))
-    stop = None if duration is None else start + int(round(duration * file_sr))
+    start = int(offset * file_sr)
+    stop = None if duration is None else start + int(duration * file_sr)
     need_resample = sr is not None and int(sr) != file_sr
+    if need_resample and res_type is None:
+        warnings.warn(f"{path}: {file_sr} Hz -> {sr} Hz converted with res_type='polyphase'; the reference's librosa.load "
+                      "default is 'soxr_hq' (libsoxr, not available here): samples differ from the reference's. Pass "
+                      "res_type='polyphase' to both to compare like with like.", ResampleDivergenceWarning, stacklevel=2)
+        res_type = "polyphase"
     if need_resample and res_type != "polyphase":
         raise NotImplementedError(f"file is {file_sr} Hz, engine wants {sr} Hz and res_type={res_type!r}: only 'polyphase' is built")
     if need_resample and mono and width == 2:

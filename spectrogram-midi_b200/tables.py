@@ -209,6 +209,20 @@ class PyinConfig:
     log_init_unvoiced: float
     log_tiny: float
 
+    @functools.cached_property
+    def cache_key(self) -> tuple:
+        """Identifies every device table derived from this configuration: all scalar parameters plus a digest of the
+        table bytes (beta / Boltzmann / HMM parameters change the tables without changing sr, hop, fmin or fmax)."""
+        import hashlib
+
+        h = hashlib.blake2b(digest_size=16)
+        for a in (self.thresholds, self.beta_probs, self.beta_cumsum, self.boltz_fact, self.boltz_exp, self.freqs,
+                  self.lt_variants, self.row_variant):
+            h.update(np.ascontiguousarray(a).tobytes())
+        return (self.sr, self.hop_length, self.frame_length, self.fmin, self.fmax, self.min_period, self.max_period,
+                self.n_pitch_bins, self.bins_per_semitone, self.n_thresholds, self.half_width, self.max_troughs,
+                self.no_trough_prob, self.n_interior_variants, h.hexdigest())
+
 
 def _transition_local_triangle(n_states: int, width: int) -> np.ndarray:
     """``librosa.sequence.transition_local(n, width, window='triangle', wrap=False)``."""

@@ -111,7 +111,25 @@ class OracleBackend:
         f0 = self.cfg.freqs[st % nb].copy()
         voiced = st < nb
         f0[~voiced] = np.nan
-        return {"f0": torch.from_numpy(f0), "voiced_flag": torch.from_numpy(voiced.astype(np.uint8))}
+        return {"f0": torch.from_numpy(f0), "voiced_flag": torch.from_numpy(voiced.astype(np.uint8)),
+                "states": torch.from_numpy(st.astype(np.int16))}
+
+    def note_events(self, res, **kwargs):
+        """the reference's v1 logic filter (oracle restatement) -> the 40-byte records kernel K7 writes"""
+        return _event_records(R.get_midi_events(res["rake_mask"], np.nan_to_num(res["f0"]), res["voiced_flag"], res["voiced_probs"],
+                                                res["rms"], SR, HOP, kwargs.get("confidence_threshold", 0.7)))
+
+
+def _event_records(ev):
+    import warnings  # noqa: F401
+
+    rec = np.zeros(len(ev), P.core.NOTE_EVENT_DTYPE)
+    for i, e in enumerate(ev):
+        rec[i]["note"], rec[i]["start"], rec[i]["end"], rec[i]["velocity"] = e["note"], e["start"], e["end"], e["velocity"]
+        rec[i]["rms_energy"], rec[i]["track"] = e["rms_energy"], e["track"] == "main"
+        rec[i]["technique"] = P.core.TECHNIQUES.index(e.get("technique"))
+        rec[i]["confidence"], rec[i]["slope"] = e["confidence"], e.get("slope", 0.0)
+    return rec
 
 
 def _worker(rank, world, port, y, out_dir):
@@ -127,9 +145,17 @@ def _worker(rank, world, port, y, out_dir):
         allev = D.gather_note_events(ev)
         assert len(allev) == sum(r + 1 for r in range(world)) and list(allev["note"][:1]) == [40]
         assert D.gather_counts(10 + rank) == [10 + r for r in range(world)]
+        assert D.collective_device() is None   # gloo: host tensors
+        # by-clip sharding with fewer clips than ranks: a rank without clips still takes part in the count gather
+        empty = D.analyze_clips_sharded(lambda idx: torch.zeros((0, 8)), 0, sr=SR)
+        assert empty["clips_per_rank"] == [0] * world and empty["clip_indices"] == []
         res = {}
         for mode in ("exact", "windowed"):
-            res[mode] = D.analyze_long_clip(y, sr=SR, hop_length=HOP, mode=mode, burn_seconds=1.5, backend=OracleBackend())
+            res[mode] = D.analyze_long_clip(y, sr=SR, hop_length=HOP, mode=mode, burn_seconds=1.5, backend=OracleBackend(),
+                                            return_events=(mode == "exact"))
+        ev = res["exact"].pop("events")
+        res["exact"]["events_bytes"] = ev.view(np.uint8)
+        res["exact"]["events_local"] = np.array([res["exact"]["events_local"]])
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **{f"{m}/{k}": v for m, r in res.items() for k, v in r.items()})
     finally:
         dist.destroy_process_group()
@@ -148,6 +174,7 @@ def test_long_clip_on_two_ranks_equals_the_serial_result(tmp_path):
     f0, vf, vp = L.pyin(y, fmin=E2, fmax=C6, sr=SR, hop_length=HOP)
     rake = R.detect_rake_patterns(L.load_audio_features(y, SR), HOP, SR, 0.6)
     rms = L.rms(y)[0]
+    local_counts = []
     for rank in range(world):
         z = np.load(os.path.join(str(tmp_path), f"rank{rank}.npz"))
         # exact mode: identical to the serial decode, on every rank
@@ -156,11 +183,19 @@ def test_long_clip_on_two_ranks_equals_the_serial_result(tmp_path):
         np.testing.assert_array_equal(z["exact/voiced_probs"], vp)
         np.testing.assert_array_equal(z["exact/rake_mask"], rake)
         np.testing.assert_allclose(z["exact/rms"], rms, rtol=1e-6)
+        # the gathered note events (each rank contributed the events that start in its own frames) are the serial list
+        serial = {k.split("/")[1]: z[k] for k in z.files if k.startswith("exact/")}
+        want = _event_records(R.get_midi_events(serial["rake_mask"], np.nan_to_num(serial["f0"]), serial["voiced_flag"],
+                                                serial["voiced_probs"], serial["rms"], SR, HOP, 0.7))
+        got = z["exact/events_bytes"].view(P.core.NOTE_EVENT_DTYPE)
+        assert len(got) == len(want) > 0 and got.tobytes() == want.tobytes()
+        local_counts.append(int(z["exact/events_local"][0]))
         # windowed mode: frame-local outputs identical, decode equal once the paths have coalesced
         np.testing.assert_array_equal(z["windowed/rake_mask"], rake)
         np.testing.assert_array_equal(z["windowed/voiced_probs"], vp)
         assert (z["windowed/voiced_flag"] == vf).mean() >= 0.99
         assert len(z["windowed/f0"]) == len(f0)
+    assert sum(local_counts) == len(got) and min(local_counts) >= 0   # a partition of the list, contributed by both ranks
 
 
 def test_single_process_path_needs_no_group():

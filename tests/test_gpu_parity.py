@@ -408,6 +408,21 @@ def test_pyin_random_clips_no_worse_than_reference_rounding(dev, seed, dur):
     assert (cents <= 1.0).mean() >= 0.99
 
 
+def test_pyin_tables_are_not_aliased_across_hmm_parameters(dev):
+    """the device-table cache was keyed on (sr, hop, fmin, fmax) only.  Two calls in one process that differ in
+    switch_prob / resolution / beta_parameters must each see their own tables (a stale row_variant with another
+    n_pitch_bins was an out-of-bounds read), and each must still equal the oracle."""
+    y, sr = SIGNALS["track22050"]()
+    y = y[: sr * 4]
+    yd = _dev(y, dev)
+    for kw in ({}, {"switch_prob": 0.05}, {"resolution": 0.2}, {"beta_parameters": (3, 12)}, {}):
+        got = P.core.pyin_batch(yd, sr=float(sr), fmin=E2, fmax=C6, **kw)
+        f0, vf, vp = L.pyin(y, fmin=E2, fmax=C6, sr=sr, hop_length=512, **kw)
+        np.testing.assert_array_equal(got["voiced_flag"][0].cpu().numpy().astype(bool), vf, err_msg=str(kw))
+        g = got["f0"][0].cpu().numpy()
+        assert (np.abs(1200 * np.log2(g[vf] / f0[vf])) <= 1.0).all(), kw
+
+
 def test_pyin_batch_equals_single_and_handles_silence(dev):
     clips = corpus.clip_batch(3, 4.0, 22050, first_seed=40)
     clips[1] = 0.0
@@ -462,6 +477,18 @@ def test_filter_classes_mirror_reference_api(dev, golden):
         FinancialPitchAnalyzer().simple_moving_average(np.ones(4), window=5)  # the reference raises here too
     c, conf = multi_filter_consensus(golden["filt/gappy/f0"], filters=[])
     assert (conf == 1).all()
+    # subsets of the filters vote through the kernel's consensus_mask (no eager-torch path): numpy on the golden rows
+    import warnings
+    for subset in (["kalman", "holt"], ["savgol"], ["holt", "savgol"]):
+        for n in ("gappy", "onevalid", "long"):
+            f0 = golden[f"filt/{n}/f0"]
+            rows = np.array([golden[f"filt/{n}/{f}"] for f in ("savgol", "kalman", "holt") if f in subset])
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want_c, want_conf = np.nanmedian(rows, axis=0), 1.0 / (1.0 + np.nanstd(rows, axis=0))
+            c, conf = multi_filter_consensus(f0, filters=subset)
+            np.testing.assert_allclose(c, want_c, rtol=1e-12, atol=1e-9, err_msg=f"{subset} {n}")
+            np.testing.assert_allclose(conf, want_conf, rtol=1e-9, atol=1e-9, err_msg=f"{subset} {n}")
 
 
 # ---------------------------------------------------------------------------------- K7 note events
@@ -793,12 +820,19 @@ def test_pcm_ingest_and_load(dev, tmp_path):
         w.setsampwidth(2)
         w.setframerate(44100)
         w.writeframes(pcm.tobytes())
-    y, sr = lib.load(path, sr=22050)
+    y, sr = lib.load(path, sr=22050, res_type="polyphase")
     assert sr == 22050 and y.dtype == np.float32
     np.testing.assert_array_equal(y, ref)
-    y_off, _ = lib.load(path, sr=22050, offset=0.1, duration=0.25)
-    a = int(round(0.1 * 44100))
-    np.testing.assert_array_equal(y_off, scipy.signal.resample_poly(mono[a:a + int(round(0.25 * 44100))], 1, 2))
+    # no res_type: the reference's librosa.load would use soxr_hq; the substitution must be announced, never silent
+    with pytest.warns(lib.ResampleDivergenceWarning):
+        y_warn, _ = lib.load(path, sr=22050)
+    np.testing.assert_array_equal(y_warn, ref)
+    y_off, _ = lib.load(path, sr=22050, offset=0.1, duration=0.25, res_type="polyphase")
+    a = int(0.1 * 44100)   # librosa truncates offset / duration to whole source frames
+    np.testing.assert_array_equal(y_off, scipy.signal.resample_poly(mono[a:a + int(0.25 * 44100)], 1, 2))
+    y_off2, _ = lib.load(path, sr=None, offset=0.30001, duration=0.10001)
+    a2 = int(0.30001 * 44100)
+    np.testing.assert_array_equal(y_off2, mono[a2:a2 + int(0.10001 * 44100)])
     y_native, sr_native = lib.load(path, sr=None)
     assert sr_native == 44100
     np.testing.assert_array_equal(y_native, mono)
@@ -806,8 +840,10 @@ def test_pcm_ingest_and_load(dev, tmp_path):
         lib.load(path, sr=22050, res_type="soxr_hq")
     with pytest.raises(NotImplementedError):
         lib.resample(mono, orig_sr=44100, target_sr=22050, res_type="kaiser_best")
-    np.testing.assert_array_equal(lib.resample(mono, orig_sr=44100, target_sr=22050), ref)
-    assert lib.resample(mono, orig_sr=22050, target_sr=22050) is mono
+    with pytest.raises(NotImplementedError):
+        lib.resample(mono, orig_sr=44100, target_sr=22050)     # librosa's default res_type is soxr_hq: refused, not substituted
+    np.testing.assert_array_equal(lib.resample(mono, orig_sr=44100, target_sr=22050, res_type="polyphase"), ref)
+    assert lib.resample(mono, orig_sr=22050, target_sr=22050, res_type="polyphase") is mono
     with pytest.raises(ValueError):
         P.core.resample_poly(torch.zeros((1, 8), device=dev), 44100.5, 22050)
 
@@ -997,6 +1033,14 @@ def test_long_clip_windows_equal_the_full_clip_result(dev, sr, mode):
     if mode == "exact":
         np.testing.assert_array_equal(res["voiced_flag"], ref["voiced_flag"])
         np.testing.assert_array_equal(np.nan_to_num(res["f0"]), ref["f0"])
+        # the note events assembled by the event gather (here: one rank, five windows) == the engine's own list
+        res2 = D.analyze_long_clip(y, sr=sr, mode="exact", windows_per_rank=5, return_events=True)
+        eng = P.AegisEngine(sample_rate=sr)
+        want = eng.note_events(ref)
+        got = res2["events"]
+        assert res2["events_local"] == len(got) == len(want) > 0
+        assert [(int(r["note"]), int(r["start"]), int(r["end"]), int(r["velocity"]), bool(r["track"])) for r in got] == \
+            [(e["note"], e["start"], e["end"], e["velocity"], e["track"] == "main") for e in want]
     else:
         assert (res["voiced_flag"] == ref["voiced_flag"]).mean() >= 0.99
 

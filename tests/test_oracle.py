@@ -285,3 +285,24 @@ def test_resampler_kernel_arithmetic_model_equals_scipy_bitwise():
             out[m] = acc
         np.testing.assert_array_equal(out, scipy.signal.resample_poly(y, up, down), err_msg=f"{orig}->{target}")
 
+
+
+def test_uncalled_reference_filters_match_golden(golden):
+    """atr_filter / ichimoku_baseline / stochastic_oscillator (financial_filters.py:144-249; defined by the reference,
+    called by nothing in it) are host numpy in the drop-in class: bit-equal to the real file's outputs."""
+    import warnings
+
+    import spectrogram_midi_b200  # noqa: F401
+    from spectrogram_midi_b200.financial_filters import FinancialNoiseFilters as F
+
+    for name in _cases(golden, "filt"):
+        f0 = golden[f"filt/{name}/f0"]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            at, am = F.atr_filter(f0.copy())
+            ich = F.ichimoku_baseline(f0.copy())
+            sto = F.stochastic_oscillator(f0.copy())
+        np.testing.assert_array_equal(at, golden[f"filt/{name}/atr"], err_msg=name)
+        np.testing.assert_array_equal(am, golden[f"filt/{name}/atr_mask"], err_msg=name)
+        np.testing.assert_array_equal(ich, golden[f"filt/{name}/ichimoku"], err_msg=name)
+        np.testing.assert_array_equal(sto, golden[f"filt/{name}/stochastic"], err_msg=name)
