@@ -6,13 +6,21 @@
 Workload at every N (weak scaling, sharded by clip, no data-path collective): BASELINE.json
 configs[1] -- a batch of 1,024 synthetic 30 s clips at 22 050 Hz per GPU; one step = one pass of
 STFT |X| + mel dB onset strength + onset peak picking + frame RMS over the batch.
-`value`  : audio-seconds analysed per second with the batch resident in HBM (CUDA events).
-`e2e`    : the same through the host-buffer plugin call (pinned host audio -> H2D -> kernels -> D2H of
-           RMS / onset envelope / onset flags), copies inside the timed region.
+`value`   : audio-seconds analysed per second with the batch resident in HBM (CUDA events).
+`e2e`     : the same through the host-buffer plugin call: pinned 16-bit PCM host buffers (the payload of a WAV file) ->
+            H2D -> K9 ingest -> kernels -> D2H of RMS / onset envelope / onset flags, copies inside the timed region;
+            beside it the copy-only time of the same bytes (the ceiling of any host-fed path) and `e2e_f32` (float32 buffers).
 `roofline`: the STFT kernel (dominant), algorithmic bytes 4*N + 4*1025*T per clip over its own
-           CUDA-event time, against MEASURED_PEAKS.json's HBM copy bandwidth.
+            CUDA-event time, against MEASURED_PEAKS.json's HBM copy bandwidth; `traffic` from the committed ncu capture,
+            null when the kernel sources changed since it was taken.
+`transcribe`: BASELINE cfg3 + the v1 logic filter on the same clips -- mel dB + rake mask + pYIN + RMS + note events:
+            device-resident value, per-kernel times, end to end from PCM host buffers, its own CPU baseline, and the
+            issue-slot utilisation of the Viterbi kernel (latency bound: no HBM roofline applies).
 `cpu_baseline` / `--impl reference`: the CPU oracle (port of the reference's librosa path; librosa
-           itself is not installable here) on the box's host cores, on a bounded sample of the same clips.
+            itself is not installable here) on the box's host cores: one single-threaded worker process per core, by
+            clip, on a bounded sample of the same clips.
+`aux.long_clip` (N > 1): BASELINE cfg4, one hour at 44.1 kHz over the N ranks with the NCCL event gather, compared by hash
+            with one rank alone.
 Prints exactly ONE JSON line on stdout.
 """
 from __future__ import annotations
@@ -56,6 +64,26 @@ def _cpu_spectral_one(y):
     peaks = L.onset_detect(onset_envelope=env, sr=SR)
     r = L.rms(y)
     return float(S[3, 3]) + float(env.sum()) + len(peaks) + float(r.sum())
+
+
+def _cpu_transcribe_one(y):
+    """The reference's v1 pipeline for one clip with the CPU oracle: mel dB + rake mask + pYIN E2..C6 + RMS +
+    get_midi_events (aegis_engine.py:41-96)."""
+    import warnings
+
+    import numpy as np
+
+    from oracle import librosa_ref as L
+    from oracle import reference_files as R
+
+    S_dB = L.load_audio_features(y, SR)
+    mask = R.detect_rake_patterns(S_dB, HOP, SR, 0.6)
+    f0, vf, vp = L.pyin(y, fmin=L.note_to_hz("E2"), fmax=L.note_to_hz("C6"), sr=SR, hop_length=HOP)
+    rms = L.rms(y)[0]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ev = R.get_midi_events(mask, np.nan_to_num(f0), vf, vp, rms, SR, HOP, 0.70)
+    return len(ev)
 
 
 _THREAD_VARS = ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS")
@@ -292,6 +320,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _hash_sources(names):
+    import hashlib
+
+    h = hashlib.sha256()
+    for n in names:
+        with open(os.path.join(ROOT, "spectrogram-midi_b200", "csrc", n), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def committed_capture(path, sources):
+    """A number that can only come from a profiler (DRAM bytes, issue utilisation) is read from the committed summary of
+    the ncu capture -- but only when that capture was taken from the kernel sources as they are now (the summary
+    records their hash); otherwise None and the reason."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", path)))
+    except (OSError, ValueError):
+        return None, f"profiles/{path} missing"
+    if rec.get("source_sha16") != _hash_sources(sources):
+        return None, f"profiles/{path} is stale: kernel sources changed since the capture"
+    return rec, None
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -325,6 +376,30 @@ def run_gpu(args):
     torch.cuda.synchronize()
     log(f"[rank {rank}] corpus: {N_CLIPS} clips x {CLIP_SECONDS:.0f} s rendered in {time.perf_counter() - t0:.1f} s")
 
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def wall(fn, reps):
+        barrier()
+        t = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        barrier()
+        return (time.perf_counter() - t) / reps
+
+    audio_s_per_step = world * N_CLIPS * CLIP_SECONDS
+
+    # ================================================================================================================
+    # headline (BASELINE cfg2): STFT |X| + onset strength / peaks + RMS, batch resident in HBM
+    # ================================================================================================================
     mag = core.alloc_frames((N_CLIPS, 1025), T, dev)  # rows on 32-byte sector boundaries
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stft_ms = []
@@ -340,12 +415,6 @@ def run_gpu(args):
         pk = core.onset_peaks(post["onset_env"], post["env_minmax"], sr=SR, hop_length=HOP)
         return feat, post, pk
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -356,49 +425,110 @@ def run_gpu(args):
     start.record()
     for _ in range(args.steps):
         step(timed=True)
-        launches += 4  # stft_fused, mel_post, peak_candidates, peak_select
+        launches += 4  # stft_fused, mel_post (onset_flux4), peak_candidates, peak_select
         ev_b.synchronize()
         stft_ms.append(ev_a.elapsed_time(ev_b))
     stop.record()
     barrier()
     elapsed_ms = start.elapsed_time(stop)
-
-    # ---- end to end through the host-buffer plugin call
-    pipe = batch.HostPipeline(N_CLIPS, n_samples, sr=SR, hop_length=HOP, device=dev, chunk_clips=128)
-    y_host = torch.empty((N_CLIPS, n_samples), dtype=torch.float32, pin_memory=True)
-    y_host.copy_(y)
-    for _ in range(2):
-        pipe.run(y_host)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        res = pipe.run(y_host)
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
     clocks = sampler.stop()
 
-    # ---- the same call fed with 16-bit PCM (what a WAV file holds): half the PCIe bytes, K9 converts on the device.
-    # A secondary number: the samples are the float clips rounded to int16, so results differ by that quantisation.
-    h2d_bytes, d2h_bytes = int(pipe.h2d_bytes), int(pipe.d2h_bytes)
-    del pipe, y_host
-    pipe16 = batch.HostPipeline(N_CLIPS, n_samples, sr=SR, hop_length=HOP, device=dev, chunk_clips=128, pcm_rate=SR)
+    # ================================================================================================================
+    # end to end through the host-buffer plugin call (cfg2).  PRIMARY: 16-bit PCM host buffers -- what a WAV file
+    # holds; the ingest kernel K9 scales to float on the device.  SECONDARY: float32 host buffers.
+    # ================================================================================================================
+    e2e_steps = max(2, min(args.steps, 4))
     pcm_host = torch.empty((N_CLIPS, n_samples), dtype=torch.int16, pin_memory=True)
     pcm_host.copy_((y * 32767.0).round().to(torch.int16))
+    pipe16 = batch.HostPipeline(N_CLIPS, n_samples, sr=SR, hop_length=HOP, device=dev, chunk_clips=128, pcm_rate=SR)
     for _ in range(2):
         pipe16.run(pcm_host)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        pipe16.run(pcm_host)
-    barrier()
-    pcm_s = (time.perf_counter() - t0) / e2e_steps
+    pcm_s = wall(lambda: pipe16.run(pcm_host), e2e_steps)
+    pcm_bytes = (int(pipe16.h2d_bytes), int(pipe16.d2h_bytes))
+    # the ceiling of that path: the same chunks copied host -> device and nothing else (one cudaMemcpyAsync per chunk)
+    sink = torch.empty((128, n_samples), dtype=torch.int16, device=dev)
 
-    t = torch.tensor([elapsed_ms, e2e_s, pcm_s], dtype=torch.float64, device=dev)
+    def copy_only(src, buf):
+        for c0 in range(0, N_CLIPS, 128):
+            buf[: min(128, N_CLIPS - c0)].copy_(src[c0 : c0 + 128], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    copy_only(pcm_host, sink)
+    h2d16_s = wall(lambda: copy_only(pcm_host, sink), e2e_steps)
+    del pipe16, sink
+
+    y_host = torch.empty((N_CLIPS, n_samples), dtype=torch.float32, pin_memory=True)
+    y_host.copy_(y)
+    pipe = batch.HostPipeline(N_CLIPS, n_samples, sr=SR, hop_length=HOP, device=dev, chunk_clips=128)
+    for _ in range(2):
+        pipe.run(y_host)
+    e2e_s = wall(lambda: pipe.run(y_host), e2e_steps)
+    f32_bytes = (int(pipe.h2d_bytes), int(pipe.d2h_bytes))
+    sink32 = torch.empty((128, n_samples), dtype=torch.float32, device=dev)
+    copy_only(y_host, sink32)
+    h2d32_s = wall(lambda: copy_only(y_host, sink32), e2e_steps)
+    del pipe, y_host, sink32
+
+    # ================================================================================================================
+    # transcription (BASELINE cfg3 + the v1 logic filter): spectral + rake mask + pYIN E2..C6 + RMS + note events
+    # on the SAME 1024 clips per GPU: device-resident, per-kernel times, and end to end from PCM host buffers
+    # ================================================================================================================
+    tr = {}
+    if not args.no_pyin:
+        cfg = P.tables.pyin_config(float(SR), HOP, batch.E2, batch.C6)
+
+        def transcribe():
+            res = batch.analyze_batch(y, sr=SR, hop_length=HOP)
+            evs = batch.note_events_batch(res, sr=SR, hop_length=HOP)
+            return res, evs
+
+        for _ in range(2):
+            transcribe()
+        tr_steps = max(2, min(args.steps, 3))
+        barrier()
+        a = ev()
+        for _ in range(tr_steps):
+            res, evs = transcribe()
+        b = ev()
+        barrier()
+        tr_ms = a.elapsed_time(b) / tr_steps
+        n_events_mean = float(evs["n_events"].float().mean())
+        del res, evs
+        # per-kernel times of one step (CUDA events around each call; same calls analyze_batch makes)
+        marks = [ev()]
+        feat = core.stft_features(y, sr=SR, hop_length=HOP, want_mag=False, want_mel=True, want_rms=True); marks.append(ev())
+        post = core.mel_post(feat["mel"], feat["mel_max"], sr=SR, hop_length=HOP, want_sdb=False, want_rake=True, want_onset=False); marks.append(ev())
+        obs = core.yin_candidates(y, cfg); marks.append(ev())
+        dec = core.viterbi_decode(obs, cfg, N_CLIPS); marks.append(ev())
+        res = {"rake_mask": post["rake_mask"], "f0": dec["f0"], "voiced_flag": dec["voiced_flag"], "voiced_probs": obs["voiced_prob"],
+               "rms": feat["rms"], "states": dec["states"]}
+        evs = batch.note_events_batch(res, sr=SR, hop_length=HOP); marks.append(ev())
+        torch.cuda.synchronize()
+        names = ["K1 stft_fused (mel + rms, no |X| store)", "K4 mel_post (dB + rake mask)", "K2 yin", "K3 viterbi (forward + backtrace)", "K7 note events"]
+        stage_ms = {n: marks[i].elapsed_time(marks[i + 1]) for i, n in enumerate(names)}
+        del feat, post, obs, dec, res, evs
+        # end to end: PCM host buffers in, perception arrays + event records out
+        tp = batch.TranscribePipeline(N_CLIPS, n_samples, sr=SR, hop_length=HOP, device=dev, chunk_clips=128, pcm=True)
+        for _ in range(2):
+            tp.run(pcm_host)
+        tr_e2e_s = wall(lambda: tp.run(pcm_host), tr_steps)
+        tr_bytes = (int(tp.h2d_bytes), int(tp.d2h_bytes))
+        del tp
+        vit, why = committed_capture("r2_viterbi_issue.json", ["viterbi.cu"])
+        tr = {"ms": tr_ms, "e2e_s": tr_e2e_s, "stage_ms": stage_ms, "bytes": tr_bytes, "n_events_mean": n_events_mean,
+              "issue": vit, "issue_note": why}
+    del pcm_host
+
+    # ---- long clip (BASELINE cfg4) at N > 1: one hour at 44.1 kHz over the ranks, exact and windowed, against one rank alone
+    long_clip = None
+    if world > 1 and not args.no_long_clip:
+        long_clip = run_long_clip(args, P, core, dev, rank, world)
+
+    vals = [elapsed_ms, e2e_s, pcm_s, h2d16_s, h2d32_s, tr.get("ms", 0.0), tr.get("e2e_s", 0.0)]
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_s, pcm_s = float(t[0]), float(t[1]), float(t[2])
-    audio_s_per_step = world * N_CLIPS * CLIP_SECONDS
+    elapsed_ms, e2e_s, pcm_s, h2d16_s, h2d32_s, tr_ms_max, tr_e2e_max = [float(v) for v in t]
     value = audio_s_per_step * args.steps / (elapsed_ms / 1e3)
 
     # ---- roofline of the STFT kernel
@@ -410,51 +540,31 @@ def run_gpu(args):
     alg_bytes = N_CLIPS * (4 * n_samples + 4 * 1025 * T)
     stft_avg_ms = float(np.mean(stft_ms))
     achieved = alg_bytes / (stft_avg_ms / 1e3) / 1e9
+    # DRAM traffic of that kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full`
+    # capture of the same launch shape -- valid only for the kernel sources it was taken from (hash checked)
+    traffic, traffic_note = None, None
+    cap, why = committed_capture("r2_stft_traffic.json", ["stft_fused.cu", "rfft2048x2.cuh"])
+    if cap is not None and N_CLIPS == 1024:
+        traffic = float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"])
+    else:
+        traffic_note = why or "capture is for 1024 clips per launch"
 
-    # DRAM traffic of that kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum from the committed
-    # `ncu --set full` capture of the same launch shape (not re-measured here: no profiler inside a timed run)
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_stft_traffic.json")))
-        if N_CLIPS == 1024:
-            traffic = float(tr["dram_bytes_read"]) + float(tr["dram_bytes_write"])
-    except (OSError, KeyError, ValueError):
-        pass
-
-    aux = {}
-    if rank == 0 and not args.no_pyin:  # cfg3 on the same clips (not the headline; reported for context)
-        try:
-            sub = y[: min(N_CLIPS, 256)]
-            for _ in range(2):
-                core.pyin_batch(sub, sr=SR, fmin=batch.E2, fmax=batch.C6)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            core.pyin_batch(sub, sr=SR, fmin=batch.E2, fmax=batch.C6)
-            b.record()
-            b.synchronize()
-            aux["pyin_E2_C6_audio_s_per_s"] = sub.shape[0] * CLIP_SECONDS / (a.elapsed_time(b) / 1e3)
-            aux["pyin_clips"] = int(sub.shape[0])
-            # the whole perception phase of audio_to_midi (spectral + rake + pYIN + RMS + trend) on the same clips
-            for _ in range(2):
-                batch.analyze_batch(sub, sr=SR, with_onsets=True, with_trend=True)
-            torch.cuda.synchronize()
-            a.record()
-            batch.analyze_batch(sub, sr=SR, with_onsets=True, with_trend=True)
-            b.record()
-            b.synchronize()
-            aux["full_perception_audio_s_per_s"] = sub.shape[0] * CLIP_SECONDS / (a.elapsed_time(b) / 1e3)
-        except Exception as e:  # pragma: no cover
-            aux["pyin_error"] = str(e)[:200]
-
-    cpu = None
+    cpu = cpu_tr = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         pool = CpuPool(cores)                        # spawned, single-threaded workers (no fork of this CUDA process)
         rate = pooled_rate(pool, y[: 2 * cores].cpu().numpy())
-        n = int(min(N_CLIPS, max(cores, round(15.0 * rate))))   # ~15 s of wall with every core busy
+        n = int(min(N_CLIPS, max(cores, round(12.0 * rate))))   # ~12 s of wall with every core busy
         cpu = cpu_baseline_record(pool, y[:n].cpu().numpy(), f"first {n} clips of the batch ({n * CLIP_SECONDS:.0f} audio-s)")
         pool.close()
+        if tr:
+            pool = CpuPool(cores, _cpu_transcribe_one)
+            probe = y[:cores].cpu().numpy()
+            _, dt = pool.throughput(probe)           # warm (numba JIT in every worker), then one clip per worker
+            n = int(min(N_CLIPS, max(cores, round(15.0 * cores / dt))))
+            cpu_tr = cpu_baseline_record(pool, y[:n].cpu().numpy(), f"first {n} clips of the batch ({n * CLIP_SECONDS:.0f} audio-s), "
+                                         "spectral + rake mask + pYIN + RMS + get_midi_events", serial_clips=1)
+            pool.close()
 
     if rank == 0:
         line = {
@@ -466,21 +576,107 @@ def run_gpu(args):
                        "host_affinity": None if host_cpus is None else f"rank 0 pinned to the {len(host_cpus)} CPUs next to its GPU (NVML)",
                        "l2": "inputs (2.7 GB) and outputs (5.4 GB) per step exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "stft_fused_kernel", "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": stft_avg_ms,
-                         "peak_source": peak_src, "share_of_step": stft_avg_ms / (elapsed_ms / args.steps)},
+                         "traffic_note": traffic_note, "kernel": "stft_fused_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                         "ms_per_launch": stft_avg_ms, "peak_source": peak_src, "share_of_step": stft_avg_ms / (elapsed_ms / args.steps)},
             "cpu_baseline": cpu,
-            "e2e": {"value": audio_s_per_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_s * 1e3, "d2h": "rms + onset envelope + onset flags (|X| stays in HBM)"},
-            "e2e_pcm16": {"value": audio_s_per_step / pcm_s, "unit": UNIT, "h2d_bytes_per_step": int(pipe16.h2d_bytes),
-                          "d2h_bytes_per_step": int(pipe16.d2h_bytes), "ms_per_step": pcm_s * 1e3,
-                          "note": "secondary: same call with the clips as 16-bit PCM host buffers (a WAV payload); scaled to float on the GPU (K9)"},
+            "e2e": {"value": audio_s_per_step / pcm_s, "unit": UNIT, "h2d_bytes_per_step": pcm_bytes[0], "d2h_bytes_per_step": pcm_bytes[1],
+                    "ms_per_step": pcm_s * 1e3,
+                    "note": "PRIMARY end-to-end: the clips as 16-bit PCM host buffers (the payload of a WAV file), pinned; chunked H2D on "
+                            "two copy streams overlapped with the kernels; K9 scales to float on the device; D2H of rms + onset envelope "
+                            "+ onset flags (|X| stays in HBM)",
+                    "h2d_copy_only_ms": h2d16_s * 1e3, "h2d_copy_only_gbs": world * pcm_bytes[0] / h2d16_s / 1e9,
+                    "fraction_of_copy_ceiling": h2d16_s / pcm_s},
+            "e2e_f32": {"value": audio_s_per_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": f32_bytes[0], "d2h_bytes_per_step": f32_bytes[1],
+                        "ms_per_step": e2e_s * 1e3, "note": "secondary: the same call with float32 host buffers (twice the PCIe bytes)",
+                        "h2d_copy_only_ms": h2d32_s * 1e3, "h2d_copy_only_gbs": world * f32_bytes[0] / h2d32_s / 1e9,
+                        "fraction_of_copy_ceiling": h2d32_s / e2e_s},
             "gpu_launches": launches,
             "clocks": clocks,
-            "aux": aux,
         }
+        if tr:
+            st = tr["stage_ms"]
+            tot = sum(st.values())
+            issue = tr["issue"]
+            line["transcribe"] = {
+                "workload": "cfg3 + v1 logic filter on the same 1024 x 30 s clips per GPU: mel dB + rake mask + pYIN E2..C6 "
+                            "(441 bins / 882 states) + RMS + get_midi_events (aegis_engine.py:41-96)",
+                "value": audio_s_per_step / (tr_ms_max / 1e3), "unit": UNIT, "ms_per_step": tr_ms_max,
+                "kernel_ms": st, "kernel_share": {k: v / tot for k, v in st.items()},
+                "note_events_per_clip": tr["n_events_mean"],
+                "e2e": {"value": audio_s_per_step / tr_e2e_max, "unit": UNIT, "ms_per_step": tr_e2e_max * 1e3,
+                        "h2d_bytes_per_step": tr["bytes"][0], "d2h_bytes_per_step": tr["bytes"][1],
+                        "note": "16-bit PCM host buffers in; rake_mask, f0, voiced_flag, voiced_probs, rms and the note-event records out"},
+                "roofline": {"bound": "issue", "kernel": "viterbi_forward_kernel",
+                             "achieved": None if issue is None else issue["smsp_issue_active_pct"], "peak": 100.0, "unit": "% issue slots",
+                             "frac": None if issue is None else issue["smsp_issue_active_pct"] / 100.0,
+                             "source": "committed ncu capture profiles/r2_viterbi_issue.json (a profiler metric cannot be read inside a "
+                                       "timed run)" if issue is not None else tr["issue_note"],
+                             "ms_per_launch": st["K3 viterbi (forward + backtrace)"]},
+                "cpu_baseline": cpu_tr,
+            }
+        if long_clip is not None:
+            line["aux"] = {"long_clip": long_clip}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_long_clip(args, P, core, dev, rank, world):
+    """BASELINE cfg4: ONE 3600 s recording at 44.1 kHz analysed by all ranks in overlapping time windows
+    (distributed.analyze_long_clip): frame-local kernels per window, all_reduce(MAX) of the mel maximum, all-gather of the
+    sparse observations (exact) or of the decoded frames (windowed), and the note-event gather -- all NCCL.  Rank 0 then
+    analyses the clip alone and the results are compared by hash."""
+    import hashlib
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from spectrogram_midi_b200 import distributed as D
+
+    sr, seg_s = 44100, 30.0
+    n_seg = int(os.environ.get("AEGIS_BENCH_LONG_SEGMENTS", "120"))     # 120 x 30 s = one hour
+    plan = P.corpus.plan_events(n_seg, seg_s, sr, first_seed=7000)      # every rank renders the same recording
+    y = core.synth_events(n_seg, int(seg_s * sr), plan, dev).reshape(-1).cpu().numpy()
+    torch.cuda.synchronize()
+
+    def digest(res):
+        h = hashlib.sha256()
+        for k in ("rake_mask", "f0", "voiced_flag", "voiced_probs", "rms"):
+            h.update(np.ascontiguousarray(res[k]).tobytes())
+        if "events" in res:
+            h.update(np.ascontiguousarray(res["events"]).tobytes())
+        return h.hexdigest()[:16]
+
+    out = {"clip_seconds": n_seg * seg_s, "sr": sr, "n_samples": int(y.shape[0]), "ranks": world}
+    for mode in ("exact", "windowed"):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = D.analyze_long_clip(y, sr=sr, mode=mode, burn_seconds=2.0, return_events=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        counts = D.gather_counts(int(res["events_local"]))
+        out[mode] = {"wall_s": float(tt[0]), "audio_s_per_s": n_seg * seg_s / float(tt[0]), "sha16": digest(res),
+                     "events": int(len(res["events"])), "events_per_rank": counts, "frames": int(len(res["f0"]))}
+        if mode == "exact":
+            exact_res = res
+    # one rank alone (no collectives): the serial answer
+    if rank == 0:
+        t0 = time.perf_counter()
+        solo = D.analyze_long_clip(y, sr=sr, mode="exact", windows_per_rank=world, return_events=True, solo=True)
+        torch.cuda.synchronize()
+        out["one_rank"] = {"wall_s": time.perf_counter() - t0, "sha16": digest(solo), "events": int(len(solo["events"]))}
+        out["exact"]["equals_one_rank"] = out["exact"]["sha16"] == out["one_rank"]["sha16"]
+        both = exact_res["voiced_flag"] & solo["voiced_flag"]
+        out["exact"]["voiced_agreement"] = float((exact_res["voiced_flag"] == solo["voiced_flag"]).mean())
+        out["speedup_vs_one_rank"] = out["one_rank"]["wall_s"] / out["exact"]["wall_s"]
+        del both
+    dist.barrier()
+    return out
 
 
 def main():
@@ -490,7 +686,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-pyin", action="store_true", help="skip the auxiliary pYIN timing")
+    ap.add_argument("--no-pyin", action="store_true", help="skip the transcription (pYIN) record")
+    ap.add_argument("--no-long-clip", action="store_true", help="skip the one-hour clip record of N > 1 runs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

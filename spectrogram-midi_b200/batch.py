@@ -98,12 +98,13 @@ def note_events_batch(result: dict, *, sr: float, hop_length: int = 512, fmin: f
     ``analyze_batch`` result (v1 arrays: f0 with zeros).  The note numbers come from the Viterbi states through a
     table computed with the reference's expression ``int(round(hz_to_midi(f)))`` on the pYIN frequency grid."""
     cfg = tables.pyin_config(float(sr), hop_length, fmin, fmax)
-    lut = np.array([int(round(float(tables.hz_to_midi(f)))) for f in cfg.freqs], dtype=np.int16)
     dev = result["f0"].device
+    lut = core._dev_tensor(("note_lut",) + cfg.cache_key, dev,     # uploaded once per configuration and device
+                           lambda: np.array([int(round(float(tables.hz_to_midi(f)))) for f in cfg.freqs], dtype=np.int16))
     f0 = torch.nan_to_num(result["f0"], nan=0.0)
     return core.note_events(result["rake_mask"], f0, result["voiced_flag"], result["voiced_probs"], result["rms"],
                             sr=sr, hop_length=hop_length, confidence_threshold=confidence_threshold,
-                            pitch_index=result["states"], note_lut=torch.from_numpy(lut).to(dev), **kwargs)
+                            pitch_index=result["states"], note_lut=lut, **kwargs)
 
 
 def note_events_financial_batch(result: dict, *, sr: float, hop_length: int = 512, confidence_threshold=None, **kwargs) -> dict:
@@ -154,7 +155,7 @@ class HostPipeline:
     """
 
     def __init__(self, n_clips: int, n_samples: int, *, sr: float, hop_length: int = 512, device=None, chunk_clips: int = 128,
-                 pcm_rate: Optional[int] = None, pcm_channels: int = 1):
+                 pcm_rate: Optional[int] = None, pcm_channels: int = 1, copy_streams: int = 2):
         self.sr, self.hop = sr, hop_length
         self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.n_clips, self.n_samples = n_clips, n_samples
@@ -172,11 +173,12 @@ class HostPipeline:
             if -(-n_src * up // down) != n_samples:
                 raise ValueError(f"no source length at {pcm_rate} Hz resamples to exactly {n_samples} samples at {sr} Hz")
             self.in_shape, in_dtype = (n_clips, n_src * pcm_channels), torch.int16
-        self.inbuf = [torch.empty((self.chunk, self.in_shape[1]), dtype=in_dtype, device=self.dev) for _ in range(2)]
+        self.nbuf = max(2, copy_streams + 1)      # one chunk in the kernels, one per copy stream in flight
+        self.inbuf = [torch.empty((self.chunk, self.in_shape[1]), dtype=in_dtype, device=self.dev) for _ in range(self.nbuf)]
         self.mag = core.alloc_frames((self.chunk, core.N_BINS), self.T, self.dev)
-        self.copy_stream = torch.cuda.Stream(device=self.dev)
-        self.in_ready = [torch.cuda.Event() for _ in range(2)]
-        self.in_free = [torch.cuda.Event() for _ in range(2)]
+        self.copy_streams = [torch.cuda.Stream(device=self.dev) for _ in range(max(1, copy_streams))]
+        self.in_ready = [torch.cuda.Event() for _ in range(self.nbuf)]
+        self.in_free = [torch.cuda.Event() for _ in range(self.nbuf)]
         self.rms = torch.empty((n_clips, self.T), dtype=torch.float32, pin_memory=True)
         self.env = torch.empty((n_clips, self.T), dtype=torch.float32, pin_memory=True)
         self.peaks = torch.empty((n_clips, self.T), dtype=torch.uint8, pin_memory=True)
@@ -188,15 +190,24 @@ class HostPipeline:
             raise ValueError(f"expected a host {self.inbuf[0].dtype} tensor {self.in_shape}")
         main = torch.cuda.current_stream(self.dev)
         starts = list(range(0, self.n_clips, self.chunk))
-        for b in range(2):
+        for b in range(self.nbuf):
             self.in_free[b].record(main)
-        for i, c0 in enumerate(starts):
-            b = i & 1
+
+        def issue_copy(i):   # one cudaMemcpyAsync per chunk, on the chunk's copy stream
+            b, c0 = i % self.nbuf, starts[i]
             n = min(self.chunk, self.n_clips - c0)
-            with torch.cuda.stream(self.copy_stream):
-                self.copy_stream.wait_event(self.in_free[b])
+            cs = self.copy_streams[i % len(self.copy_streams)]
+            with torch.cuda.stream(cs):
+                cs.wait_event(self.in_free[b])
                 self.inbuf[b][:n].copy_(y_host[c0 : c0 + n], non_blocking=True)
-                self.in_ready[b].record(self.copy_stream)
+                self.in_ready[b].record(cs)
+
+        ahead = self.nbuf - 1
+        for i in range(min(ahead, len(starts))):
+            issue_copy(i)
+        for i, c0 in enumerate(starts):
+            b = i % self.nbuf
+            n = min(self.chunk, self.n_clips - c0)
             main.wait_event(self.in_ready[b])
             yb = self.inbuf[b][:n]
             if self.pcm_rate is not None:
@@ -207,8 +218,89 @@ class HostPipeline:
                                  want_rake=False, want_onset=True)
             pk = core.onset_peaks(post["onset_env"], post["env_minmax"], sr=self.sr, hop_length=self.hop)
             self.in_free[b].record(main)
+            if i + ahead < len(starts):
+                issue_copy(i + ahead)
             self.rms[c0 : c0 + n].copy_(feat["rms"], non_blocking=True)
             self.env[c0 : c0 + n].copy_(post["onset_env"], non_blocking=True)
             self.peaks[c0 : c0 + n].copy_(pk["peaks"], non_blocking=True)
         main.synchronize()
         return {"rms": self.rms, "onset_env": self.env, "onset_peaks": self.peaks}
+
+
+class TranscribePipeline:
+    """Host-buffer plugin call for full transcription of a batch: 16-bit PCM (or float32) host audio in, the reference's
+    perception arrays and the note-event records out.
+
+    Per chunk of ``chunk_clips`` clips: H2D on one of ``copy_streams`` copy streams (chunk i+1 travels while chunk i is
+    analysed), ingest (K9, when the host batch is PCM), ``analyze_batch`` (K1, K4, K2, K3: rake mask, pYIN, RMS --
+    aegis_engine.py:41-75), ``note_events_batch`` (K7: get_midi_events, midi_logic.py:32-148), then D2H of ``rake_mask, f0,
+    voiced_flag, voiced_probs, rms`` (the dict of aegis_engine.py:72-75) and of the event records into pinned host arrays.
+    """
+
+    def __init__(self, n_clips: int, n_samples: int, *, sr: float, hop_length: int = 512, device=None, chunk_clips: int = 128,
+                 pcm: bool = True, copy_streams: int = 2, confidence_threshold: float = 0.7):
+        self.sr, self.hop, self.thr = sr, hop_length, confidence_threshold
+        self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.n_clips, self.n_samples, self.pcm = n_clips, n_samples, pcm
+        self.chunk = min(chunk_clips, n_clips)
+        self.T = core.frame_count(n_samples, hop_length)
+        in_dtype = torch.int16 if pcm else torch.float32
+        self.in_shape = (n_clips, n_samples)
+        self.nbuf = max(2, copy_streams + 1)
+        self.inbuf = [torch.empty((self.chunk, n_samples), dtype=in_dtype, device=self.dev) for _ in range(self.nbuf)]
+        self.copy_streams = [torch.cuda.Stream(device=self.dev) for _ in range(max(1, copy_streams))]
+        self.in_ready = [torch.cuda.Event() for _ in range(self.nbuf)]
+        self.in_free = [torch.cuda.Event() for _ in range(self.nbuf)]
+        min_frames, _ = core.note_frame_limits(sr, hop_length)
+        self.max_events = self.T // (min_frames + 1) + 1
+        pin = dict(pin_memory=True)
+        self.out = {
+            "rake_mask": torch.empty((n_clips, self.T), dtype=torch.uint8, **pin),
+            "f0": torch.empty((n_clips, self.T), dtype=torch.float64, **pin),
+            "voiced_flag": torch.empty((n_clips, self.T), dtype=torch.uint8, **pin),
+            "voiced_probs": torch.empty((n_clips, self.T), dtype=torch.float64, **pin),
+            "rms": torch.empty((n_clips, self.T), dtype=torch.float32, **pin),
+            "events": torch.empty((n_clips, self.max_events, core.NOTE_EVENT_DTYPE.itemsize), dtype=torch.uint8, **pin),
+            "n_events": torch.empty((n_clips,), dtype=torch.int32, **pin),
+        }
+        self.h2d_bytes = n_clips * n_samples * (2 if pcm else 4)
+        self.d2h_bytes = sum(int(t.numel()) * t.element_size() for t in self.out.values())
+
+    def run(self, y_host: torch.Tensor) -> dict:
+        if y_host.is_cuda or tuple(y_host.shape) != self.in_shape or y_host.dtype != self.inbuf[0].dtype:
+            raise ValueError(f"expected a host {self.inbuf[0].dtype} tensor {self.in_shape}")
+        main = torch.cuda.current_stream(self.dev)
+        starts = list(range(0, self.n_clips, self.chunk))
+        for b in range(self.nbuf):
+            self.in_free[b].record(main)
+
+        def issue_copy(i):   # one cudaMemcpyAsync per chunk, on the chunk's copy stream
+            b, c0 = i % self.nbuf, starts[i]
+            n = min(self.chunk, self.n_clips - c0)
+            cs = self.copy_streams[i % len(self.copy_streams)]
+            with torch.cuda.stream(cs):
+                cs.wait_event(self.in_free[b])
+                self.inbuf[b][:n].copy_(y_host[c0 : c0 + n], non_blocking=True)
+                self.in_ready[b].record(cs)
+
+        ahead = self.nbuf - 1
+        for i in range(min(ahead, len(starts))):
+            issue_copy(i)
+        for i, c0 in enumerate(starts):
+            b = i % self.nbuf
+            n = min(self.chunk, self.n_clips - c0)
+            main.wait_event(self.in_ready[b])
+            yb = self.inbuf[b][:n]
+            if self.pcm:
+                yb = core.resample_poly(yb, int(self.sr), int(self.sr))   # int16 -> float32 / 32768 on the device (K9)
+            res = analyze_batch(yb, sr=self.sr, hop_length=self.hop)
+            self.in_free[b].record(main)
+            if i + ahead < len(starts):
+                issue_copy(i + ahead)
+            ev = note_events_batch(res, sr=self.sr, hop_length=self.hop, confidence_threshold=self.thr, max_events=self.max_events)
+            for k in ("rake_mask", "f0", "voiced_flag", "voiced_probs", "rms"):
+                self.out[k][c0 : c0 + n].copy_(res[k], non_blocking=True)
+            self.out["events"][c0 : c0 + n].copy_(ev["events"], non_blocking=True)
+            self.out["n_events"][c0 : c0 + n].copy_(ev["n_events"], non_blocking=True)
+        main.synchronize()
+        return self.out

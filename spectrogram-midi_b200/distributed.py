@@ -229,7 +229,7 @@ MIN_MARGIN_FRAMES = 32  # the rake run-length gate looks at up to 30 neighbourin
 def analyze_long_clip(y, *, sr: float, hop_length: int = 512, fmin: Optional[float] = None, fmax: Optional[float] = None,
                       rake_sensitivity: float = 0.6, mode: str = "exact", burn_seconds: float = 2.0, group=None,
                       backend=None, windows_per_rank: int = 1, return_events: bool = False,
-                      event_kwargs: Optional[dict] = None) -> dict:
+                      event_kwargs: Optional[dict] = None, solo: bool = False) -> dict:
     """Perception arrays of ONE long clip computed by all ranks of ``group`` (each rank can read the clip,
     or at least its own windows, from host memory).  Every rank returns the full-length result:
     ``rake_mask, f0 (NaN unvoiced), voiced_flag, voiced_probs, rms`` as numpy arrays (aegis_engine.py:72-75).
@@ -244,10 +244,14 @@ def analyze_long_clip(y, *, sr: float, hop_length: int = 512, fmin: Optional[flo
     dB scale needs the clip-wide RMS maximum), so every rank runs it on the gathered frame arrays -- microseconds per
     second of audio -- keeps the events that START inside its own frames, and ``gather_note_events`` puts the list
     together (NCCL over NVLink on a GPU box).  The list equals the single-GPU one by construction.
+    ``solo=True`` ignores the process group: this rank analyses the whole clip alone (the serial answer a multi-rank
+    run is compared with).
     """
     if mode not in ("exact", "windowed"):
         raise ValueError("mode must be 'exact' or 'windowed'")
-    rank, world = _world(group)
+    rank, world = (0, 1) if solo else _world(group)
+    reduce_max = (lambda t: t) if solo else (lambda t: all_reduce_max(t, group))
+    gather = (lambda t: [t]) if solo else (lambda t: all_gather_ragged(t, group))
     if backend is None:
         from .batch import C6, E2
 
@@ -263,7 +267,7 @@ def analyze_long_clip(y, *, sr: float, hop_length: int = 512, fmin: Optional[flo
     local_max = feats[0]["mel_max"].clone()
     for f in feats[1:]:
         local_max = torch.maximum(local_max, f["mel_max"])
-    mel_max = all_reduce_max(local_max, group)
+    mel_max = reduce_max(local_max)
 
     own_parts = []
     for w, feat in zip(mine, feats):
@@ -281,7 +285,7 @@ def analyze_long_clip(y, *, sr: float, hop_length: int = 512, fmin: Optional[flo
                 own[k] = feat[k][a:b]
         own_parts.append(own)
     own = {k: torch.cat([o[k] for o in own_parts]) for k in own_parts[0]}
-    full = {k: torch.cat(all_gather_ragged(v.contiguous(), group)) for k, v in own.items()}
+    full = {k: torch.cat(gather(v.contiguous())) for k, v in own.items()}
     if mode == "exact":
         # coupling 2, exact: the gathered sparse observations are decoded as the single chain they are
         dec = backend.decode(full.pop("cand_bin"), full.pop("cand_prob"), full.pop("cand_count"), full["voiced_probs"])
@@ -300,7 +304,7 @@ def analyze_long_clip(y, *, sr: float, hop_length: int = 512, fmin: Optional[flo
         lo, hi = (mine[0].own_lo, mine[-1].own_hi) if mine else (0, 0)
         keep = (ev["start"] >= lo) & (ev["start"] < hi)
         res["events_local"] = int(keep.sum())
-        res["events"] = gather_note_events(ev[keep], group=group, dtype=ev.dtype)
+        res["events"] = ev[keep] if solo else gather_note_events(ev[keep], group=group, dtype=ev.dtype)
     return res
 
 
