@@ -431,7 +431,6 @@ def run_gpu(args):
     stop.record()
     barrier()
     elapsed_ms = start.elapsed_time(stop)
-    clocks = sampler.stop()
 
     # ================================================================================================================
     # end to end through the host-buffer plugin call (cfg2).  PRIMARY: 16-bit PCM host buffers -- what a WAV file
@@ -518,6 +517,7 @@ def run_gpu(args):
         tr = {"ms": tr_ms, "e2e_s": tr_e2e_s, "stage_ms": stage_ms, "bytes": tr_bytes, "n_events_mean": n_events_mean,
               "issue": vit, "issue_note": why}
     del pcm_host
+    clocks = sampler.stop()   # sampled every 200 ms from the headline loop to the end of the transcription section
 
     # ---- long clip (BASELINE cfg4) at N > 1: one hour at 44.1 kHz over the ranks, exact and windowed, against one rank alone
     long_clip = None

@@ -231,26 +231,34 @@ class TranscribePipeline:
     """Host-buffer plugin call for full transcription of a batch: 16-bit PCM (or float32) host audio in, the reference's
     perception arrays and the note-event records out.
 
-    Per chunk of ``chunk_clips`` clips: H2D on one of ``copy_streams`` copy streams (chunk i+1 travels while chunk i is
-    analysed), ingest (K9, when the host batch is PCM), ``analyze_batch`` (K1, K4, K2, K3: rake mask, pYIN, RMS --
-    aegis_engine.py:41-75), ``note_events_batch`` (K7: get_midi_events, midi_logic.py:32-148), then D2H of ``rake_mask, f0,
-    voiced_flag, voiced_probs, rms`` (the dict of aegis_engine.py:72-75) and of the event records into pinned host arrays.
+    The host batch travels in pieces of ``chunk_clips`` clips (one cudaMemcpyAsync each, round-robin over ``copy_streams``
+    copy streams) into a device buffer for the whole batch; the kernels run on GROUPS of ``group_clips`` clips as soon as a
+    group's pieces have landed -- a group defaults to four clips per SM, the number of Viterbi chains (one CTA each) that
+    are resident at once, so the sequential-over-frames decoder always runs full waves while later pieces are still on
+    the bus.  Per group: ingest (K9, when the host batch is PCM), ``analyze_batch`` (K1, K4, K2, K3: rake mask, pYIN, RMS
+    -- aegis_engine.py:41-75), ``note_events_batch`` (K7: get_midi_events, midi_logic.py:32-148), then D2H of ``rake_mask,
+    f0, voiced_flag, voiced_probs, rms`` (the dict of aegis_engine.py:72-75) and of the event records into pinned arrays.
     """
 
     def __init__(self, n_clips: int, n_samples: int, *, sr: float, hop_length: int = 512, device=None, chunk_clips: int = 128,
-                 pcm: bool = True, copy_streams: int = 2, confidence_threshold: float = 0.7):
+                 pcm: bool = True, copy_streams: int = 2, confidence_threshold: float = 0.7, group_clips: Optional[int] = None):
+        from . import _native as nat
+
         self.sr, self.hop, self.thr = sr, hop_length, confidence_threshold
         self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.n_clips, self.n_samples, self.pcm = n_clips, n_samples, pcm
-        self.chunk = min(chunk_clips, n_clips)
+        self.chunk = max(1, min(chunk_clips, n_clips))
+        if group_clips is None:
+            with torch.cuda.device(self.dev):
+                group_clips = 4 * int(nat.load().aegis_device_sm_count())
+        self.group = max(self.chunk, min(group_clips, n_clips))
         self.T = core.frame_count(n_samples, hop_length)
         in_dtype = torch.int16 if pcm else torch.float32
         self.in_shape = (n_clips, n_samples)
-        self.nbuf = max(2, copy_streams + 1)
-        self.inbuf = [torch.empty((self.chunk, n_samples), dtype=in_dtype, device=self.dev) for _ in range(self.nbuf)]
+        self.inbuf = torch.empty(self.in_shape, dtype=in_dtype, device=self.dev)
         self.copy_streams = [torch.cuda.Stream(device=self.dev) for _ in range(max(1, copy_streams))]
-        self.in_ready = [torch.cuda.Event() for _ in range(self.nbuf)]
-        self.in_free = [torch.cuda.Event() for _ in range(self.nbuf)]
+        self.pieces = list(range(0, n_clips, self.chunk))
+        self.landed = [torch.cuda.Event() for _ in self.pieces]
         min_frames, _ = core.note_frame_limits(sr, hop_length)
         self.max_events = self.T // (min_frames + 1) + 1
         pin = dict(pin_memory=True)
@@ -267,40 +275,31 @@ class TranscribePipeline:
         self.d2h_bytes = sum(int(t.numel()) * t.element_size() for t in self.out.values())
 
     def run(self, y_host: torch.Tensor) -> dict:
-        if y_host.is_cuda or tuple(y_host.shape) != self.in_shape or y_host.dtype != self.inbuf[0].dtype:
-            raise ValueError(f"expected a host {self.inbuf[0].dtype} tensor {self.in_shape}")
+        if y_host.is_cuda or tuple(y_host.shape) != self.in_shape or y_host.dtype != self.inbuf.dtype:
+            raise ValueError(f"expected a host {self.inbuf.dtype} tensor {self.in_shape}")
         main = torch.cuda.current_stream(self.dev)
-        starts = list(range(0, self.n_clips, self.chunk))
-        for b in range(self.nbuf):
-            self.in_free[b].record(main)
-
-        def issue_copy(i):   # one cudaMemcpyAsync per chunk, on the chunk's copy stream
-            b, c0 = i % self.nbuf, starts[i]
-            n = min(self.chunk, self.n_clips - c0)
+        start = torch.cuda.Event()
+        start.record(main)           # the previous run's kernels are done with the input buffer
+        for i, c0 in enumerate(self.pieces):
             cs = self.copy_streams[i % len(self.copy_streams)]
             with torch.cuda.stream(cs):
-                cs.wait_event(self.in_free[b])
-                self.inbuf[b][:n].copy_(y_host[c0 : c0 + n], non_blocking=True)
-                self.in_ready[b].record(cs)
-
-        ahead = self.nbuf - 1
-        for i in range(min(ahead, len(starts))):
-            issue_copy(i)
-        for i, c0 in enumerate(starts):
-            b = i % self.nbuf
-            n = min(self.chunk, self.n_clips - c0)
-            main.wait_event(self.in_ready[b])
-            yb = self.inbuf[b][:n]
+                if i < len(self.copy_streams):
+                    cs.wait_event(start)
+                self.inbuf[c0 : c0 + self.chunk].copy_(y_host[c0 : c0 + self.chunk], non_blocking=True)
+                self.landed[i].record(cs)
+        for g0 in range(0, self.n_clips, self.group):
+            g1 = min(self.n_clips, g0 + self.group)
+            for i, c0 in enumerate(self.pieces):
+                if c0 < g1 and c0 + self.chunk > g0:
+                    main.wait_event(self.landed[i])
+            yb = self.inbuf[g0:g1]
             if self.pcm:
                 yb = core.resample_poly(yb, int(self.sr), int(self.sr))   # int16 -> float32 / 32768 on the device (K9)
             res = analyze_batch(yb, sr=self.sr, hop_length=self.hop)
-            self.in_free[b].record(main)
-            if i + ahead < len(starts):
-                issue_copy(i + ahead)
             ev = note_events_batch(res, sr=self.sr, hop_length=self.hop, confidence_threshold=self.thr, max_events=self.max_events)
             for k in ("rake_mask", "f0", "voiced_flag", "voiced_probs", "rms"):
-                self.out[k][c0 : c0 + n].copy_(res[k], non_blocking=True)
-            self.out["events"][c0 : c0 + n].copy_(ev["events"], non_blocking=True)
-            self.out["n_events"][c0 : c0 + n].copy_(ev["n_events"], non_blocking=True)
+                self.out[k][g0:g1].copy_(res[k], non_blocking=True)
+            self.out["events"][g0:g1].copy_(ev["events"], non_blocking=True)
+            self.out["n_events"][g0:g1].copy_(ev["n_events"], non_blocking=True)
         main.synchronize()
         return self.out

@@ -8,7 +8,9 @@
 //
 // Kernel 1 (frame parallel): rms -> dB relative to the clip maximum (librosa.amplitude_to_db(ref=np.max), float32
 // arithmetic as in numpy; log10 is evaluated in double and rounded once, i.e. correctly rounded float32) and the
-// per-frame MIDI note (-1 = inactive).  Kernel 2: one thread per clip walks its frames once (independent loads,
+// per-frame MIDI note (-1 = inactive) and the frame's continuous MIDI pitch 12 log2(f / 440) + 69 (the double-precision
+// log2 is by far the longest step of the walk: it is taken here, frame parallel, not in the sequential kernel).
+// Kernel 2: one thread per clip walks its frames once (independent loads,
 // L2 resident), keeps least-squares sums of the running event, finishes events (slope, vibrato range), and applies
 // the duration filter, the merge and the hammer-on / pull-off rule in streaming form: an event is written once the
 // next surviving event is known.  A clip is a sequential chain of ~T steps of a few dozen instructions: 1292 frames
@@ -22,9 +24,13 @@ namespace aegis {
 
 constexpr int NT_THREADS = 256;
 
+// librosa.hz_to_midi, the expression both kernels used before the log2 was hoisted (same contraction: one definition)
+__device__ __forceinline__ double midi_pitch(double f) { return 12.0 * (log2(f) - log2(440.0)) + 69.0; }
+
 // per frame: rms dB and MIDI note (or -1)
 __global__ void __launch_bounds__(NT_THREADS)
-notes_frames_kernel(const aegis_notes_params p, const float* __restrict__ rms_max, float* __restrict__ rms_db, short* __restrict__ note) {
+notes_frames_kernel(const aegis_notes_params p, const float* __restrict__ rms_max, float* __restrict__ rms_db, short* __restrict__ note,
+                    double* __restrict__ pitch) {
     const int clip = blockIdx.y;
     const int t = blockIdx.x * NT_THREADS + threadIdx.x;
     if (t >= p.n_frames) return;
@@ -43,6 +49,7 @@ notes_frames_kernel(const aegis_notes_params p, const float* __restrict__ rms_ma
         }
     }
     note[i] = static_cast<short>(n);
+    pitch[i] = n >= 0 ? midi_pitch(f) : 0.0;
 }
 
 struct Ev {
@@ -65,16 +72,16 @@ __device__ __forceinline__ void write_event(aegis_note_event* dst, const Ev& e) 
     dst->slope = e.slope;
 }
 
-__global__ void __launch_bounds__(64)
-notes_events_kernel(const aegis_notes_params p, const float* __restrict__ rms_db, const short* __restrict__ note) {
+__global__ void __launch_bounds__(32)
+notes_events_kernel(const aegis_notes_params p, const float* __restrict__ rms_db, const short* __restrict__ note,
+                    const double* __restrict__ pitch) {
     const int clip = blockIdx.x * blockDim.x + threadIdx.x;
     if (clip >= p.n_clips) return;
     const int T = p.n_frames;
     const long long base = static_cast<long long>(clip) * T;
     const short* nt = note + base;
-    const double* f0 = p.f0 + base;
+    const double* yp = pitch + base;
     aegis_note_event* out = p.events + static_cast<long long>(clip) * p.max_events;
-    const double LOG2_440 = log2(440.0);
     const double ms_per_frame = (static_cast<double>(p.hop) / p.sr) * 1000;
     int n_out = 0;
     bool have_pending = false, have_last = false;
@@ -111,8 +118,7 @@ notes_events_kernel(const aegis_notes_params p, const float* __restrict__ rms_db
             const double icpt = ym - slope * xm;
             double rmin = DBL_MAX, rmax = -DBL_MAX;
             for (int t = e.start; t <= e.end; ++t) {
-                const double y = 12.0 * (log2(f0[t]) - LOG2_440) + 69.0;
-                const double r = y - (slope * (t - e.start) + icpt);
+                const double r = yp[t] - (slope * (t - e.start) + icpt);
                 rmin = fmin(rmin, r);
                 rmax = fmax(rmax, r);
             }
@@ -142,7 +148,7 @@ notes_events_kernel(const aegis_notes_params p, const float* __restrict__ rms_db
             open = false;
         }
         if (n >= 0) {
-            const double y = 12.0 * (log2(f0[t]) - LOG2_440) + 69.0;
+            const double y = yp[t];
             if (!open) {
                 const float energy = rms_db[base + t];
                 const double conf = p.voiced_prob[base + t];
@@ -185,13 +191,14 @@ extern "C" int aegis_note_events(const aegis_notes_params* p, void* stream) {
     float* rms_max = reinterpret_cast<float*>(scratch);
     float* rms_db = rms_max + ((p->n_clips + 3) / 4) * 4;
     short* note = reinterpret_cast<short*>(rms_db + frames);
+    double* pitch = reinterpret_cast<double*>(scratch + (((reinterpret_cast<unsigned char*>(note + frames) - scratch) + 15) / 16) * 16);
     if (p->n_frames > 0) {
         rms_max_kernel<NT_THREADS><<<p->n_clips, NT_THREADS, 0, st>>>(p->rms, p->rms_clip_stride, p->n_frames, rms_max);
         if (int rc = check_launch("aegis_note_events(rms max)")) return rc;
-        notes_frames_kernel<<<dim3((p->n_frames + NT_THREADS - 1) / NT_THREADS, p->n_clips), NT_THREADS, 0, st>>>(*p, rms_max, rms_db, note);
+        notes_frames_kernel<<<dim3((p->n_frames + NT_THREADS - 1) / NT_THREADS, p->n_clips), NT_THREADS, 0, st>>>(*p, rms_max, rms_db, note, pitch);
         if (int rc = check_launch("aegis_note_events(frames)")) return rc;
     }
-    notes_events_kernel<<<(p->n_clips + 63) / 64, 64, 0, st>>>(*p, rms_db, note);
+    notes_events_kernel<<<(p->n_clips + 31) / 32, 32, 0, st>>>(*p, rms_db, note, pitch);
     return check_launch("aegis_note_events(events)");
 }
 
@@ -199,5 +206,5 @@ extern "C" int aegis_note_events(const aegis_notes_params* p, void* stream) {
 extern "C" long long aegis_note_events_bytes(int n_clips, int n_frames, int max_events) {
     const long long frames = static_cast<long long>(n_clips) * n_frames;
     return static_cast<long long>(n_clips) * max_events * static_cast<long long>(sizeof(aegis_note_event)) +
-           ((n_clips + 3) / 4) * 4 * 4LL + frames * 4 + frames * 2 + 16;
+           ((n_clips + 3) / 4) * 4 * 4LL + frames * 4 + frames * 2 + 32 + frames * 8 + 16;
 }

@@ -6,7 +6,25 @@
 //   beta(2,18)-weighted thresholds with a Boltzmann prior over trough rank -> parabolic period
 //   refinement -> 10-cent pitch bins.  Output is the sparse column of the HMM observation matrix.
 //
-// A CTA of 128 threads handles two consecutive frames of one clip (a "pair"), built on the same
+// hop == 512 (the reference's only hop, aegis_engine.py:17): yin_direct_kernel, no FFT at all.  The autocorrelation
+//   acf_t[tau] = sum_{j=1..1024} y_t[j] * y_t[j + tau]
+// of frame t is a sum of products over a 1024-sample window that slides by 512 samples per frame, so it is the sum of two
+// BLOCK SUMS of 512 products each, and every block sum is shared by two consecutive frames: half the multiplies of a
+// per-frame evaluation, only for the lags pYIN reads (tau <= max_period: 268 at 22.05 kHz, 536 at 44.1 kHz), in plain FP32
+// FMAs with no twiddles, no exchanges and no three-pass code that overflows the instruction cache.  A CTA of 8 warps
+// takes 15 consecutive frames of a clip = 16 blocks = 8 block pairs, one pair per warp: a lane owns 16 consecutive
+// samples of each block (registers), slides a 16-sample window over them lag by lag (one shared-memory load per lag
+// and block, conflict-free in a 17-word-per-16-samples skewed layout) and accumulates 16 lags at a time with packed
+// f32x2 FMAs (lo = first block, hi = second block: the two never mix); a butterfly transpose-reduce sums the 32 lanes.
+// Per block sum: a 16-term FMA chain per lane, then a binary tree over the lanes -- measured ~4x closer to the float64
+// difference function than librosa's own float32 FFT evaluation (it is not bit-equal to it, and never was: pocketfft's
+// rounding cannot be restated).  Block sums depend on nothing but their own samples, so a frame's result is the same
+// whatever clip, batch or window it is analysed in.
+// Energies / cumulative means are prefix scans in double, one warp per frame; the trough / threshold / prior stage runs
+// one warp per frame with ballot compaction and shuffle reductions.
+//
+// Other hops (4..508): yin_fft_kernel, the round-1 path.  A CTA of 128 threads handles two consecutive frames
+// of one clip (a "pair"), built on the same
 // 2048-point FFT passes as the STFT kernel:
 //   forward FFT of (frame + i*reversed-first-half) gives both spectra librosa multiplies;
 //   the two frames' product spectra are packed as P1 + i*P2 and inverted with ONE transform
@@ -66,8 +84,145 @@ __device__ __forceinline__ void fft_finish_inplace(int lt, cf* v, const FftTwidd
     __syncthreads();
 }
 
+// Candidate stage of one frame by one warp (librosa __pyin_helper): troughs of the CMND curve
+// yv[0..L), their probabilities over the beta-weighted thresholds with the Boltzmann prior on the trough rank, parabolic
+// refinement, 10-cent bins; writes the frame's sparse observation (bins ascending, unique) and its voiced probability.
+__device__ __forceinline__ void yin_candidates_of_frame(const aegis_yin_params& p, const double* yv, const int L, const int minp,
+                                            unsigned short* tk, unsigned char* tq, double* tp, const int max_troughs,
+                                            const long long fidx, const int lane) {
+    // 1. troughs, compacted in lag order
+    int nt = 0;
+    for (int base = 0; base < L; base += 32) {
+        const int k = base + lane;
+        bool tr = false;
+        if (k < L && L >= 2) {
+            const double x = yv[k];
+            if (k == 0) tr = x < yv[1];
+            else if (k == L - 1) tr = x < yv[k - 1];
+            else tr = (x < yv[k - 1]) && (x <= yv[k + 1]);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, tr);
+        if (tr) {
+            const int pos = nt + __popc(m & ((1u << lane) - 1u));
+            if (pos < max_troughs) tk[pos] = static_cast<unsigned short>(k);
+        }
+        nt += __popc(m);
+    }
+    nt = min(nt, max_troughs);
+    __syncwarp();
+    int count = 0;
+    double vsum = 0.0;
+    if (nt > 0) {
+        // 2. first threshold index each trough is below; global minimum (first on ties)
+        const int nth = p.n_thresholds;
+        double best_h = DBL_MAX;
+        int best_i = 0x7fffffff;
+        for (int i = lane; i < nt; i += 32) {
+            const double h = yv[tk[i]];
+            int q = (h >= 1.0) ? nth : ((h <= 0.0) ? 0 : static_cast<int>(h * nth));  // guess, then fix
+            q = max(0, min(q, nth));
+            while (q > 0 && h < __ldg(p.thresholds + q - 1)) --q;
+            while (q < nth && !(h < __ldg(p.thresholds + q))) ++q;
+            tq[i] = static_cast<unsigned char>(q);
+            tp[i] = 0.0;
+            if (h < best_h) { best_h = h; best_i = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double oh = __shfl_xor_sync(0xffffffffu, best_h, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (oh < best_h || (oh == best_h && oi < best_i)) { best_h = oh; best_i = oi; }
+        }
+        __syncwarp();
+        // 3. troughs below each threshold (this lane owns thresholds lane, lane+32, ...)
+        int nj[4] = {0, 0, 0, 0}, pj[4] = {0, 0, 0, 0};
+        for (int i = 0; i < nt; ++i) {
+            const int q = tq[i];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) nj[r] += (q <= lane + 32 * r) ? 1 : 0;
+        }
+        double fj[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int j = lane + 32 * r;
+            fj[r] = (j < nth && nj[r] > 0) ? __ldg(p.boltz_fact + nj[r]) : 0.0;
+        }
+        // 4. probability of each trough: sum_j prior(rank among troughs below th_j) * beta_j
+        for (int i = 0; i < nt; ++i) {
+            const int q = tq[i];
+            if (q >= nth) continue;  // warp-uniform
+            double c = 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int j = lane + 32 * r;
+                if (j < nth && q <= j) {
+                    c += (fj[r] * __ldg(p.boltz_exp + pj[r])) * __ldg(p.beta_probs + j);
+                    ++pj[r];
+                }
+            }
+            c = warp_sum_d(c);
+            if (lane == 0) tp[i] = c;
+        }
+        __syncwarp();
+        // 5. every lane turns its troughs' lags into pitch bins (parabolic refinement, log2: the expensive
+        //    part, in parallel; tk[] is overwritten with the bin, 0xffff = not a candidate) ...
+        if (lane == 0) tp[best_i] += p.no_trough_prob * __ldg(p.beta_cumsum + tq[best_i]);
+        __syncwarp();
+        {
+            const double scale = 12.0 * p.bins_per_semitone;
+            for (int i = lane; i < nt; i += 32) {
+                unsigned short bin16 = 0xffffu;
+                if (tp[i] != 0.0) {
+                    const int k = tk[i];
+                    double shift = 0.0;
+                    if (k > 0 && k < L - 1) {
+                        const double a = yv[k + 1] + yv[k - 1] - 2.0 * yv[k];
+                        const double b = (yv[k + 1] - yv[k - 1]) / 2.0;
+                        if (!(fabs(b) >= fabs(a))) shift = -b / a;
+                    }
+                    const double period = static_cast<double>(minp + k) + shift;
+                    const double f0 = p.sr / period;
+                    double bf = rint(scale * log2(f0 / p.fmin));
+                    bf = fmin(fmax(bf, 0.0), static_cast<double>(p.n_pitch_bins));
+                    const int bin = static_cast<int>(bf);
+                    if (bin < p.n_pitch_bins) bin16 = static_cast<unsigned short>(bin);   // else: unvoiced rows, overwritten
+                }
+                tk[i] = bin16;
+            }
+        }
+        __syncwarp();
+        //    ... and lane 0 emits them in ascending-bin order (= descending lag); equal bins: the larger lag wins
+        if (lane == 0) {
+            unsigned short* ob = p.cand_bin + fidx * p.max_cand;
+            double* op = p.cand_prob + fidx * p.max_cand;
+            int last_bin = -1;
+            bool over = false;
+            for (int i = nt - 1; i >= 0; --i) {
+                const int bin = tk[i];
+                if (bin == 0xffff) continue;
+                if (bin == last_bin) continue;        // overwritten by the later (larger-lag) write
+                last_bin = bin;
+                if (count < p.max_cand) {
+                    ob[count] = static_cast<unsigned short>(bin);
+                    const double pr = tp[i];
+                    op[count] = pr;
+                    vsum += pr;
+                    ++count;
+                } else {
+                    over = true;
+                }
+            }
+            if (over) atomicExch(p.overflow, 1);
+        }
+    }
+    if (lane == 0) {
+        p.cand_count[fidx] = count;
+        p.voiced_prob[fidx] = fmin(fmax(vsum, 0.0), 1.0);
+    }
+}
+
 __global__ void __launch_bounds__(YIN_THREADS, 4)
-yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n_pairs) {
+yin_fft_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n_pairs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     YinSmem& s = *reinterpret_cast<YinSmem*>(smem_raw);
     YinScratchE& se = *reinterpret_cast<YinScratchE*>(s.buf);
@@ -225,142 +380,191 @@ yin_kernel(const aegis_yin_params p, const int pairs_per_clip, const long long n
             const int fr = warp >> 1;
             const int t = t0 + fr;
             if (t < T) {
-                const double* yv = se.yin[fr];
-                unsigned short* tk = sc.tk[fr];
-                unsigned char* tq = sc.tq[fr];
-                double* tp = sc.tp[fr];
-                const long long fidx = static_cast<long long>(clip) * T + t;
-                // 1. troughs, compacted in lag order
-                int nt = 0;
-                for (int base = 0; base < L; base += 32) {
-                    const int k = base + lane;
-                    bool tr = false;
-                    if (k < L && L >= 2) {
-                        const double x = yv[k];
-                        if (k == 0) tr = x < yv[1];
-                        else if (k == L - 1) tr = x < yv[k - 1];
-                        else tr = (x < yv[k - 1]) && (x <= yv[k + 1]);
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, tr);
-                    if (tr) {
-                        const int pos = nt + __popc(m & ((1u << lane) - 1u));
-                        if (pos < YIN_MAX_TROUGHS) tk[pos] = static_cast<unsigned short>(k);
-                    }
-                    nt += __popc(m);
-                }
-                nt = min(nt, YIN_MAX_TROUGHS);
-                __syncwarp();
-                int count = 0;
-                double vsum = 0.0;
-                if (nt > 0) {
-                    // 2. first threshold index each trough is below; global minimum (first on ties)
-                    const int nth = p.n_thresholds;
-                    double best_h = DBL_MAX;
-                    int best_i = 0x7fffffff;
-                    for (int i = lane; i < nt; i += 32) {
-                        const double h = yv[tk[i]];
-                        int q = (h >= 1.0) ? nth : ((h <= 0.0) ? 0 : static_cast<int>(h * nth));  // guess, then fix
-                        q = max(0, min(q, nth));
-                        while (q > 0 && h < __ldg(p.thresholds + q - 1)) --q;
-                        while (q < nth && !(h < __ldg(p.thresholds + q))) ++q;
-                        tq[i] = static_cast<unsigned char>(q);
-                        tp[i] = 0.0;
-                        if (h < best_h) { best_h = h; best_i = i; }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double oh = __shfl_xor_sync(0xffffffffu, best_h, o);
-                        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-                        if (oh < best_h || (oh == best_h && oi < best_i)) { best_h = oh; best_i = oi; }
-                    }
-                    __syncwarp();
-                    // 3. troughs below each threshold (this lane owns thresholds lane, lane+32, ...)
-                    int nj[4] = {0, 0, 0, 0}, pj[4] = {0, 0, 0, 0};
-                    for (int i = 0; i < nt; ++i) {
-                        const int q = tq[i];
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) nj[r] += (q <= lane + 32 * r) ? 1 : 0;
-                    }
-                    double fj[4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int j = lane + 32 * r;
-                        fj[r] = (j < nth && nj[r] > 0) ? __ldg(p.boltz_fact + nj[r]) : 0.0;
-                    }
-                    // 4. probability of each trough: sum_j prior(rank among troughs below th_j) * beta_j
-                    for (int i = 0; i < nt; ++i) {
-                        const int q = tq[i];
-                        if (q >= nth) continue;  // warp-uniform
-                        double c = 0.0;
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const int j = lane + 32 * r;
-                            if (j < nth && q <= j) {
-                                c += (fj[r] * __ldg(p.boltz_exp + pj[r])) * __ldg(p.beta_probs + j);
-                                ++pj[r];
-                            }
-                        }
-                        c = warp_sum_d(c);
-                        if (lane == 0) tp[i] = c;
-                    }
-                    __syncwarp();
-                    // 5. every lane turns its troughs' lags into pitch bins (parabolic refinement, log2: the expensive
-                    //    part, in parallel; tk[] is overwritten with the bin, 0xffff = not a candidate) ...
-                    if (lane == 0) tp[best_i] += p.no_trough_prob * __ldg(p.beta_cumsum + tq[best_i]);
-                    __syncwarp();
-                    {
-                        const double scale = 12.0 * p.bins_per_semitone;
-                        for (int i = lane; i < nt; i += 32) {
-                            unsigned short bin16 = 0xffffu;
-                            if (tp[i] != 0.0) {
-                                const int k = tk[i];
-                                double shift = 0.0;
-                                if (k > 0 && k < L - 1) {
-                                    const double a = yv[k + 1] + yv[k - 1] - 2.0 * yv[k];
-                                    const double b = (yv[k + 1] - yv[k - 1]) / 2.0;
-                                    if (!(fabs(b) >= fabs(a))) shift = -b / a;
-                                }
-                                const double period = static_cast<double>(minp + k) + shift;
-                                const double f0 = p.sr / period;
-                                double bf = rint(scale * log2(f0 / p.fmin));
-                                bf = fmin(fmax(bf, 0.0), static_cast<double>(p.n_pitch_bins));
-                                const int bin = static_cast<int>(bf);
-                                if (bin < p.n_pitch_bins) bin16 = static_cast<unsigned short>(bin);   // else: unvoiced rows, overwritten
-                            }
-                            tk[i] = bin16;
-                        }
-                    }
-                    __syncwarp();
-                    //    ... and lane 0 emits them in ascending-bin order (= descending lag); equal bins: the larger lag wins
-                    if (lane == 0) {
-                        unsigned short* ob = p.cand_bin + fidx * p.max_cand;
-                        double* op = p.cand_prob + fidx * p.max_cand;
-                        int last_bin = -1;
-                        bool over = false;
-                        for (int i = nt - 1; i >= 0; --i) {
-                            const int bin = tk[i];
-                            if (bin == 0xffff) continue;
-                            if (bin == last_bin) continue;        // overwritten by the later (larger-lag) write
-                            last_bin = bin;
-                            if (count < p.max_cand) {
-                                ob[count] = static_cast<unsigned short>(bin);
-                                const double pr = tp[i];
-                                op[count] = pr;
-                                vsum += pr;
-                                ++count;
-                            } else {
-                                over = true;
-                            }
-                        }
-                        if (over) atomicExch(p.overflow, 1);
-                    }
-                }
-                if (lane == 0) {
-                    p.cand_count[fidx] = count;
-                    p.voiced_prob[fidx] = fmin(fmax(vsum, 0.0), 1.0);
-                }
+                yin_candidates_of_frame(p, se.yin[fr], L, minp, sc.tk[fr], sc.tq[fr], sc.tp[fr], YIN_MAX_TROUGHS,
+                                        static_cast<long long>(clip) * T + t, lane);
             }
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// hop == 512: direct block-sum autocorrelation
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int YD_THREADS = 256;                    // 8 warps = 8 block pairs
+constexpr int YD_BLOCKS = 16;                      // blocks of 512 products per CTA
+constexpr int YD_FRAMES = YD_BLOCKS - 1;           // frame i = block i + block i+1
+constexpr int YD_SPAN = YD_BLOCKS * 512 + 1024;    // samples m = 0 .. 9215 relative to the first frame's first sample
+constexpr int YD_PHYS = YD_SPAN + YD_SPAN / 16 + 32;   // skewed layout phys(m) = m + (m >> 4), + slack for one look-ahead load
+
+struct YinDirectLayout {      // byte offsets into dynamic shared memory (computed on the host from max_period)
+    int n_groups;             // lag groups of 16
+    int b_pitch;              // floats per block row of B (n_groups * 16)
+    int off_b, off_warp;      // B sums; first per-warp scratch area
+    int warp_bytes;           // per-warp scratch: yin (double), d (float), tp (double), tk (u16), tq (u8)
+    int off_d, off_tp, off_tk, off_tq;   // inside a warp's area
+    int max_troughs;
+    int total_bytes;
+};
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// inclusive warp scan of doubles (Hillis-Steele)
+__device__ __forceinline__ double warp_scan_incl_d(double v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(YD_THREADS, 2)
+yin_direct_kernel(const aegis_yin_params p, const YinDirectLayout lay, const int runs_per_clip) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* xs = reinterpret_cast<float*>(smem_raw);
+    float* Bs = reinterpret_cast<float*>(smem_raw + lay.off_b);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int clip = blockIdx.x / runs_per_clip;
+    const int t0 = (blockIdx.x - clip * runs_per_clip) * YD_FRAMES;
+    const int T = p.n_frames;
+    const long long N = p.n_samples;
+    const int maxp = p.max_period, minp = p.min_period;
+    const int L = maxp - minp + 1;
+    const float* __restrict__ yc = p.y + static_cast<long long>(clip) * p.clip_stride;
+    const long long g0 = static_cast<long long>(t0) * 512 - p.pad;   // clip sample of m = 0
+    const int n_fr = min(YD_FRAMES, T - t0);                         // frames of this run
+    // samples this run reads: m < 512 * (n_fr + 1) + 1 + 16 * 31 + 15 + maxp ... simply fill what the frames span
+    const int m_end = min(YD_SPAN, 512 * (n_fr - 1) + 2048);
+
+    // ---- phase A: samples -> shared, skewed (zeros outside the clip: center padding)
+    for (int m = tid; m < YD_SPAN; m += YD_THREADS) {
+        const long long gi = g0 + m;
+        xs[m + (m >> 4)] = (m < m_end && gi >= 0 && gi < N) ? __ldg(yc + gi) : 0.f;
+    }
+    if (tid < 32) xs[YD_SPAN + YD_SPAN / 16 + tid] = 0.f;
+    __syncthreads();
+
+    // ---- phase B: block sums B[b][tau] = sum_{n in block b} x[n] x[n + tau], block b = samples m = 512 b + 1 .. 512 b + 512.
+    // Warp w: blocks 2w (lo) and 2w+1 (hi).  Lane l: the 16 samples m = 512 b + 1 + 16 l + i.
+    if (2 * warp < n_fr + 1) {
+        const float* pa = xs + 544 * (2 * warp) + 17 * lane + 1;    // phys(512 b + 1 + 16 l) ; block 2w+1 is 544 words further
+        unsigned long long a[16], R[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int o = i + ((1 + i) >> 4);
+            a[i] = pack2(pa[o], pa[544 + o]);
+            R[i] = a[i];                                             // window W[j] = x[.. + j], j = 0 .. 15 (tau = 0)
+        }
+        float* brow = Bs + (2 * warp + (lane >> 4)) * lay.b_pitch + (lane & 15);
+        const bool hi_half = (lane & 16) != 0;
+#pragma unroll 1
+        for (int g = 0; g < lay.n_groups; ++g) {
+            const float* pw = pa + 17 * g;                           // W[16 g + s + 16] sits at pw[s + 17 + (s == 15)]
+            unsigned long long c[16];
+#pragma unroll
+            for (int s_ = 0; s_ < 16; ++s_) {
+                unsigned long long acc = 0ull;                       // (+0.f, +0.f)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc = ffma2(a[i], R[(s_ + i) & 15], acc);
+                c[s_] = acc;
+                const int o = s_ + 17 + (s_ == 15 ? 1 : 0);
+                R[s_] = pack2(pw[o], pw[544 + o]);
+            }
+            // transpose-reduce: 16 lags x 2 blocks = 32 values over 32 lanes; lane q ends with block (q >> 4), lag 16 g + (q & 15)
+            float v[16];
+#pragma unroll
+            for (int s_ = 0; s_ < 16; ++s_) {
+                float lo, hi;
+                unpack2(c[s_], lo, hi);
+                const float mine = hi_half ? hi : lo, other = hi_half ? lo : hi;
+                v[s_] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+            }
+#pragma unroll
+            for (int w_ = 8; w_ >= 1; w_ >>= 1) {
+                const bool up = (lane & w_) != 0;
+#pragma unroll
+                for (int s_ = 0; s_ < w_; ++s_) {
+                    const float keep = up ? v[s_ + w_] : v[s_], send = up ? v[s_] : v[s_ + w_];
+                    v[s_] = keep + __shfl_xor_sync(0xffffffffu, send, w_);
+                }
+            }
+            brow[16 * g] = v[0];
+        }
+    }
+    __syncthreads();
+
+    // ---- phases E + C, one warp per frame: energies, difference function, cumulative mean, CMND; then the candidates
+    unsigned char* wbase = smem_raw + lay.off_warp + warp * lay.warp_bytes;
+    double* yin = reinterpret_cast<double*>(wbase);
+    float* dbuf = reinterpret_cast<float*>(wbase + lay.off_d);
+    double* tp = reinterpret_cast<double*>(wbase + lay.off_tp);
+    unsigned short* tk = reinterpret_cast<unsigned short*>(wbase + lay.off_tk);
+    unsigned char* tq = wbase + lay.off_tq;
+    for (int fr = warp; fr < n_fr; fr += YD_THREADS / 32) {
+        const int t = t0 + fr;
+        const float* f = xs;                       // frame sample j = x[m = 512 fr + j]
+        auto fs = [&](int j) -> float { const int m = 512 * fr + j; return f[m + (m >> 4)]; };
+        double acc = 0.0;
+#pragma unroll 4
+        for (int j = 1 + lane; j <= FFT_N / 2; j += 32) { const float v = fs(j); acc += static_cast<double>(v * v); }
+        const double e0 = warp_sum_d(acc);
+        const int chunk = (maxp + 31) / 32;
+        const int lo = 1 + lane * chunk, hi = min(lo + chunk, maxp + 1);
+        double run = 0.0;
+#pragma unroll 1
+        for (int tau = lo; tau < hi; ++tau) {
+            const float u1 = fs(FFT_N / 2 + tau), u0 = fs(tau);
+            run += static_cast<double>(u1 * u1) - static_cast<double>(u0 * u0);
+        }
+        double incl = warp_scan_incl_d(run, lane);
+        double base = e0 + (incl - run);           // e0 + sum of the lower lanes' chunks
+        float e0f = static_cast<float>(e0);
+        if (fabsf(e0f) < 1e-6f) e0f = 0.f;
+        const float* B0 = Bs + fr * lay.b_pitch;
+        const float* B1 = B0 + lay.b_pitch;
+        run = 0.0;
+        double dsum = 0.0;
+#pragma unroll 1
+        for (int tau = lo; tau < hi; ++tau) {
+            const float u1 = fs(FFT_N / 2 + tau), u0 = fs(tau);
+            run += static_cast<double>(u1 * u1) - static_cast<double>(u0 * u0);
+            float e = static_cast<float>(base + run);
+            if (fabsf(e) < 1e-6f) e = 0.f;
+            float acf = B0[tau] + B1[tau];
+            if (fabsf(acf) < 1e-6f) acf = 0.f;
+            const float dv = (e0f + e) - 2.0f * acf;
+            dbuf[tau] = dv;
+            dsum += static_cast<double>(dv);
+        }
+        incl = warp_scan_incl_d(dsum, lane);
+        base = incl - dsum;
+        run = 0.0;
+        __syncwarp();
+#pragma unroll 1
+        for (int tau = lo; tau < hi; ++tau) {
+            run += static_cast<double>(dbuf[tau]);
+            if (tau >= minp) {
+                const double cm = static_cast<double>(static_cast<float>(base + run)) / static_cast<double>(tau);
+                const double yv = static_cast<double>(dbuf[tau]) / (cm + DBL_MIN);
+                yin[tau - minp] = yv;
+                if (p.cmnd_out != nullptr) p.cmnd_out[(static_cast<long long>(clip) * T + t) * L + (tau - minp)] = yv;
+            }
+        }
+        __syncwarp();
+        yin_candidates_of_frame(p, yin, L, minp, tk, tq, tp, lay.max_troughs, static_cast<long long>(clip) * T + t, lane);
+        __syncwarp();
     }
 }
 
@@ -378,15 +582,43 @@ extern "C" int aegis_yin_candidates(const aegis_yin_params* p, void* stream) {
     AEGIS_REQUIRE(p->cand_bin && p->cand_prob && p->cand_count && p->voiced_prob && p->overflow && p->max_cand >= 1,
                   "aegis_yin_candidates: outputs missing");
     if (p->n_clips == 0 || p->n_frames == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p->hop == 512) {   // the reference's hop: direct block-sum autocorrelation
+        YinDirectLayout lay{};
+        const int L = p->max_period - p->min_period + 1;
+        lay.n_groups = (p->max_period + 1 + 15) / 16;
+        lay.b_pitch = lay.n_groups * 16;
+        lay.off_b = ((YD_PHYS * 4 + 15) / 16) * 16;
+        lay.off_warp = lay.off_b + ((YD_BLOCKS * lay.b_pitch * 4 + 15) / 16) * 16;
+        lay.max_troughs = L / 2 + 1 < YIN_MAX_TROUGHS ? L / 2 + 1 : YIN_MAX_TROUGHS;
+        int o = ((L * 8 + 15) / 16) * 16;
+        lay.off_d = o;       o += (((p->max_period + 1) * 4 + 15) / 16) * 16;
+        lay.off_tp = o;      o += ((lay.max_troughs * 8 + 15) / 16) * 16;
+        lay.off_tk = o;      o += ((lay.max_troughs * 2 + 15) / 16) * 16;
+        lay.off_tq = o;      o += ((lay.max_troughs + 15) / 16) * 16;
+        lay.warp_bytes = o;
+        lay.total_bytes = lay.off_warp + (YD_THREADS / 32) * lay.warp_bytes;
+        AEGIS_REQUIRE(lay.total_bytes <= 227 * 1024, "aegis_yin_candidates: %d B shared memory needed for max_period=%d", lay.total_bytes, p->max_period);
+        cudaError_t e = cudaFuncSetAttribute(yin_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total_bytes);
+        if (e != cudaSuccess) {
+            set_error("aegis_yin_candidates: cannot reserve %d B shared memory: %s", lay.total_bytes, cudaGetErrorString(e));
+            return 2;
+        }
+        const int runs_per_clip = (p->n_frames + YD_FRAMES - 1) / YD_FRAMES;
+        const long long n_runs = static_cast<long long>(runs_per_clip) * p->n_clips;
+        AEGIS_REQUIRE(n_runs < (1ll << 31), "aegis_yin_candidates: too many frame runs for one launch");
+        yin_direct_kernel<<<static_cast<unsigned>(n_runs), YD_THREADS, lay.total_bytes, st>>>(*p, lay, runs_per_clip);
+        return check_launch("aegis_yin_candidates(direct)");
+    }
     const int pairs_per_clip = (p->n_frames + 1) / 2;
     const long long n_pairs = static_cast<long long>(pairs_per_clip) * p->n_clips;
-    cudaError_t e = cudaFuncSetAttribute(yin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(YinSmem)));
+    cudaError_t e = cudaFuncSetAttribute(yin_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(YinSmem)));
     if (e != cudaSuccess) {
         set_error("aegis_yin_candidates: cannot reserve %zu B shared memory: %s", sizeof(YinSmem), cudaGetErrorString(e));
         return 2;
     }
     const long long max_grid = static_cast<long long>(sm_count()) * 4;
     const int grid = static_cast<int>(n_pairs < max_grid ? n_pairs : max_grid);
-    yin_kernel<<<grid, YIN_THREADS, sizeof(YinSmem), static_cast<cudaStream_t>(stream)>>>(*p, pairs_per_clip, n_pairs);
+    yin_fft_kernel<<<grid, YIN_THREADS, sizeof(YinSmem), st>>>(*p, pairs_per_clip, n_pairs);
     return check_launch("aegis_yin_candidates");
 }
