@@ -2,9 +2,10 @@
 
 ``FinancialPitchAnalyzer`` keeps the reference's constructor and method signatures
 (financial_analysis.py:36-226, 368-423) for the numeric parts: SMA, EMA, Bollinger bands, MACD and
-the trend / confidence arrays of ``analyze_pitch_financial``.  The string-label loops
-(``detect_articulation_bollinger``, ``detect_slides_macd``) and the RSI ghost-note filter operate
-on labels / note events and remain with the consumer.
+the trend / confidence arrays of ``analyze_pitch_financial``.  On the hot path the string-label loops and the RSI
+ghost-note filter run inside kernel K8; ``detect_articulation_bollinger`` / ``detect_slides_macd`` are also provided here
+as host label loops over the GPU-computed bands / MACD series (financial_analysis.py:148-196, 228-271), which is what the
+``use_financial=False`` branch of ``get_midi_events_financial`` calls per note event.
 """
 from __future__ import annotations
 
@@ -39,6 +40,44 @@ class FinancialPitchAnalyzer:
     def macd(self, data, fast=12, slow=26, signal=9):
         out = _run(data, ["macd_line", "macd_sig", "macd_hist"], macd_fast=fast, macd_slow=slow, macd_signal=signal)
         return out["macd_line"], out["macd_sig"], out["macd_hist"]
+
+    def detect_articulation_bollinger(self, f0, window=10, sensitivity=2.0):
+        """Per-frame labels from the band position of ``f0`` (financial_analysis.py:148-196): 'bend' above the upper band,
+        'noise' below the lower one, 'vibrato' once the side has changed twice in a row, else 'normal'; None at NaN."""
+        f0 = np.asarray(f0, dtype=np.float64)
+        _, upper, lower = self.bollinger_bands(f0, window, sensitivity)
+        labels, prev, flips = [], 0, 0          # side: +1 above, -1 below, 0 inside
+        for x, up, lo in zip(f0, upper, lower):
+            if np.isnan(x):
+                labels.append(None)
+                continue
+            side = 1 if x > up else (-1 if x < lo else 0)
+            flips = flips + 1 if (prev != side and prev != 0) else 0
+            labels.append("vibrato" if flips >= 2 else ("bend" if side > 0 else ("noise" if side < 0 else "normal")))
+            prev = side
+        return labels
+
+    def detect_slides_macd(self, f0, threshold=0.5):
+        """Per-frame slide labels from the MACD (5 / 20 / 9) of the MIDI-pitch series (financial_analysis.py:228-271)."""
+        from .librosa_compat import hz_to_midi
+
+        f0 = np.asarray(f0, dtype=np.float64)
+        semis = np.full_like(f0, np.nan)
+        ok = ~np.isnan(f0)
+        if np.any(ok):
+            semis[ok] = hz_to_midi(f0[ok])
+        line, _, hist = self.macd(semis, fast=5, slow=20, signal=9)
+        out = []
+        for m, h in zip(line, hist):
+            if np.isnan(m):
+                out.append(None)
+            elif m > threshold and h > 0:
+                out.append("slide_up")
+            elif m < -threshold and h < 0:
+                out.append("slide_down")
+            else:
+                out.append("normal")
+        return out
 
     def bollinger_confidence(self, f0, window=10):
         """The ``confidence`` array of analyze_pitch_financial (financial_analysis.py:404-416)."""

@@ -716,6 +716,26 @@ def test_financial_note_events_batch_equals_oracle(dev, kw):
         assert events > 20
 
 
+def test_financial_logic_filter_fallback_branch_matches_reference_golden(dev):
+    """get_midi_events_financial(use_financial=False) -- the reference function's fallback branch
+    (midi_logic_financial.py:178-196 + detect_articulations_financial per note; never taken by the v2 engine): host frame loop,
+    Bollinger bands / MACD of every note's pitch slice from kernel K5.  Every field equals what the real file returns."""
+    from spectrogram_midi_b200.midi_logic_financial import get_midi_events_financial
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fin_fallback_golden.npz"))
+    tech = [None, "normal", "bend", "vibrato", "noise", "slide"]
+    for name in g["fb/names"]:
+        k, a = f"fb/{name}", g[f"fb/{name}/args"]
+        ev = get_midi_events_financial(g[f"{k}/rake_mask"], g[f"{k}/f0"], g[f"{k}/voiced_flag"], g[f"{k}/voiced_prob"], g[f"{k}/rms"],
+                                       int(a[0]), 512, confidence_threshold=None if np.isnan(a[1]) else float(a[1]),
+                                       use_financial=False, noise_gate_db=float(a[2]), sustain_ms=float(a[3]), min_note_duration_ms=float(a[4]))
+        ints = np.array([[e["note"], e["start"], e["end"], e["velocity"], int(e["track"] == "main"), tech.index(e.get("technique")),
+                          int("technique" in e)] for e in ev], dtype=np.int64).reshape(-1, 7)
+        np.testing.assert_array_equal(ints, g[f"{k}/events"], err_msg=str(name))
+        np.testing.assert_array_equal(np.array([e["confidence"] for e in ev]), g[f"{k}/confidence"], err_msg=str(name))
+        assert all(e["financial_artic"] is None and e["financial_slide"] is None for e in ev)
+
+
 def test_financial_engine_note_events(dev):
     """AegisFinancialEngine.perception -> note_events (K1..K6, K5, K8) == the restatement on the same host arrays."""
     from oracle import financial_events as FE
