@@ -30,6 +30,14 @@
 //      so its candidate is smaller than the twin's by > 0.8: it never wins, never ties.  Such states
 //      are not computed at all (V = -inf, no back-pointer): in a frame with voiced_prob < 1 only the
 //      warps that hold a candidate bin evaluate voiced destinations.
+//   4. COLLAPSE: in a frame whose unvoiced observation is (about) log(tiny) -- voiced_prob == 1, most frames of a clean
+//      note -- every state without a candidate carries an observation <= lp_u, so its value is at most
+//      lp_u + max(V[t-1]) + LTMAX (LTMAX = the largest log transition) and its candidate for ANY destination of the next
+//      frame at most that + LTMAX, while a candidate state c offers at least V[t][c] + log(tiny) to every destination.
+//      When  lower_bound(V[t][c]) + log(tiny) > lp_u + upper_bound(max V[t-1]) + 2 LTMAX + 1e-6  for some c, no state
+//      without a candidate can win or tie anywhere in frame t+1, nor be the final state: the frame computes the voiced
+//      destinations of the windows that hold candidates and nothing else (all other values -inf, no back-pointers).
+//      The bounds use only V[t-1] and the candidate lists of frames t-1 and t, so every warp takes the same decision.
 // Rows of the transition table that differ in the last ulp (librosa's pairwise row sums) are kept as
 // "variants": the few interior ones in shared memory (padded with -inf so that no lane needs a range
 // check), the truncated edge rows in global memory (a source row is warp-uniform inside a chunk, the
@@ -74,7 +82,19 @@ struct VitSmem {
     unsigned short prev[2][VT_MAX_BINS];           // [destination voicing][bin]: winning source of the previous frame (temporal coherence)
     unsigned cand_windows[3];                      // bit w: window w holds a candidate bin in frame t (slot t % 3)
     int next_task[2];                              // task counter of frame t (slot t & 1)
+    int cand_n[3];                                 // candidates of frame t (slot t % 3); the first 32 are listed below
+    unsigned short cand_bin[3][32];
+    double cand_lp[3][32];                         // log(prob + tiny) of the listed candidates
+    double lt_max;                                 // largest finite log transition of the whole table
 };
+
+// table entry for (source row, same|switch, offset 0 <= o < W), any row
+template <int W>
+__device__ __forceinline__ double lt_entry(const VitSmem& s, const aegis_viterbi_params& p, int brow, int sel, int o) {
+    const unsigned off = s.rowoff[VT_HALO + brow];
+    if (!(off & VT_EDGE_BIT)) return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(&s.lt[0][sel][VT_LT_PAD + o]) + off);
+    return __ldg(p.lt_variants + (off & 0x7FFFu) + sel * W + o);
+}
 
 // (a, ia) has the lower source index: (b, ib) wins only when strictly greater -- numpy's first-index argmax
 __device__ __forceinline__ void take_later(double& a, int& ia, double b, int ib) {
@@ -131,12 +151,7 @@ __device__ __forceinline__ void viterbi_task(const VitSmem& s, const aegis_viter
     const double* Vc0 = &s.V[cur][0][VT_HALO];
     const unsigned short* roff = &s.rowoff[VT_HALO];
     constexpr int VROW = VT_MAX_BINS + 2 * VT_HALO;          // Vc1 = Vc0 + VROW
-    // table entry for (source row, same|switch, offset 0 <= o < W), any row
-    auto lt_row = [&](int brow, int sel, int o) -> double {
-        const unsigned off = roff[brow];
-        if (!(off & VT_EDGE_BIT)) return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(&s.lt[0][sel][VT_LT_PAD + o]) + off);
-        return __ldg(p.lt_variants + (off & 0x7FFFu) + sel * W + o);
-    };
+    auto lt_row = [&](int brow, int sel, int o) -> double { return lt_entry<W>(s, p, brow, sel, o); };
 
     // ---- lower bound L: the candidates from this destination's own bin, and from the source that won in the previous frame
     // (decoded paths move slowly, so that real candidate is usually (near) optimal and prunes almost every chunk)
@@ -295,9 +310,18 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
         s.prev[0][i] = static_cast<unsigned short>(min(i, n - 1));
         s.prev[1][i] = static_cast<unsigned short>(n + min(i, n - 1));
     }
-    if (b < 3) s.cand_windows[b] = 0u;
+    if (b < 3) { s.cand_windows[b] = 0u; s.cand_n[b] = 0; }
     if (b < 2) s.next_task[b] = 0;
+    if (b == 0) s.lt_max = NEG_INF;
     __syncthreads();
+    {   // largest finite log transition (all entries are negative: the bit pattern shrinks as the value grows)
+        double m = NEG_INF;
+        for (int i = b; i < p.n_variants * 2 * W; i += NT) {
+            const double v = __ldg(p.lt_variants + i);
+            if (v > m) m = v;
+        }
+        atomicMin(reinterpret_cast<unsigned long long*>(&s.lt_max), static_cast<unsigned long long>(__double_as_longlong(m)));
+    }
     for (int i = b; i < nsv * 2 * W; i += NT) {
         const int var = i / (2 * W), rem = i - var * 2 * W;
         s.lt[var][rem / W][VT_LT_PAD + rem % W] = __ldg(p.lt_variants + i);
@@ -358,9 +382,12 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
         const int cnt = min(__ldg(ccnt), p.max_cand);
         for (int i = b; i < cnt; i += NT) {
             const int bin = cbin[i];
-            s.obs_lp[0][bin] = log(cprob[i] + DBL_MIN);
+            const double v = log(cprob[i] + DBL_MIN);
+            s.obs_lp[0][bin] = v;
             atomicOr(&s.cand_windows[0], 1u << (bin >> 5));
+            if (i < 32) { s.cand_bin[0][i] = static_cast<unsigned short>(bin); s.cand_lp[0][i] = v; }
         }
+        if (b == 0) s.cand_n[0] = cnt;
     }
     __syncthreads();
 
@@ -377,11 +404,11 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
         const unsigned hmin = __reduce_min_sync(0xffffffffu, static_cast<unsigned>(__double2hiint(xv)));
         if (lane == 0) s.seg_hi[nxt][v][win] = hmin;
     };
-    auto publish_empty = [&](const int nxt, const int win) {   // a window whose voiced states are all dominated
+    auto publish_empty = [&](const int nxt, const int v, const int win) {   // a window whose states of voicing v are all dominated
         const int d = 32 * win + lane;
-        if (d < n) s.V[nxt][0][VT_HALO + d] = NEG_INF;
-        if ((lane & 7) == 0) s.M[nxt][0][(d >> 3) + VT_CHUNK_PAD] = NEG_INF;
-        if (lane == 0) s.seg_hi[nxt][0][win] = 0xFFF00000u;
+        if (d < n) s.V[nxt][v][VT_HALO + d] = NEG_INF;
+        if ((lane & 7) == 0) s.M[nxt][v][(d >> 3) + VT_CHUNK_PAD] = NEG_INF;
+        if (lane == 0) s.seg_hi[nxt][v][win] = 0xFFF00000u;
     };
 
     for (int t = 0; t < T; ++t) {
@@ -422,9 +449,34 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
             // then only the windows that hold a candidate compute voiced destinations.
             const bool dense_v = !(lp_u > LOGTINY + 10.0);
             const unsigned all_win = n_win >= 32 ? 0xFFFFFFFFu : ((1u << n_win) - 1u);
-            const unsigned vmask = dense_v ? all_win : s.cand_windows[t % 3];
+            const unsigned cmask = s.cand_windows[t % 3];
+            // COLLAPSE test (see the file header): inputs are V[t-1] and the candidate lists of frames t-1 and t only
+            bool collapse = false;
+            if (dense_v) {
+                const int K = s.cand_n[t % 3], Kp = s.cand_n[(t + 2) % 3];
+                if (K >= 1 && K <= 32 && Kp <= 32) {
+                    double lb = NEG_INF;
+                    if (lane < K) {
+                        const int c = s.cand_bin[t % 3][lane];
+                        // a real candidate of (voiced, c): its own bin's unvoiced state, or a candidate state of frame t-1 in band
+                        double L = s.V[cur][1][VT_HALO + c] + lt_entry<W>(s, p, c, 1, hw);
+                        for (int k = 0; k < Kp; ++k) {
+                            const int cp = s.cand_bin[(t + 2) % 3][k];
+                            const int o = c - cp + hw;
+                            if (o >= 0 && o < W) L = dmax(L, s.V[cur][0][VT_HALO + cp] + lt_entry<W>(s, p, cp, 0, o));
+                        }
+                        lb = s.cand_lp[t % 3][lane] + L;
+                    }
+                    const double lbmax = warp_max_d(lb);
+                    const unsigned h = lane < n_win ? min(s.seg_hi[cur][0][lane], s.seg_hi[cur][1][lane]) : 0xFFFFFFFFu;
+                    const double vmax_ub = upper_bound_from_hi(__reduce_min_sync(0xffffffffu, h));
+                    collapse = lbmax + LOGTINY > lp_u + vmax_ub + 2.0 * s.lt_max + 1e-6;
+                }
+            }
+            const bool all_voiced = dense_v && !collapse;       // every voiced destination is computed and kept
+            const unsigned vmask = all_voiced ? all_win : cmask;
             const int n_voiced = __popc(vmask);
-            const int n_tasks = n_voiced + n_win;
+            const int n_tasks = n_voiced + (collapse ? 0 : n_win);
             // tasks 0 .. n_voiced-1: voiced destinations of the windows in vmask; then the unvoiced destinations of every
             // window, edge windows first (their tables sit in global memory: the longest tasks start first)
             while (true) {
@@ -437,7 +489,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                     dv = 0;
                     unsigned m = vmask;   // the task-th set bit
                     for (int k = 0; k < task; ++k) m &= m - 1;
-                    win = dense_v ? task : __ffs(m) - 1;
+                    win = all_voiced ? task : __ffs(m) - 1;
                 } else {
                     dv = 1;
                     const int k = task - n_voiced;
@@ -456,7 +508,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                         s.prev[1][d] = static_cast<unsigned short>(arg);
                     }
                     if (!((vmask >> win) & 1u)) {   // nobody computes this window's voiced states
-                        publish_empty(nxt, win);
+                        publish_empty(nxt, 0, win);
                         if (fv && live) fv[d] = NEG_INF;
                     }
                 } else {
@@ -464,7 +516,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                         const double lp_v = s.obs_lp[cur][d];
                         s.obs_lp[cur][d] = LOGTINY;   // reset for frame t+2
                         s.prev[0][d] = static_cast<unsigned short>(arg);
-                        if (dense_v || lp_v > LOGTINY) {
+                        if (all_voiced || lp_v > LOGTINY) {
                             vnew = lp_v + best;
                             bp_row[d] = static_cast<unsigned short>(arg);
                         }
@@ -472,6 +524,17 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                 }
                 publish(nxt, dv, win, vnew);
                 if (fv && live) fv[dv * n + d] = vnew;
+            }
+            if (collapse) {   // everything that was not computed is dominated: -inf, no back-pointer
+                for (int win = warp; win < n_win; win += NW) {
+                    const int d = 32 * win + lane;
+                    publish_empty(nxt, 1, win);
+                    if (fv && d < n) fv[n + d] = NEG_INF;
+                    if (!((vmask >> win) & 1u)) {
+                        publish_empty(nxt, 0, win);
+                        if (fv && d < n) fv[d] = NEG_INF;
+                    }
+                }
             }
         }
         // logs of the NEXT frame's observations, one copy of the (long) double-precision log: pass 0 the candidates
@@ -487,8 +550,10 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                     if (pass == 0) {
                         s.obs_lp[nxt][nbin] = v;
                         atomicOr(&s.cand_windows[(t + 1) % 3], 1u << (nbin >> 5));
+                        if (b < 32) { s.cand_bin[(t + 1) % 3][b] = static_cast<unsigned short>(nbin); s.cand_lp[(t + 1) % 3][b] = v; }
                     } else {
                         s.lp_u[nxt] = v;
+                        s.cand_n[(t + 1) % 3] = ncnt;
                     }
                 }
             }
