@@ -207,7 +207,7 @@ __device__ __forceinline__ void viterbi_task(const VitSmem& s, const aegis_viter
         {
             const int r = lane < NCHW ? lane : 0;
             pb = lane < NCHW ? Mrow[r] + s.ubrmax[sel][r] : NEG_INF;
-            mask = __ballot_sync(0xffffffffu, pb >= Lmin);
+            mask = __ballot_sync(0xffffffffu, lane < NCHW && pb >= Lmin);   // (-inf >= -inf holds: the lane test is not redundant)
         }
         const double* ubr_l = &s.ubr[sel][VT_UBR_PAD + ohi0];      // this lane's bound for window chunk r: ubr_l[-8 r]
         // shared address of this lane's table entry for (variant 0, window chunk 0, source 0); chunk r, source j of a row
@@ -471,6 +471,9 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                     const unsigned h = lane < n_win ? min(s.seg_hi[cur][0][lane], s.seg_hi[cur][1][lane]) : 0xFFFFFFFFu;
                     const double vmax_ub = upper_bound_from_hi(__reduce_min_sync(0xffffffffu, h));
                     collapse = lbmax + LOGTINY > lp_u + vmax_ub + 2.0 * s.lt_max + 1e-6;
+#ifdef VT_NO_COLLAPSE   // A/B builds only
+                    collapse = false;
+#endif
                 }
             }
             const bool all_voiced = dense_v && !collapse;       // every voiced destination is computed and kept
