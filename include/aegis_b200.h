@@ -28,7 +28,7 @@ extern "C" {
 
 #define AEGIS_N_FFT 2048
 #define AEGIS_N_BINS 1025
-#define AEGIS_ABI_VERSION 1
+#define AEGIS_ABI_VERSION 2
 
 int aegis_abi_version(void);
 const char* aegis_last_error(void);
@@ -157,9 +157,13 @@ typedef struct {
     double* voiced_prob;       /* [n_clips * n_frames] */
     int32_t* overflow;         /* [1]: set non-zero if any frame had more than max_cand candidates */
     double* cmnd_out;          /* optional [n_clips * n_frames][max_period - min_period + 1] CMND curves, or NULL */
+    float* block_sums;         /* optional workspace of aegis_yin_workspace_bytes(...) bytes (hop 512 only): with it the
+                                  autocorrelation block sums and the per-frame stage run as two kernels (faster: the second
+                                  runs at full occupancy); NULL = one fused kernel, same results */
 } aegis_yin_params;
 
 int aegis_yin_candidates(const aegis_yin_params* p, void* stream);
+long long aegis_yin_workspace_bytes(int n_clips, int n_frames, int max_period);
 
 /* ---------------------------------------------------------------------------------------------
  * K3  pitch/voicing HMM Viterbi decode (2*n_pitch_bins states, banded transitions, exact

@@ -11,7 +11,7 @@ import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AEGIS_B200_LIB") or os.path.join(PKG_DIR, "libaegis_b200.so")  # the override is for kernel A/B experiments
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _f32p = C.c_void_p
 _ptr = C.c_void_p
@@ -61,7 +61,7 @@ class YinParams(C.Structure):
         ("thresholds", _ptr), ("beta_probs", _ptr), ("beta_cumsum", _ptr),
         ("boltz_fact", _ptr), ("boltz_exp", _ptr), ("no_trough_prob", f64),
         ("cand_bin", _ptr), ("cand_prob", _ptr), ("cand_count", _ptr), ("voiced_prob", _ptr),
-        ("overflow", _ptr), ("cmnd_out", _ptr),
+        ("overflow", _ptr), ("cmnd_out", _ptr), ("block_sums", _ptr),
     ]
 
 
@@ -197,6 +197,8 @@ def load() -> C.CDLL:
     lib.aegis_device_sm_count.restype = C.c_int
     lib.aegis_note_events_bytes.restype = C.c_longlong
     lib.aegis_note_events_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.aegis_yin_workspace_bytes.restype = C.c_longlong
+    lib.aegis_yin_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.aegis_fin_scratch_bytes.restype = C.c_longlong
     lib.aegis_fin_scratch_bytes.argtypes = [C.c_int, C.c_int]
     for name in ("aegis_smf_write_v1", "aegis_smf_write_v2"):

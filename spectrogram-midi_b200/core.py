@@ -210,8 +210,9 @@ def onset_peaks(onset_env: torch.Tensor, env_minmax: torch.Tensor, *, sr: float,
 # ----------------------------------------------------------------------------------------------
 def yin_candidates(y: torch.Tensor, cfg: tables.PyinConfig, *, center: bool = True,
                    max_cand: Optional[int] = None, pad: Optional[int] = None, n_frames: Optional[int] = None,
-                   want_cmnd: bool = False) -> dict:
-    """Sparse pYIN observations per frame (bins ascending, unique) + voiced probability."""
+                   want_cmnd: bool = False, split: bool = True) -> dict:
+    """Sparse pYIN observations per frame (bins ascending, unique) + voiced probability.  ``split=False`` withholds the
+    block-sum workspace, so hop 512 runs as one fused kernel instead of two (identical results; for tests)."""
     _check_fft(cfg.frame_length, cfg.hop_length)
     y = _check_audio(y)
     dev = y.device
@@ -242,6 +243,11 @@ def yin_candidates(y: torch.Tensor, cfg: tables.PyinConfig, *, center: bool = Tr
     overflow = torch.zeros((1,), dtype=torch.int32, device=dev)
     P.cand_bin, P.cand_prob, P.cand_count = cand_bin.data_ptr(), cand_prob.data_ptr(), cand_count.data_ptr()
     P.voiced_prob, P.overflow = voiced_prob.data_ptr(), overflow.data_ptr()
+    work = None
+    if split and cfg.hop_length == 512 and n_fr > 0:   # block-sum workspace: the two-kernel form of K2 (same results as the fused one)
+        nbytes = int(nat.load().aegis_yin_workspace_bytes(n_clips, T, cfg.max_period))
+        work = torch.empty(((nbytes + 3) // 4,), dtype=torch.float32, device=dev)
+        P.block_sums = work.data_ptr()
     cmnd = None
     if want_cmnd:
         cmnd = torch.empty((n_fr, cfg.n_lags), dtype=torch.float64, device=dev)

@@ -568,6 +568,170 @@ yin_direct_kernel(const aegis_yin_params p, const YinDirectLayout lay, const int
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// hop == 512, two kernels (used when the caller provides the block-sum workspace): the FMA-bound block sums at 128
+// registers per thread, then everything per frame at high occupancy (the energy / CMND / candidate stage is a chain of
+// short dependent steps: it wants warps, not registers).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int YS_SPAN_MAX = YD_BLOCKS * 512 + 1 + 16 * 64;                // 16 blocks + look-ahead of the widest lag range
+constexpr int YS_PHYS = YS_SPAN_MAX + YS_SPAN_MAX / 16 + 32;
+
+// block sums of blocks [16 run, 16 run + 16) of a clip -> bsum[clip][block][b_pitch]
+__global__ void __launch_bounds__(YD_THREADS, 2)
+yin_blocksum_kernel(const aegis_yin_params p, const int n_groups, const int b_pitch, const int runs_per_clip, const int n_blocks) {
+    __shared__ float xs[YS_PHYS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int clip = blockIdx.x / runs_per_clip;
+    const int k0 = (blockIdx.x - clip * runs_per_clip) * YD_BLOCKS;          // first block of this run
+    const long long N = p.n_samples;
+    const float* __restrict__ yc = p.y + static_cast<long long>(clip) * p.clip_stride;
+    const long long g0 = static_cast<long long>(k0) * 512 - p.pad;           // clip sample of m = 0; block b = m in [512 b + 1, 512 b + 512]
+    const int span = YD_BLOCKS * 512 + 1 + 16 * n_groups;
+    for (int m = tid; m < span; m += YD_THREADS) {
+        const long long gi = g0 + m;
+        xs[m + (m >> 4)] = (gi >= 0 && gi < N) ? __ldg(yc + gi) : 0.f;
+    }
+    __syncthreads();
+    if (k0 + 2 * warp >= n_blocks) return;                                    // no barrier follows
+    const float* pa = xs + 544 * (2 * warp) + 17 * lane + 1;                 // phys(512 b + 1 + 16 l); block 2w+1 is 544 words further
+    unsigned long long a[16], R[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int o = i + ((1 + i) >> 4);
+        a[i] = pack2(pa[o], pa[544 + o]);
+        R[i] = a[i];
+    }
+    const int kb = k0 + 2 * warp + (lane >> 4);                               // the block this lane stores
+    float* brow = p.block_sums + (static_cast<long long>(clip) * n_blocks + min(kb, n_blocks - 1)) * b_pitch + (lane & 15);
+    const bool store = kb < n_blocks;
+    const bool hi_half = (lane & 16) != 0;
+#pragma unroll 1
+    for (int g = 0; g < n_groups; ++g) {
+        const float* pw = pa + 17 * g;
+        unsigned long long c[16];
+#pragma unroll
+        for (int s_ = 0; s_ < 16; ++s_) {
+            unsigned long long acc = 0ull;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc = ffma2(a[i], R[(s_ + i) & 15], acc);
+            c[s_] = acc;
+            const int o = s_ + 17 + (s_ == 15 ? 1 : 0);
+            R[s_] = pack2(pw[o], pw[544 + o]);
+        }
+        float v[16];
+#pragma unroll
+        for (int s_ = 0; s_ < 16; ++s_) {
+            float lo, hi;
+            unpack2(c[s_], lo, hi);
+            const float mine = hi_half ? hi : lo, other = hi_half ? lo : hi;
+            v[s_] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+        }
+#pragma unroll
+        for (int w_ = 8; w_ >= 1; w_ >>= 1) {
+            const bool up = (lane & w_) != 0;
+#pragma unroll
+            for (int s_ = 0; s_ < w_; ++s_) {
+                const float keep = up ? v[s_ + w_] : v[s_], send = up ? v[s_] : v[s_ + w_];
+                v[s_] = keep + __shfl_xor_sync(0xffffffffu, send, w_);
+            }
+        }
+        if (store) brow[16 * g] = v[0];
+    }
+}
+
+constexpr int YF_WARPS = 8;   // frames per CTA of the per-frame kernel
+
+struct YinFrameLayout {
+    int b_pitch, n_blocks;
+    int span;                 // samples staged per CTA: 7 * 512 + 1025 + max_period
+    int off_b, off_warp, warp_bytes, off_d, off_tp, off_tk, off_tq, max_troughs, total_bytes;
+};
+
+__global__ void __launch_bounds__(32 * YF_WARPS)
+yin_frame_kernel(const aegis_yin_params p, const YinFrameLayout lay, const int groups_per_clip) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* xs = reinterpret_cast<float*>(smem_raw);
+    float* Bs = reinterpret_cast<float*>(smem_raw + lay.off_b);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int clip = blockIdx.x / groups_per_clip;
+    const int t0 = (blockIdx.x - clip * groups_per_clip) * YF_WARPS;
+    const int T = p.n_frames;
+    const long long N = p.n_samples;
+    const int maxp = p.max_period, minp = p.min_period;
+    const int L = maxp - minp + 1;
+    const float* __restrict__ yc = p.y + static_cast<long long>(clip) * p.clip_stride;
+    const long long g0 = static_cast<long long>(t0) * 512 - p.pad;
+    const int n_fr = min(YF_WARPS, T - t0);
+    const int m_end = 512 * (n_fr - 1) + 1025 + maxp;
+    for (int m = tid; m < m_end; m += 32 * YF_WARPS) {
+        const long long gi = g0 + m;
+        xs[m] = (gi >= 0 && gi < N) ? __ldg(yc + gi) : 0.f;
+    }
+    {   // block sums of blocks t0 .. t0 + n_fr
+        const float* src = p.block_sums + (static_cast<long long>(clip) * lay.n_blocks + t0) * lay.b_pitch;
+        const int cnt = (n_fr + 1) * lay.b_pitch;
+        for (int i = tid; i < cnt; i += 32 * YF_WARPS) Bs[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    if (warp >= n_fr) return;
+    unsigned char* wbase = smem_raw + lay.off_warp + warp * lay.warp_bytes;
+    double* yin = reinterpret_cast<double*>(wbase);
+    float* dbuf = reinterpret_cast<float*>(wbase + lay.off_d);
+    double* tp = reinterpret_cast<double*>(wbase + lay.off_tp);
+    unsigned short* tk = reinterpret_cast<unsigned short*>(wbase + lay.off_tk);
+    unsigned char* tq = wbase + lay.off_tq;
+    const int fr = warp, t = t0 + fr;
+    const float* f = xs + 512 * fr;                       // frame sample j = f[j]
+    double acc = 0.0;
+#pragma unroll 4
+    for (int j = 1 + lane; j <= FFT_N / 2; j += 32) { const float v = f[j]; acc += static_cast<double>(v * v); }
+    const double e0 = warp_sum_d(acc);
+    const int chunk = (maxp + 31) / 32;
+    const int lo = 1 + lane * chunk, hi = min(lo + chunk, maxp + 1);
+    double run = 0.0;
+#pragma unroll 1
+    for (int tau = lo; tau < hi; ++tau) {
+        const float u1 = f[FFT_N / 2 + tau], u0 = f[tau];
+        run += static_cast<double>(u1 * u1) - static_cast<double>(u0 * u0);
+    }
+    double incl = warp_scan_incl_d(run, lane);
+    double base = e0 + (incl - run);
+    float e0f = static_cast<float>(e0);
+    if (fabsf(e0f) < 1e-6f) e0f = 0.f;
+    const float* B0 = Bs + fr * lay.b_pitch;
+    const float* B1 = B0 + lay.b_pitch;
+    run = 0.0;
+    double dsum = 0.0;
+#pragma unroll 1
+    for (int tau = lo; tau < hi; ++tau) {
+        const float u1 = f[FFT_N / 2 + tau], u0 = f[tau];
+        run += static_cast<double>(u1 * u1) - static_cast<double>(u0 * u0);
+        float e = static_cast<float>(base + run);
+        if (fabsf(e) < 1e-6f) e = 0.f;
+        float acf = B0[tau] + B1[tau];
+        if (fabsf(acf) < 1e-6f) acf = 0.f;
+        const float dv = (e0f + e) - 2.0f * acf;
+        dbuf[tau] = dv;
+        dsum += static_cast<double>(dv);
+    }
+    incl = warp_scan_incl_d(dsum, lane);
+    base = incl - dsum;
+    run = 0.0;
+#pragma unroll 1
+    for (int tau = lo; tau < hi; ++tau) {
+        run += static_cast<double>(dbuf[tau]);
+        if (tau >= minp) {
+            const double cm = static_cast<double>(static_cast<float>(base + run)) / static_cast<double>(tau);
+            const double yv = static_cast<double>(dbuf[tau]) / (cm + DBL_MIN);
+            yin[tau - minp] = yv;
+            if (p.cmnd_out != nullptr) p.cmnd_out[(static_cast<long long>(clip) * T + t) * L + (tau - minp)] = yv;
+        }
+    }
+    __syncwarp();
+    yin_candidates_of_frame(p, yin, L, minp, tk, tq, tp, lay.max_troughs, static_cast<long long>(clip) * T + t, lane);
+}
+
 }  // namespace aegis
 
 extern "C" int aegis_yin_candidates(const aegis_yin_params* p, void* stream) {
@@ -583,7 +747,43 @@ extern "C" int aegis_yin_candidates(const aegis_yin_params* p, void* stream) {
                   "aegis_yin_candidates: outputs missing");
     if (p->n_clips == 0 || p->n_frames == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (p->hop == 512) {   // the reference's hop: direct block-sum autocorrelation
+    if (p->hop == 512 && p->block_sums != nullptr) {   // the reference's hop, workspace given: block sums, then the per-frame stage
+        const int L = p->max_period - p->min_period + 1;
+        const int n_groups = (p->max_period + 1 + 15) / 16;
+        const int b_pitch = n_groups * 16;
+        const int n_blocks = p->n_frames + 1;
+        const int runs_per_clip = (n_blocks + YD_BLOCKS - 1) / YD_BLOCKS;
+        const long long n_runs = static_cast<long long>(runs_per_clip) * p->n_clips;
+        AEGIS_REQUIRE(n_runs < (1ll << 31), "aegis_yin_candidates: too many block runs for one launch");
+        yin_blocksum_kernel<<<static_cast<unsigned>(n_runs), YD_THREADS, 0, st>>>(*p, n_groups, b_pitch, runs_per_clip, n_blocks);
+        if (int rc = check_launch("aegis_yin_candidates(block sums)")) return rc;
+        YinFrameLayout lay{};
+        lay.b_pitch = b_pitch;
+        lay.n_blocks = n_blocks;
+        lay.span = 512 * (YF_WARPS - 1) + 1025 + p->max_period;
+        lay.off_b = ((lay.span * 4 + 15) / 16) * 16;
+        lay.off_warp = lay.off_b + (((YF_WARPS + 1) * b_pitch * 4 + 15) / 16) * 16;
+        lay.max_troughs = L / 2 + 1 < YIN_MAX_TROUGHS ? L / 2 + 1 : YIN_MAX_TROUGHS;
+        int o = ((L * 8 + 15) / 16) * 16;
+        lay.off_d = o;       o += (((p->max_period + 1) * 4 + 15) / 16) * 16;
+        lay.off_tp = o;      o += ((lay.max_troughs * 8 + 15) / 16) * 16;
+        lay.off_tk = o;      o += ((lay.max_troughs * 2 + 15) / 16) * 16;
+        lay.off_tq = o;      o += ((lay.max_troughs + 15) / 16) * 16;
+        lay.warp_bytes = o;
+        lay.total_bytes = lay.off_warp + YF_WARPS * lay.warp_bytes;
+        AEGIS_REQUIRE(lay.total_bytes <= 227 * 1024, "aegis_yin_candidates: %d B shared memory needed for max_period=%d", lay.total_bytes, p->max_period);
+        cudaError_t e = cudaFuncSetAttribute(yin_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total_bytes);
+        if (e != cudaSuccess) {
+            set_error("aegis_yin_candidates: cannot reserve %d B shared memory: %s", lay.total_bytes, cudaGetErrorString(e));
+            return 2;
+        }
+        const int groups_per_clip = (p->n_frames + YF_WARPS - 1) / YF_WARPS;
+        const long long n_groups_total = static_cast<long long>(groups_per_clip) * p->n_clips;
+        AEGIS_REQUIRE(n_groups_total < (1ll << 31), "aegis_yin_candidates: too many frame groups for one launch");
+        yin_frame_kernel<<<static_cast<unsigned>(n_groups_total), 32 * YF_WARPS, lay.total_bytes, st>>>(*p, lay, groups_per_clip);
+        return check_launch("aegis_yin_candidates(frames)");
+    }
+    if (p->hop == 512) {   // no workspace: one kernel does both stages (15 frames per CTA)
         YinDirectLayout lay{};
         const int L = p->max_period - p->min_period + 1;
         lay.n_groups = (p->max_period + 1 + 15) / 16;
@@ -621,4 +821,11 @@ extern "C" int aegis_yin_candidates(const aegis_yin_params* p, void* stream) {
     const int grid = static_cast<int>(n_pairs < max_grid ? n_pairs : max_grid);
     yin_fft_kernel<<<grid, YIN_THREADS, sizeof(YinSmem), st>>>(*p, pairs_per_clip, n_pairs);
     return check_launch("aegis_yin_candidates");
+}
+
+// bytes of the block-sum workspace of aegis_yin_candidates (hop 512): (n_frames + 1) rows of 16 * ceil((max_period + 1) / 16) floats per clip
+extern "C" long long aegis_yin_workspace_bytes(int n_clips, int n_frames, int max_period) {
+    if (n_clips <= 0 || n_frames <= 0 || max_period < 0) return 0;
+    const long long pitch = 16LL * ((max_period + 1 + 15) / 16);
+    return static_cast<long long>(n_clips) * (n_frames + 1) * pitch * 4;
 }

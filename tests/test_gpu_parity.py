@@ -423,6 +423,28 @@ def test_pyin_tables_are_not_aliased_across_hmm_parameters(dev):
         assert (np.abs(1200 * np.log2(g[vf] / f0[vf])) <= 1.0).all(), kw
 
 
+def test_yin_fused_and_split_kernels_agree_bit_for_bit(dev):
+    """K2 at hop 512 has two forms: block sums + per-frame stage as two kernels (with the workspace) or one fused kernel
+    (without).  A block sum depends only on its own samples and is summed in one fixed order, so both forms -- and any
+    batch / window a frame is analysed in -- give identical bits.  Other hops take the FFT kernel (not bit-equal)."""
+    for sr in (22050, 44100):
+        y = np.stack([corpus.random_clip(40 + i, 3.0, sr) for i in range(3)])
+        y[2, 20000:] = 0.0
+        cfg = tables.pyin_config(float(sr), 512, E2, C6)
+        yd = _dev(y, dev)
+        a = P.core.yin_candidates(yd, cfg, want_cmnd=True)
+        b = P.core.yin_candidates(yd, cfg, want_cmnd=True, split=False)
+        one = P.core.yin_candidates(yd[1:2], cfg, want_cmnd=True)
+        for k in ("cand_count", "voiced_prob", "cmnd"):
+            assert torch.equal(a[k], b[k]), (sr, k)
+        T = a["n_frames"]
+        cnt = a["cand_count"].view(3, T)
+        m = torch.arange(a["max_cand"], device=dev)[None, None, :] < cnt[:, :, None]
+        for k in ("cand_bin", "cand_prob"):
+            assert torch.equal(a[k].view(3, T, -1)[m], b[k].view(3, T, -1)[m]), (sr, k)
+        assert torch.equal(a["cmnd"][1], one["cmnd"][0]) and torch.equal(a["voiced_prob"][1], one["voiced_prob"][0])
+
+
 def test_pyin_batch_equals_single_and_handles_silence(dev):
     clips = corpus.clip_batch(3, 4.0, 22050, first_seed=40)
     clips[1] = 0.0
