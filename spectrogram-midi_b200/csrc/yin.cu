@@ -87,7 +87,18 @@ __device__ __forceinline__ void fft_finish_inplace(int lt, cf* v, const FftTwidd
 // Candidate stage of one frame by one warp (librosa __pyin_helper): troughs of the CMND curve
 // yv[0..L), their probabilities over the beta-weighted thresholds with the Boltzmann prior on the trough rank, parabolic
 // refinement, 10-cent bins; writes the frame's sparse observation (bins ascending, unique) and its voiced probability.
-__device__ __forceinline__ void yin_candidates_of_frame(const aegis_yin_params& p, const double* yv, const int L, const int minp,
+struct YinTables {   // the prior tables: global pointers (read through the read-only path) or copies in shared memory
+    const double* thresholds;
+    const double* beta_probs;
+    const double* beta_cumsum;
+    const double* boltz_fact;
+    const double* boltz_exp;
+};
+template <bool SHARED>
+__device__ __forceinline__ double tab(const double* q) { return SHARED ? *q : __ldg(q); }
+
+template <bool SHARED>
+__device__ __forceinline__ void yin_candidates_of_frame(const aegis_yin_params& p, const YinTables& tb, const double* yv, const int L, const int minp,
                                             unsigned short* tk, unsigned char* tq, double* tp, const int max_troughs,
                                             const long long fidx, const int lane) {
     // 1. troughs, compacted in lag order
@@ -121,8 +132,8 @@ __device__ __forceinline__ void yin_candidates_of_frame(const aegis_yin_params& 
             const double h = yv[tk[i]];
             int q = (h >= 1.0) ? nth : ((h <= 0.0) ? 0 : static_cast<int>(h * nth));  // guess, then fix
             q = max(0, min(q, nth));
-            while (q > 0 && h < __ldg(p.thresholds + q - 1)) --q;
-            while (q < nth && !(h < __ldg(p.thresholds + q))) ++q;
+            while (q > 0 && h < tab<SHARED>(tb.thresholds + q - 1)) --q;
+            while (q < nth && !(h < tab<SHARED>(tb.thresholds + q))) ++q;
             tq[i] = static_cast<unsigned char>(q);
             tp[i] = 0.0;
             if (h < best_h) { best_h = h; best_i = i; }
@@ -145,7 +156,7 @@ __device__ __forceinline__ void yin_candidates_of_frame(const aegis_yin_params& 
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int j = lane + 32 * r;
-            fj[r] = (j < nth && nj[r] > 0) ? __ldg(p.boltz_fact + nj[r]) : 0.0;
+            fj[r] = (j < nth && nj[r] > 0) ? tab<SHARED>(tb.boltz_fact + nj[r]) : 0.0;
         }
         // 4. probability of each trough: sum_j prior(rank among troughs below th_j) * beta_j
         for (int i = 0; i < nt; ++i) {
@@ -156,7 +167,7 @@ __device__ __forceinline__ void yin_candidates_of_frame(const aegis_yin_params& 
             for (int r = 0; r < 4; ++r) {
                 const int j = lane + 32 * r;
                 if (j < nth && q <= j) {
-                    c += (fj[r] * __ldg(p.boltz_exp + pj[r])) * __ldg(p.beta_probs + j);
+                    c += (fj[r] * tab<SHARED>(tb.boltz_exp + pj[r])) * tab<SHARED>(tb.beta_probs + j);
                     ++pj[r];
                 }
             }
@@ -166,7 +177,7 @@ __device__ __forceinline__ void yin_candidates_of_frame(const aegis_yin_params& 
         __syncwarp();
         // 5. every lane turns its troughs' lags into pitch bins (parabolic refinement, log2: the expensive
         //    part, in parallel; tk[] is overwritten with the bin, 0xffff = not a candidate) ...
-        if (lane == 0) tp[best_i] += p.no_trough_prob * __ldg(p.beta_cumsum + tq[best_i]);
+        if (lane == 0) tp[best_i] += p.no_trough_prob * tab<SHARED>(tb.beta_cumsum + tq[best_i]);
         __syncwarp();
         {
             const double scale = 12.0 * p.bins_per_semitone;
@@ -380,7 +391,8 @@ yin_fft_kernel(const aegis_yin_params p, const int pairs_per_clip, const long lo
             const int fr = warp >> 1;
             const int t = t0 + fr;
             if (t < T) {
-                yin_candidates_of_frame(p, se.yin[fr], L, minp, sc.tk[fr], sc.tq[fr], sc.tp[fr], YIN_MAX_TROUGHS,
+                const YinTables tb{p.thresholds, p.beta_probs, p.beta_cumsum, p.boltz_fact, p.boltz_exp};
+                yin_candidates_of_frame<false>(p, tb, se.yin[fr], L, minp, sc.tk[fr], sc.tq[fr], sc.tp[fr], YIN_MAX_TROUGHS,
                                         static_cast<long long>(clip) * T + t, lane);
             }
         }
@@ -563,7 +575,8 @@ yin_direct_kernel(const aegis_yin_params p, const YinDirectLayout lay, const int
             }
         }
         __syncwarp();
-        yin_candidates_of_frame(p, yin, L, minp, tk, tq, tp, lay.max_troughs, static_cast<long long>(clip) * T + t, lane);
+        const YinTables tb{p.thresholds, p.beta_probs, p.beta_cumsum, p.boltz_fact, p.boltz_exp};
+        yin_candidates_of_frame<false>(p, tb, yin, L, minp, tk, tq, tp, lay.max_troughs, static_cast<long long>(clip) * T + t, lane);
         __syncwarp();
     }
 }
@@ -645,7 +658,7 @@ constexpr int YF_WARPS = 8;   // frames per CTA of the per-frame kernel
 struct YinFrameLayout {
     int b_pitch, n_blocks;
     int span;                 // samples staged per CTA: 7 * 512 + 1025 + max_period
-    int off_b, off_warp, warp_bytes, off_d, off_tp, off_tk, off_tq, max_troughs, total_bytes;
+    int off_b, off_tab, off_warp, warp_bytes, off_d, off_tp, off_tk, off_tq, max_troughs, total_bytes;
 };
 
 __global__ void __launch_bounds__(32 * YF_WARPS)
@@ -673,6 +686,13 @@ yin_frame_kernel(const aegis_yin_params p, const YinFrameLayout lay, const int g
         const int cnt = (n_fr + 1) * lay.b_pitch;
         for (int i = tid; i < cnt; i += 32 * YF_WARPS) Bs[i] = __ldg(src + i);
     }
+    // the prior tables, copied once per CTA: thresholds | beta_probs | beta_cumsum | boltz_fact | boltz_exp
+    double* tabs = reinterpret_cast<double*>(smem_raw + lay.off_tab);
+    const int nth = p.n_thresholds, nbz = lay.max_troughs + 1;
+    for (int i = tid; i < nth; i += 32 * YF_WARPS) { tabs[i] = __ldg(p.thresholds + i); tabs[nth + i] = __ldg(p.beta_probs + i); }
+    for (int i = tid; i <= nth; i += 32 * YF_WARPS) tabs[2 * nth + i] = __ldg(p.beta_cumsum + i);
+    for (int i = tid; i < nbz; i += 32 * YF_WARPS) { tabs[3 * nth + 1 + i] = __ldg(p.boltz_fact + i); tabs[3 * nth + 1 + nbz + i] = __ldg(p.boltz_exp + i); }
+    const YinTables tb{tabs, tabs + nth, tabs + 2 * nth, tabs + 3 * nth + 1, tabs + 3 * nth + 1 + nbz};
     __syncthreads();
     if (warp >= n_fr) return;
     unsigned char* wbase = smem_raw + lay.off_warp + warp * lay.warp_bytes;
@@ -729,7 +749,7 @@ yin_frame_kernel(const aegis_yin_params p, const YinFrameLayout lay, const int g
         }
     }
     __syncwarp();
-    yin_candidates_of_frame(p, yin, L, minp, tk, tq, tp, lay.max_troughs, static_cast<long long>(clip) * T + t, lane);
+    yin_candidates_of_frame<true>(p, tb, yin, L, minp, tk, tq, tp, lay.max_troughs, static_cast<long long>(clip) * T + t, lane);
 }
 
 }  // namespace aegis
@@ -762,8 +782,9 @@ extern "C" int aegis_yin_candidates(const aegis_yin_params* p, void* stream) {
         lay.n_blocks = n_blocks;
         lay.span = 512 * (YF_WARPS - 1) + 1025 + p->max_period;
         lay.off_b = ((lay.span * 4 + 15) / 16) * 16;
-        lay.off_warp = lay.off_b + (((YF_WARPS + 1) * b_pitch * 4 + 15) / 16) * 16;
         lay.max_troughs = L / 2 + 1 < YIN_MAX_TROUGHS ? L / 2 + 1 : YIN_MAX_TROUGHS;
+        lay.off_tab = lay.off_b + (((YF_WARPS + 1) * b_pitch * 4 + 15) / 16) * 16;
+        lay.off_warp = lay.off_tab + (((3 * p->n_thresholds + 1 + 2 * (lay.max_troughs + 1)) * 8 + 15) / 16) * 16;
         int o = ((L * 8 + 15) / 16) * 16;
         lay.off_d = o;       o += (((p->max_period + 1) * 4 + 15) / 16) * 16;
         lay.off_tp = o;      o += ((lay.max_troughs * 8 + 15) / 16) * 16;
