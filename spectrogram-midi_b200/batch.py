@@ -231,48 +231,89 @@ class TranscribePipeline:
     """Host-buffer plugin call for full transcription of a batch: 16-bit PCM (or float32) host audio in, the reference's
     perception arrays and the note-event records out.
 
-    The host batch travels in pieces of ``chunk_clips`` clips (one cudaMemcpyAsync each, round-robin over ``copy_streams``
-    copy streams) into a device buffer for the whole batch; the kernels run on GROUPS of ``group_clips`` clips as soon as a
-    group's pieces have landed -- a group defaults to four clips per SM, the number of Viterbi chains (one CTA each) that
-    are resident at once, so the sequential-over-frames decoder always runs full waves while later pieces are still on
-    the bus.  Per group: ingest (K9, when the host batch is PCM), ``analyze_batch`` (K1, K4, K2, K3: rake mask, pYIN, RMS
-    -- aegis_engine.py:41-75), ``note_events_batch`` (K7: get_midi_events, midi_logic.py:32-148), then D2H of ``rake_mask,
-    f0, voiced_flag, voiced_probs, rms`` (the dict of aegis_engine.py:72-75) and of the event records into pinned arrays.
+    The host batch travels in PIECES of ``chunk_clips`` clips (default: one clip per SM; one cudaMemcpyAsync each,
+    round-robin over ``copy_streams`` copy streams) into a device buffer for the whole batch.  The frame-parallel kernels
+    run on every piece as soon as it has landed, while later pieces are still on the bus: ingest (K9, when the host batch
+    is PCM), K1 + K4 (mel dB, rake mask, RMS) and K2 (pYIN observations, written into batch-wide buffers).  The decoder
+    is sequential over frames with one CTA per clip, four resident per SM, so K3 (Viterbi) and K7 (note events) run on
+    GROUPS of ``group_clips`` clips (default four pieces = four clips per SM: always full waves), then the group's
+    ``rake_mask, f0, voiced_flag, voiced_probs, rms`` (the dict of aegis_engine.py:72-75) and its event records go to
+    pinned host arrays.  Results equal ``analyze_batch`` + ``note_events_batch`` on the whole batch bit for bit.
     """
 
-    def __init__(self, n_clips: int, n_samples: int, *, sr: float, hop_length: int = 512, device=None, chunk_clips: int = 128,
-                 pcm: bool = True, copy_streams: int = 2, confidence_threshold: float = 0.7, group_clips: Optional[int] = None):
+    def __init__(self, n_clips: int, n_samples: int, *, sr: float, hop_length: int = 512, device=None, chunk_clips: Optional[int] = None,
+                 pcm: bool = True, copy_streams: int = 2, confidence_threshold: float = 0.7, group_clips: Optional[int] = None,
+                 fmin: float = E2, fmax: float = C6, rake_sensitivity: float = 0.6):
         from . import _native as nat
 
-        self.sr, self.hop, self.thr = sr, hop_length, confidence_threshold
+        self.sr, self.hop, self.thr, self.ratio = sr, hop_length, confidence_threshold, rake_sensitivity
+        self.fmin, self.fmax = fmin, fmax
         self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.n_clips, self.n_samples, self.pcm = n_clips, n_samples, pcm
-        self.chunk = max(1, min(chunk_clips, n_clips))
-        if group_clips is None:
-            with torch.cuda.device(self.dev):
-                group_clips = 4 * int(nat.load().aegis_device_sm_count())
-        self.group = max(self.chunk, min(group_clips, n_clips))
-        self.T = core.frame_count(n_samples, hop_length)
+        with torch.cuda.device(self.dev):
+            n_sm = int(nat.load().aegis_device_sm_count())
+        self.chunk = max(1, min(n_sm if chunk_clips is None else chunk_clips, n_clips))
+        self.group = max(self.chunk, min(4 * self.chunk if group_clips is None else group_clips, n_clips))
+        self.T = T = core.frame_count(n_samples, hop_length)
+        self.cfg = tables.pyin_config(float(sr), int(hop_length), float(fmin), float(fmax))
+        mc = self.cfg.max_troughs
         in_dtype = torch.int16 if pcm else torch.float32
         self.in_shape = (n_clips, n_samples)
-        self.inbuf = torch.empty(self.in_shape, dtype=in_dtype, device=self.dev)
-        self.copy_streams = [torch.cuda.Stream(device=self.dev) for _ in range(max(1, copy_streams))]
+        dev = self.dev
+        self.inbuf = torch.empty(self.in_shape, dtype=in_dtype, device=dev)
+        self.copy_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, copy_streams))]
         self.pieces = list(range(0, n_clips, self.chunk))
         self.landed = [torch.cuda.Event() for _ in self.pieces]
+        # batch-wide device buffers filled piece by piece
+        self.obs = {"cand_bin": torch.empty((n_clips * T, mc), dtype=torch.int16, device=dev),
+                    "cand_prob": torch.empty((n_clips * T, mc), dtype=torch.float64, device=dev),
+                    "cand_count": torch.empty((n_clips * T,), dtype=torch.int32, device=dev),
+                    "voiced_prob": torch.empty((n_clips, T), dtype=torch.float64, device=dev)}
+        self.rake = torch.empty((n_clips, T), dtype=torch.uint8, device=dev)
+        self.rms = torch.empty((n_clips, T), dtype=torch.float32, device=dev)
         min_frames, _ = core.note_frame_limits(sr, hop_length)
-        self.max_events = self.T // (min_frames + 1) + 1
+        self.max_events = T // (min_frames + 1) + 1
         pin = dict(pin_memory=True)
         self.out = {
-            "rake_mask": torch.empty((n_clips, self.T), dtype=torch.uint8, **pin),
-            "f0": torch.empty((n_clips, self.T), dtype=torch.float64, **pin),
-            "voiced_flag": torch.empty((n_clips, self.T), dtype=torch.uint8, **pin),
-            "voiced_probs": torch.empty((n_clips, self.T), dtype=torch.float64, **pin),
-            "rms": torch.empty((n_clips, self.T), dtype=torch.float32, **pin),
+            "rake_mask": torch.empty((n_clips, T), dtype=torch.uint8, **pin),
+            "f0": torch.empty((n_clips, T), dtype=torch.float64, **pin),
+            "voiced_flag": torch.empty((n_clips, T), dtype=torch.uint8, **pin),
+            "voiced_probs": torch.empty((n_clips, T), dtype=torch.float64, **pin),
+            "rms": torch.empty((n_clips, T), dtype=torch.float32, **pin),
             "events": torch.empty((n_clips, self.max_events, core.NOTE_EVENT_DTYPE.itemsize), dtype=torch.uint8, **pin),
             "n_events": torch.empty((n_clips,), dtype=torch.int32, **pin),
         }
         self.h2d_bytes = n_clips * n_samples * (2 if pcm else 4)
         self.d2h_bytes = sum(int(t.numel()) * t.element_size() for t in self.out.values())
+
+    def _piece(self, c0: int, c1: int):
+        """frame-parallel kernels of clips [c0, c1): K9, K1, K4, K2"""
+        T = self.T
+        yb = self.inbuf[c0:c1]
+        if self.pcm:
+            yb = core.resample_poly(yb, int(self.sr), int(self.sr))   # int16 -> float32 / 32768 on the device (K9)
+        spec = spectral_features(yb, sr=self.sr, hop_length=self.hop, rake_sensitivity=self.ratio, with_onsets=False)
+        self.rake[c0:c1].copy_(spec["rake_mask"])
+        self.rms[c0:c1].copy_(spec["rms"])
+        sl = slice(c0 * T, c1 * T)
+        core.yin_candidates(yb, self.cfg, out={"cand_bin": self.obs["cand_bin"][sl], "cand_prob": self.obs["cand_prob"][sl],
+                                               "cand_count": self.obs["cand_count"][sl], "voiced_prob": self.obs["voiced_prob"][c0:c1]})
+
+    def _group(self, g0: int, g1: int):
+        """decoder + logic filter of clips [g0, g1): K3, K7, then the results to the host"""
+        T = self.T
+        sl = slice(g0 * T, g1 * T)
+        obs = {"cand_bin": self.obs["cand_bin"][sl], "cand_prob": self.obs["cand_prob"][sl], "cand_count": self.obs["cand_count"][sl],
+               "voiced_prob": self.obs["voiced_prob"][g0:g1], "n_frames": T, "max_cand": self.cfg.max_troughs}
+        dec = core.viterbi_decode(obs, self.cfg, g1 - g0)
+        res = {"rake_mask": self.rake[g0:g1], "voiced_flag": dec["voiced_flag"], "voiced_probs": self.obs["voiced_prob"][g0:g1],
+               "rms": self.rms[g0:g1], "f0": torch.nan_to_num(dec["f0"], nan=0.0), "states": dec["states"]}
+        ev = note_events_batch(res, sr=self.sr, hop_length=self.hop, fmin=self.fmin, fmax=self.fmax, confidence_threshold=self.thr,
+                               max_events=self.max_events)
+        for k in ("rake_mask", "f0", "voiced_flag", "voiced_probs", "rms"):
+            self.out[k][g0:g1].copy_(res[k], non_blocking=True)
+        self.out["events"][g0:g1].copy_(ev["events"], non_blocking=True)
+        self.out["n_events"][g0:g1].copy_(ev["n_events"], non_blocking=True)
 
     def run(self, y_host: torch.Tensor) -> dict:
         if y_host.is_cuda or tuple(y_host.shape) != self.in_shape or y_host.dtype != self.inbuf.dtype:
@@ -287,19 +328,13 @@ class TranscribePipeline:
                     cs.wait_event(start)
                 self.inbuf[c0 : c0 + self.chunk].copy_(y_host[c0 : c0 + self.chunk], non_blocking=True)
                 self.landed[i].record(cs)
-        for g0 in range(0, self.n_clips, self.group):
-            g1 = min(self.n_clips, g0 + self.group)
-            for i, c0 in enumerate(self.pieces):
-                if c0 < g1 and c0 + self.chunk > g0:
-                    main.wait_event(self.landed[i])
-            yb = self.inbuf[g0:g1]
-            if self.pcm:
-                yb = core.resample_poly(yb, int(self.sr), int(self.sr))   # int16 -> float32 / 32768 on the device (K9)
-            res = analyze_batch(yb, sr=self.sr, hop_length=self.hop)
-            ev = note_events_batch(res, sr=self.sr, hop_length=self.hop, confidence_threshold=self.thr, max_events=self.max_events)
-            for k in ("rake_mask", "f0", "voiced_flag", "voiced_probs", "rms"):
-                self.out[k][g0:g1].copy_(res[k], non_blocking=True)
-            self.out["events"][g0:g1].copy_(ev["events"], non_blocking=True)
-            self.out["n_events"][g0:g1].copy_(ev["n_events"], non_blocking=True)
+        g0 = 0
+        for i, c0 in enumerate(self.pieces):
+            c1 = min(self.n_clips, c0 + self.chunk)
+            main.wait_event(self.landed[i])
+            self._piece(c0, c1)
+            if c1 - g0 >= self.group or c1 == self.n_clips:
+                self._group(g0, c1)
+                g0 = c1
         main.synchronize()
         return self.out

@@ -210,9 +210,11 @@ def onset_peaks(onset_env: torch.Tensor, env_minmax: torch.Tensor, *, sr: float,
 # ----------------------------------------------------------------------------------------------
 def yin_candidates(y: torch.Tensor, cfg: tables.PyinConfig, *, center: bool = True,
                    max_cand: Optional[int] = None, pad: Optional[int] = None, n_frames: Optional[int] = None,
-                   want_cmnd: bool = False, split: bool = True) -> dict:
+                   want_cmnd: bool = False, split: bool = True, out: Optional[dict] = None) -> dict:
     """Sparse pYIN observations per frame (bins ascending, unique) + voiced probability.  ``split=False`` withholds the
-    block-sum workspace, so hop 512 runs as one fused kernel instead of two (identical results; for tests)."""
+    block-sum workspace, so hop 512 runs as one fused kernel instead of two (identical results; for tests).  ``out`` may
+    hold preallocated ``cand_bin`` / ``cand_prob`` / ``cand_count`` / ``voiced_prob`` tensors for these clips (slices of
+    batch-wide buffers: ``batch.TranscribePipeline`` fills them piece by piece and decodes whole groups)."""
     _check_fft(cfg.frame_length, cfg.hop_length)
     y = _check_audio(y)
     dev = y.device
@@ -236,10 +238,19 @@ def yin_candidates(y: torch.Tensor, cfg: tables.PyinConfig, *, center: bool = Tr
     P.boltz_fact = _dev_tensor(key + ("bf",), dev, lambda: cfg.boltz_fact).data_ptr()
     P.boltz_exp = _dev_tensor(key + ("be",), dev, lambda: cfg.boltz_exp).data_ptr()
     P.no_trough_prob = cfg.no_trough_prob
-    cand_bin = torch.empty((n_fr, max_cand), dtype=torch.int16, device=dev)
-    cand_prob = torch.empty((n_fr, max_cand), dtype=torch.float64, device=dev)
-    cand_count = torch.empty((n_fr,), dtype=torch.int32, device=dev)
-    voiced_prob = torch.empty((n_fr,), dtype=torch.float64, device=dev)
+    if out is not None:
+        cand_bin, cand_prob, cand_count, voiced_prob = out["cand_bin"], out["cand_prob"], out["cand_count"], out["voiced_prob"].view(-1)
+        ok = (cand_bin.shape == (n_fr, max_cand) and cand_prob.shape == (n_fr, max_cand) and cand_count.shape == (n_fr,)
+              and voiced_prob.shape == (n_fr,) and cand_bin.dtype == torch.int16 and cand_prob.dtype == torch.float64
+              and cand_count.dtype == torch.int32 and voiced_prob.dtype == torch.float64
+              and all(t.is_contiguous() and t.device == dev for t in (cand_bin, cand_prob, cand_count, voiced_prob)))
+        if not ok:
+            raise ValueError("yin_candidates(out=...): buffers must be contiguous CUDA tensors of this call's shapes and dtypes")
+    else:
+        cand_bin = torch.empty((n_fr, max_cand), dtype=torch.int16, device=dev)
+        cand_prob = torch.empty((n_fr, max_cand), dtype=torch.float64, device=dev)
+        cand_count = torch.empty((n_fr,), dtype=torch.int32, device=dev)
+        voiced_prob = torch.empty((n_fr,), dtype=torch.float64, device=dev)
     overflow = torch.zeros((1,), dtype=torch.int32, device=dev)
     P.cand_bin, P.cand_prob, P.cand_count = cand_bin.data_ptr(), cand_prob.data_ptr(), cand_count.data_ptr()
     P.voiced_prob, P.overflow = voiced_prob.data_ptr(), overflow.data_ptr()

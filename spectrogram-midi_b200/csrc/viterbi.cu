@@ -48,6 +48,7 @@
 // high-word bounds rely on); K2 guarantees it.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace aegis {
@@ -601,8 +602,12 @@ static int launch_forward(const aegis_viterbi_params* p, cudaStream_t st) {
     const int n_win = (p->n_pitch_bins + 31) / 32;
     void (*kern)(const aegis_viterbi_params) = nullptr;
     int nw = 0;
-    if (n_win <= 14) { kern = viterbi_forward_kernel<HW, 7, 4>; nw = 7; }     // 441 bins (E2..C6): 7 warps, four clips per SM
-    else { kern = viterbi_forward_kernel<HW, 8, 4>; nw = 8; }                 // up to 512 bins
+    // warps per CTA (tasks are pulled dynamically, so any count works): A/B timed through AEGIS_VT_WARPS
+    static const int forced = []() { const char* e = getenv("AEGIS_VT_WARPS"); return e ? atoi(e) : 0; }();
+    nw = forced ? forced : (n_win <= 14 ? 7 : 8);
+    if (nw == 6) kern = viterbi_forward_kernel<HW, 6, 4>;
+    else if (nw == 7) kern = viterbi_forward_kernel<HW, 7, 4>;     // 441 bins (E2..C6): 7 warps, four clips per SM
+    else { kern = viterbi_forward_kernel<HW, 8, 4>; nw = 8; }      // up to 512 bins
     static_assert(sizeof(VitSmem) <= 48 * 1024, "VitSmem must fit static shared memory");
     kern<<<p->n_clips, 32 * nw, 0, st>>>(*p);
     return check_launch("aegis_viterbi(forward)");

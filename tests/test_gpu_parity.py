@@ -921,6 +921,32 @@ def test_host_pipeline_pcm_ingest(dev):
         pipe2.run(torch.from_numpy(pcm).pin_memory())
 
 
+def test_transcribe_pipeline_equals_batch_calls(dev):
+    """TranscribePipeline (PCM host buffers in, pieces copied on side streams, frame-parallel kernels per piece, decoder +
+    logic filter per group) returns exactly what analyze_batch + note_events_batch return for the whole batch."""
+    sr, n_clips, n = 22050, 7, 22050 * 3
+    clips = corpus.clip_batch(n_clips, 3.0, sr, first_seed=500)
+    pcm = np.round(clips * 32767.0).astype(np.int16)
+    y = torch.from_numpy(pcm.astype(np.float32) / 32768.0).to(dev)
+    want = P.batch.analyze_batch(y, sr=sr)
+    want_ev = P.batch.note_events_batch(want, sr=sr)
+    for chunk, group in ((2, 4), (3, 3), (7, 7), (1, 2)):
+        pipe = P.batch.TranscribePipeline(n_clips, n, sr=sr, device=dev, chunk_clips=chunk, group_clips=group, pcm=True)
+        for _ in range(2):   # buffers are reused across runs
+            got = pipe.run(torch.from_numpy(pcm).pin_memory())
+        for k in ("rake_mask", "f0", "voiced_flag", "voiced_probs", "rms"):
+            assert torch.equal(got[k], want[k].cpu()), (chunk, group, k)
+        assert torch.equal(got["n_events"], want_ev["n_events"].cpu())
+        for c in range(n_clips):
+            ne = int(got["n_events"][c])
+            assert ne > 0 and torch.equal(got["events"][c, :ne], want_ev["events"][c, :ne].cpu()), (chunk, group, c)
+    pipe32 = P.batch.TranscribePipeline(n_clips, n, sr=sr, device=dev, chunk_clips=4, pcm=False)
+    got = pipe32.run(torch.from_numpy(pcm.astype(np.float32) / 32768.0).pin_memory())
+    assert torch.equal(got["f0"], want["f0"].cpu()) and pipe32.h2d_bytes == 2 * pipe.h2d_bytes
+    with pytest.raises(ValueError):
+        pipe32.run(torch.from_numpy(pcm).pin_memory())
+
+
 # ---------------------------------------------------------------------------------- K6 guitar filters
 def test_guitar_filters_match_reference_golden(dev, guitar_golden):
     """aegis_guitar_filters against the outputs of the real aegis_engine_core_v2/guitar_specific.py (bit-exact)."""
