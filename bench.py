@@ -506,6 +506,28 @@ def run_gpu(args):
         names = ["K1 stft_fused (mel + rms, no |X| store)", "K4 mel_post (dB + rake mask)", "K2 yin", "K3 viterbi (forward + backtrace)", "K7 note events"]
         stage_ms = {n: marks[i].elapsed_time(marks[i + 1]) for i, n in enumerate(names)}
         del feat, post, obs, dec, res, evs
+        # the v2 ("financial") pipeline on the same clips, BASELINE cfg5's shape of work (aegis_engine_financial.py:73-171):
+        # perception + dB image + guitar filters (K6) + consensus trend (K5) + the financial logic filter (K5 x2 + K8)
+
+        def transcribe_v2():
+            r2 = batch.analyze_batch(y, sr=SR, hop_length=HOP, with_trend=True, with_guitar=True, nan_to_num=False)
+            return batch.note_events_financial_batch(r2, sr=SR, hop_length=HOP)
+
+        v2_ms = None
+        try:
+            for _ in range(2):
+                transcribe_v2()
+            barrier()
+            a = ev()
+            for _ in range(tr_steps):
+                e2 = transcribe_v2()
+            b = ev()
+            barrier()
+            v2_ms = a.elapsed_time(b) / tr_steps
+            v2_events = float(e2["n_events"].float().mean())
+            del e2
+        except Exception as e:  # pragma: no cover
+            log("transcribe_v2 failed:", e)
         # end to end: PCM host buffers in, perception arrays + event records out
         tp = batch.TranscribePipeline(N_CLIPS, n_samples, sr=SR, hop_length=HOP, device=dev, chunk_clips=128, pcm=True)
         for _ in range(2):
@@ -515,7 +537,7 @@ def run_gpu(args):
         del tp
         vit, why = committed_capture("r2_viterbi_issue.json", ["viterbi.cu"])
         tr = {"ms": tr_ms, "e2e_s": tr_e2e_s, "stage_ms": stage_ms, "bytes": tr_bytes, "n_events_mean": n_events_mean,
-              "issue": vit, "issue_note": why}
+              "issue": vit, "issue_note": why, "v2_ms": v2_ms, "v2_events": v2_events if v2_ms is not None else None}
     del pcm_host
     clocks = sampler.stop()   # sampled every 200 ms from the headline loop to the end of the transcription section
 
@@ -524,11 +546,11 @@ def run_gpu(args):
     if world > 1 and not args.no_long_clip:
         long_clip = run_long_clip(args, P, core, dev, rank, world)
 
-    vals = [elapsed_ms, e2e_s, pcm_s, h2d16_s, h2d32_s, tr.get("ms", 0.0), tr.get("e2e_s", 0.0)]
+    vals = [elapsed_ms, e2e_s, pcm_s, h2d16_s, h2d32_s, tr.get("ms", 0.0), tr.get("e2e_s", 0.0), tr.get("v2_ms") or 0.0]
     t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_s, pcm_s, h2d16_s, h2d32_s, tr_ms_max, tr_e2e_max = [float(v) for v in t]
+    elapsed_ms, e2e_s, pcm_s, h2d16_s, h2d32_s, tr_ms_max, tr_e2e_max, v2_ms_max = [float(v) for v in t]
     value = audio_s_per_step * args.steps / (elapsed_ms / 1e3)
 
     # ---- roofline of the STFT kernel
@@ -603,6 +625,11 @@ def run_gpu(args):
                 "value": audio_s_per_step / (tr_ms_max / 1e3), "unit": UNIT, "ms_per_step": tr_ms_max,
                 "kernel_ms": st, "kernel_share": {k: v / tot for k, v in st.items()},
                 "note_events_per_clip": tr["n_events_mean"],
+                "v2_financial": None if not v2_ms_max else {
+                    "workload": "the v2 engine's pipeline on the same clips (BASELINE cfg5's shape of work): perception + dB image + "
+                                "guitar filters (K6) + consensus trend (K5) + financial logic filter (K5 x2 + K8)",
+                    "value": audio_s_per_step / (v2_ms_max / 1e3), "unit": UNIT, "ms_per_step": v2_ms_max,
+                    "note_events_per_clip": tr["v2_events"]},
                 "e2e": {"value": audio_s_per_step / tr_e2e_max, "unit": UNIT, "ms_per_step": tr_e2e_max * 1e3,
                         "h2d_bytes_per_step": tr["bytes"][0], "d2h_bytes_per_step": tr["bytes"][1],
                         "note": "16-bit PCM host buffers in; rake_mask, f0, voiced_flag, voiced_probs, rms and the note-event records out"},
