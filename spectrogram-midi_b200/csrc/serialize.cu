@@ -94,11 +94,10 @@ extern "C" long long aegis_smf_write_v1(const aegis_note_event* events, int32_t 
         return -1;
     }
     const double secs_per_frame = static_cast<double>(opt->hop) / opt->sr;
-    // mido.second2tick(1.0, ticks_per_beat=480, tempo=500000).  mido is unpinned in the reference's requirements.txt; this
-    // matches mido >= 1.3 (second2tick returns the ROUNDED int: 960).  mido 1.2.x returns the float
-    // 1.0 / (500000 * 1e-6 / 480), which is 960.0000000000001 in binary64: int(start * spf * tps) could then differ by one
-    // tick where the product lands within 1e-13 of an integer.  Parity against mido itself is unpinned (mido is not
-    // installable here): DESIGN.md section 3.
+    // mido.second2tick(1.0, ticks_per_beat=480, tempo=500000).  mido is unpinned in the reference's requirements.txt:
+    // mido >= 1.3 returns the rounded int 960, mido 1.2.x the float 1.0 / (500000 * 1e-6 / 480), which evaluates to
+    // exactly 960.0 in binary64 (500000 * 1e-6 == 0.5) -- the same constant either way, so int(start * spf * tps) cannot
+    // differ between the two.  (The file bytes themselves remain unpinned against mido: DESIGN.md section 3.)
     const double ticks_per_sec = 960.0;
     std::vector<Msg> msgs;
     msgs.reserve(static_cast<size_t>(n_events) * 4);
