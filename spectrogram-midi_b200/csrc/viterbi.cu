@@ -127,6 +127,28 @@ __device__ __forceinline__ double lds_table(unsigned addr) {
     return v;
 }
 
+// The same task when the previous frame COLLAPSED: every state of V[t-1] is -inf except its (listed) voiced candidate
+// states, so the dense argmax over all 2n sources reduces to those few, visited in ascending state index with a strict
+// comparison -- in band with the row's table entry, out of band with log(tiny) -- which is the definition itself.
+template <int HW>
+__device__ __forceinline__ void viterbi_task_sparse(const VitSmem& s, const aegis_viterbi_params& p, const int cur, const int win,
+                                                    const int dv, const int lane, const int slot_prev, const int n_prev,
+                                                    double& best, int& arg) {
+    constexpr int hw = HW, W = 2 * HW + 1;
+    const int d = 32 * win + lane;
+    best = -INFINITY;
+    arg = 0;
+#pragma unroll 1
+    for (int k = 0; k < n_prev; ++k) {
+        const int c = s.cand_bin[slot_prev][k];          // warp-uniform, ascending bins
+        const double x = s.V[cur][0][VT_HALO + c];
+        const int o = d - c + hw;
+        const double tv = (o >= 0 && o < W) ? lt_entry<W>(s, p, c, dv, o) : p.log_tiny;   // table (voiced source -> dv) = dv
+        const double v = x + tv;
+        if (v > best) { best = v; arg = c; }
+    }
+}
+
 // One task: the 32 destinations of window `win`, destination voicing `dv` (0 voiced, 1 unvoiced), frame t >= 1.
 // Returns max_k (V[t-1][k] + log_trans[k -> destination]) and its first argmax for this lane's destination.
 // Exactness of the pruning (everything is float64, first-index argmax as in numpy):
@@ -412,6 +434,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
         if (lane == 0) s.seg_hi[nxt][v][win] = 0xFFF00000u;
     };
 
+    bool prev_collapsed = false;   // frame t-1 collapsed: V[t-1] holds nothing but its candidate states (warp-uniform, same in every warp)
     for (int t = 0; t < T; ++t) {
         const int cur = t & 1, nxt = cur ^ 1;
         int ncnt = 0, nbin = 0;   // prefetch the next frame's sparse observation
@@ -477,6 +500,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
 #endif
                 }
             }
+            const bool sparse_sources = prev_collapsed && s.cand_n[(t + 2) % 3] <= 32;   // all of frame t-1's finite states are listed
             const bool all_voiced = dense_v && !collapse;       // every voiced destination is computed and kept
             const unsigned vmask = all_voiced ? all_win : cmask;
             const int n_voiced = __popc(vmask);
@@ -503,7 +527,8 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                 const bool live = d < n;
                 double best;
                 int arg;
-                viterbi_task<HW>(s, p, cur, win, dv, lane, n, n_win, best, arg);
+                if (sparse_sources) viterbi_task_sparse<HW>(s, p, cur, win, dv, lane, (t + 2) % 3, s.cand_n[(t + 2) % 3], best, arg);
+                else viterbi_task<HW>(s, p, cur, win, dv, lane, n, n_win, best, arg);
                 double vnew = NEG_INF;
                 if (dv == 1) {
                     if (live) {
@@ -529,6 +554,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                 publish(nxt, dv, win, vnew);
                 if (fv && live) fv[dv * n + d] = vnew;
             }
+            prev_collapsed = collapse;
             if (collapse) {   // everything that was not computed is dominated: -inf, no back-pointer
                 for (int win = warp; win < n_win; win += NW) {
                     const int d = 32 * win + lane;
