@@ -319,8 +319,17 @@ class TranscribePipeline:
         if y_host.is_cuda or tuple(y_host.shape) != self.in_shape or y_host.dtype != self.inbuf.dtype:
             raise ValueError(f"expected a host {self.inbuf.dtype} tensor {self.in_shape}")
         main = torch.cuda.current_stream(self.dev)
-        start = torch.cuda.Event()
+        trace = getattr(self, "trace", None)     # debugging aid: set pipe.trace = [] to get (label, ms since start) marks
+        start = torch.cuda.Event(enable_timing=trace is not None)
         start.record(main)           # the previous run's kernels are done with the input buffer
+        marks = []
+
+        def mark(label):
+            if trace is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(main)
+                marks.append((label, e))
+
         for i, c0 in enumerate(self.pieces):
             cs = self.copy_streams[i % len(self.copy_streams)]
             with torch.cuda.stream(cs):
@@ -332,9 +341,14 @@ class TranscribePipeline:
         for i, c0 in enumerate(self.pieces):
             c1 = min(self.n_clips, c0 + self.chunk)
             main.wait_event(self.landed[i])
+            mark(f"piece {i} landed")
             self._piece(c0, c1)
+            mark(f"piece {i} K9+K1+K4+K2 done")
             if c1 - g0 >= self.group or c1 == self.n_clips:
                 self._group(g0, c1)
+                mark(f"group [{g0},{c1}) K3+K7+D2H issued/done")
                 g0 = c1
         main.synchronize()
+        if trace is not None:
+            trace[:] = [(label, start.elapsed_time(e)) for label, e in marks]
         return self.out
