@@ -231,18 +231,19 @@ class TranscribePipeline:
     """Host-buffer plugin call for full transcription of a batch: 16-bit PCM (or float32) host audio in, the reference's
     perception arrays and the note-event records out.
 
-    The host batch travels in PIECES of ``chunk_clips`` clips (default: one clip per SM; one cudaMemcpyAsync each,
-    round-robin over ``copy_streams`` copy streams) into a device buffer for the whole batch.  The frame-parallel kernels
+    The host batch travels in PIECES of ``chunk_clips`` clips (default: one clip per SM; one cudaMemcpyAsync each on ONE
+    copy stream: with two streams the copy engine drained one stream's pieces before the other's, and piece 1 landed after
+    piece 6 -- `tools/pipeline_trace.py`) into a device buffer for the whole batch.  The frame-parallel kernels
     run on every piece as soon as it has landed, while later pieces are still on the bus: ingest (K9, when the host batch
     is PCM), K1 + K4 (mel dB, rake mask, RMS) and K2 (pYIN observations, written into batch-wide buffers).  The decoder
     is sequential over frames with one CTA per clip, four resident per SM, so K3 (Viterbi) and K7 (note events) run on
-    GROUPS of ``group_clips`` clips (default four pieces = four clips per SM: always full waves), then the group's
+    GROUPS of ``group_clips`` clips (default eight clips per SM = two full waves), then the group's
     ``rake_mask, f0, voiced_flag, voiced_probs, rms`` (the dict of aegis_engine.py:72-75) and its event records go to
     pinned host arrays.  Results equal ``analyze_batch`` + ``note_events_batch`` on the whole batch bit for bit.
     """
 
     def __init__(self, n_clips: int, n_samples: int, *, sr: float, hop_length: int = 512, device=None, chunk_clips: Optional[int] = None,
-                 pcm: bool = True, copy_streams: int = 2, confidence_threshold: float = 0.7, group_clips: Optional[int] = None,
+                 pcm: bool = True, copy_streams: int = 1, confidence_threshold: float = 0.7, group_clips: Optional[int] = None,
                  fmin: float = E2, fmax: float = C6, rake_sensitivity: float = 0.6):
         from . import _native as nat
 
@@ -253,7 +254,9 @@ class TranscribePipeline:
         with torch.cuda.device(self.dev):
             n_sm = int(nat.load().aegis_device_sm_count())
         self.chunk = max(1, min(n_sm if chunk_clips is None else chunk_clips, n_clips))
-        self.group = max(self.chunk, min(4 * self.chunk if group_clips is None else group_clips, n_clips))
+        # a group = up to two full waves of Viterbi chains (4 per SM each): the decoder's time per wave is nearly flat in the
+        # number of chains, so fewer, fuller launches win (measured, tools/pipeline_trace.py: 592 clips 17.4 ms, 432 clips 15.8 ms)
+        self.group = max(self.chunk, min(8 * n_sm if group_clips is None else group_clips, n_clips))
         self.T = T = core.frame_count(n_samples, hop_length)
         self.cfg = tables.pyin_config(float(sr), int(hop_length), float(fmin), float(fmax))
         mc = self.cfg.max_troughs
