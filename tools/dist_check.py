@@ -36,6 +36,19 @@ mine = res["clip_indices"]
 ok &= torch.equal(res["states"], full["states"][mine]) and sum(res["clips_per_rank"]) == n_clips
 if rank == 0:
     print(f"[world {world}] by-clip sharding: clips per rank {res['clips_per_rank']}, states identical to the unsharded batch: {torch.equal(res['states'], full['states'][mine])}", flush=True)
+# fewer clips than ranks: the rank without clips still joins the count gather, on the device NCCL needs
+one = D.analyze_clips_sharded(lambda idx: torch.from_numpy(clips[idx]).to(dev), 1, sr=sr)
+ok &= one["clips_per_rank"] == [1] + [0] * (world - 1) and (len(one["clip_indices"]) == (1 if rank == 0 else 0))
+if rank == 0:
+    print(f"[world {world}] one clip over {world} ranks: clips per rank {one['clips_per_rank']}", flush=True)
+# note events of the long clip: every rank contributes the events that start in its frames, gathered over NCCL
+ev = D.analyze_long_clip(y, sr=sr, mode="exact", return_events=True)
+want = P.AegisEngine(sample_rate=sr).note_events(ref)
+same_ev = [(int(r["note"]), int(r["start"]), int(r["end"])) for r in ev["events"]] == [(e["note"], e["start"], e["end"]) for e in want]
+counts = D.gather_counts(int(ev["events_local"]))
+ok &= same_ev and sum(counts) == len(want)
+if rank == 0:
+    print(f"[world {world}] event gather: {len(want)} events, per rank {counts}, identical to the single-GPU list: {same_ev}", flush=True)
 t = torch.tensor([int(ok)], device=dev)
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
