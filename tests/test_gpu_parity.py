@@ -423,6 +423,26 @@ def test_pyin_tables_are_not_aliased_across_hmm_parameters(dev):
         assert (np.abs(1200 * np.log2(g[vf] / f0[vf])) <= 1.0).all(), kw
 
 
+def test_turbo_worker_and_parallel_pitch_tracking(dev):
+    """Row a-6: `_pyin_worker((chunk, sr, hop))` (aegis_engine_core/worker.py:3-15) returns librosa.pyin of the chunk --
+    checked against the oracle on a chunk of the test track -- and `AegisEngine._parallel_pitch_tracking` returns the
+    serial full-clip decode (what Turbo Mode approximates with independent chunks, aegis_engine.py:183-216)."""
+    y, sr = SIGNALS["track22050"]()
+    chunk = y[4000 : 4000 + 3 * sr]
+    f0, vf, vp = P.worker._pyin_worker((chunk, sr, 512))
+    r0, rv, rp = L.pyin(chunk, fmin=E2, fmax=C6, sr=sr, hop_length=512)
+    assert f0.dtype == np.float64 and vf.dtype == bool and vp.dtype == np.float64 and f0.shape == r0.shape
+    np.testing.assert_array_equal(vf, rv)
+    np.testing.assert_allclose(vp, rp, atol=2e-3)
+    assert (np.abs(1200 * np.log2(f0[vf] / r0[vf])) <= 1.0).all() and np.isnan(f0[~vf]).all()
+    eng = P.AegisEngine(sample_rate=sr)
+    t0, tv, tp = eng._parallel_pitch_tracking(y)
+    s0, sv, sp = P.librosa_compat.pyin(y, fmin=E2, fmax=C6, sr=sr, hop_length=512)
+    np.testing.assert_array_equal(tv, sv)
+    np.testing.assert_array_equal(t0, s0)
+    np.testing.assert_array_equal(tp, sp)
+
+
 def test_yin_fused_and_split_kernels_agree_bit_for_bit(dev):
     """K2 at hop 512 has two forms: block sums + per-frame stage as two kernels (with the workspace) or one fused kernel
     (without).  A block sum depends only on its own samples and is summed in one fixed order, so both forms -- and any
