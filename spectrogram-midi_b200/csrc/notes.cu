@@ -10,11 +10,11 @@
 // arithmetic as in numpy; log10 is evaluated in double and rounded once, i.e. correctly rounded float32) and the
 // per-frame MIDI note (-1 = inactive) and the frame's continuous MIDI pitch 12 log2(f / 440) + 69 (the double-precision
 // log2 is by far the longest step of the walk: it is taken here, frame parallel, not in the sequential kernel).
-// Kernel 2: one thread per clip walks its frames once (independent loads,
-// L2 resident), keeps least-squares sums of the running event, finishes events (slope, vibrato range), and applies
-// the duration filter, the merge and the hammer-on / pull-off rule in streaming form: an event is written once the
-// next surviving event is known.  A clip is a sequential chain of ~T steps of a few dozen instructions: 1292 frames
-// take ~50 us, all clips in parallel.
+// Kernel 2: one warp per clip walks its frames once (rows staged in shared memory), keeps least-squares sums of the
+// running event, finishes events (slope, vibrato range), and applies the duration filter, the merge and the hammer-on /
+// pull-off rule in streaming form: an event is written once the next surviving event is known.  A clip is a sequential
+// chain of ~T steps of a few dozen instructions, all clips in parallel.  (Round 1 and early round 2 ran one THREAD per
+// clip: 32 unrelated state machines per warp serialised on each other's branches, 2.2 ms for 1024 clips.)
 #include <cfloat>
 #include <cmath>
 #include "common.cuh"
@@ -72,15 +72,46 @@ __device__ __forceinline__ void write_event(aegis_note_event* dst, const Ev& e) 
     dst->slope = e.slope;
 }
 
+// One warp per clip.  The walk is a sequential chain (the least-squares sums are accumulated in frame order, as the
+// oracle does), so every lane runs it redundantly on the same data -- control flow stays warp-uniform, no lane waits for
+// another clip's branch -- and the lanes split the one data-parallel piece, the residual range of a finished run (min /
+// max are order independent).  Lane 0 writes.  STAGED: the clip's note / pitch rows are first copied to shared memory
+// with coalesced loads, so the chain runs on shared-memory latency; clips too long for that walk the global rows.
+constexpr int NE_STAGE_MAX_FRAMES = 20000;   // 10 B per frame of dynamic shared memory
+
+__device__ __forceinline__ double warp_min_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <bool STAGED>
 __global__ void __launch_bounds__(32)
 notes_events_kernel(const aegis_notes_params p, const float* __restrict__ rms_db, const short* __restrict__ note,
                     const double* __restrict__ pitch) {
-    const int clip = blockIdx.x * blockDim.x + threadIdx.x;
-    if (clip >= p.n_clips) return;
+    extern __shared__ __align__(16) unsigned char ne_smem[];
+    const int clip = blockIdx.x;
+    const int lane = threadIdx.x;
     const int T = p.n_frames;
     const long long base = static_cast<long long>(clip) * T;
     const short* nt = note + base;
     const double* yp = pitch + base;
+    if (STAGED) {
+        double* yp_s = reinterpret_cast<double*>(ne_smem);
+        short* nt_s = reinterpret_cast<short*>(yp_s + T);
+        for (int t = lane; t < T; t += 32) {
+            yp_s[t] = yp[t];
+            nt_s[t] = nt[t];
+        }
+        __syncwarp();
+        nt = nt_s;
+        yp = yp_s;
+    }
     aegis_note_event* out = p.events + static_cast<long long>(clip) * p.max_events;
     const double ms_per_frame = (static_cast<double>(p.hop) / p.sr) * 1000;
     int n_out = 0;
@@ -100,7 +131,7 @@ notes_events_kernel(const aegis_notes_params p, const float* __restrict__ rms_db
                 else if (dp >= -2 && dp < 0 && weak) { e.technique = 5; e.slope = 0.0; }
             }
         }
-        if (n_out < p.max_events) write_event(out + n_out, e);
+        if (lane == 0 && n_out < p.max_events) write_event(out + n_out, e);
         ++n_out;
         // the rule reads note / velocity / energy / end of the predecessor: none of them is changed by the rule itself
         last = e;
@@ -117,11 +148,13 @@ notes_events_kernel(const aegis_notes_params p, const float* __restrict__ rms_db
             const double slope = (sxy - xm * sy) / sxx;
             const double icpt = ym - slope * xm;
             double rmin = DBL_MAX, rmax = -DBL_MAX;
-            for (int t = e.start; t <= e.end; ++t) {
+            for (int t = e.start + lane; t <= e.end; t += 32) {
                 const double r = yp[t] - (slope * (t - e.start) + icpt);
                 rmin = fmin(rmin, r);
                 rmax = fmax(rmax, r);
             }
+            rmin = warp_min_f64(rmin);
+            rmax = warp_max_f64(rmax);
             if (rmax - rmin > 0.3) { e.technique = 1; e.slope = slope; }
             else if (slope > 0.05) { e.technique = 2; e.slope = slope; }
             else if (fabs(slope) > 0.02) { e.technique = 3; e.slope = slope; }
@@ -169,7 +202,7 @@ notes_events_kernel(const aegis_notes_params p, const float* __restrict__ rms_db
     }
     if (open) finish(cur, sy, sxy);
     if (have_pending) emit(pending);
-    p.n_events[clip] = n_out;
+    if (lane == 0) p.n_events[clip] = n_out;
 }
 
 }  // namespace aegis
@@ -198,7 +231,16 @@ extern "C" int aegis_note_events(const aegis_notes_params* p, void* stream) {
         notes_frames_kernel<<<dim3((p->n_frames + NT_THREADS - 1) / NT_THREADS, p->n_clips), NT_THREADS, 0, st>>>(*p, rms_max, rms_db, note, pitch);
         if (int rc = check_launch("aegis_note_events(frames)")) return rc;
     }
-    notes_events_kernel<<<(p->n_clips + 31) / 32, 32, 0, st>>>(*p, rms_db, note, pitch);
+    if (p->n_frames <= NE_STAGE_MAX_FRAMES) {
+        const size_t smem = static_cast<size_t>(p->n_frames) * 10 + 16;
+        if (smem > 48 * 1024) {
+            const cudaError_t e = cudaFuncSetAttribute(notes_events_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            AEGIS_REQUIRE(e == cudaSuccess, "aegis_note_events: %s", cudaGetErrorString(e));
+        }
+        notes_events_kernel<true><<<p->n_clips, 32, smem, st>>>(*p, rms_db, note, pitch);
+    } else {
+        notes_events_kernel<false><<<p->n_clips, 32, 0, st>>>(*p, rms_db, note, pitch);
+    }
     return check_launch("aegis_note_events(events)");
 }
 

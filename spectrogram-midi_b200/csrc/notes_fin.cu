@@ -9,7 +9,7 @@
 //   prepare  (frame parallel)  f0_clean = f0 where voiced else NaN; semitones = hz_to_midi(f0_clean); rms -> dB
 //   frames   (frame parallel)  one 16-byte record per frame: combined confidence, MIDI note of the trend (or -1),
 //                              band side of f0 (above / inside / below / no pitch), slide label, velocity
-//   events   (one thread per clip) adaptive threshold with numpy's summation order; the band-crossing counter and
+//   events   (one warp per clip) adaptive threshold with numpy's summation order; the band-crossing counter and
 //                              the note state machine in one walk over the records; duration filter and sustain merge
 //                              in streaming form; then, on the clip's few events, the RSI density filter, the key
 //                              histogram, the out-of-scale filter and the 2-second chord windows.
@@ -17,6 +17,7 @@
 // This file is compiled with -fmad=false: every product and sum is rounded as in the reference's numpy expressions.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include "common.cuh"
 #include "notes_common.cuh"
 
@@ -196,33 +197,109 @@ __device__ __forceinline__ bool in_scale(int pc, int root, int mode) {
     return (c_scale_mask[mode] >> ((pc - root + 12) % 12)) & 1;
 }
 
-__global__ void __launch_bounds__(64)
-fin_events_kernel(const aegis_fin_params p, const FinFrame* __restrict__ frames, double* __restrict__ compact) {
-    const int clip = blockIdx.x * blockDim.x + threadIdx.x;
-    if (clip >= p.n_clips) return;
+// The RSI verdicts without walking the series.  The density series is 0 / 1 with at most two edges per event, and
+// between edges Wilder's recurrence is a pure decay g <- fl(fl(13 g) / 14): n such steps are g (13/14)^n up to a relative
+// error of 2 n ulp.  The reference's result depends on the RSI only through `rsi < threshold` at the event starts, so the
+// closed form decides every verdict whose distance from the threshold exceeds a bound on its own error (4 L ulp relative
+// on g and l, hence 50x that on the RSI, plus slack); anything closer -- or in the subnormal range, where the relative
+// bound does not hold -- returns false and the caller walks the series exactly.  Same verdicts, ~n_events steps instead
+// of 10 T sequential double divisions (12 920 for a 30 s clip: ~1 ms on one lane).
+__device__ bool rsi_verdicts_closed_form(aegis_fin_event* out, int n_ev, long long L, double g, double l, double thr) {
+    constexpr long long period = 14;
+    constexpr double TINY = 1e-280;
+    const double ratio = 13.0 / 14.0;
+    const double rel = 4.0 * static_cast<double>(L) * 1.2e-16 + 1e-12;
+    const double margin = 50.0 * rel + 1e-9;
+    bool had_gain = g > 0, had_loss = l > 0;
+    long long pos = period;
+    auto advance = [&](long long i, double gain, double loss) {   // steps pos+1 .. i-1 decay, step i takes (gain, loss)
+        const long long n = i - 1 - pos;
+        if (n > 0) {
+            const double f = pow(ratio, static_cast<double>(n));
+            g = g * f;
+            l = l * f;
+        }
+        g = (g * (period - 1) + gain) / period;
+        l = (l * (period - 1) + loss) / period;
+        pos = i;
+    };
+    for (int k = 0; k < n_ev; ++k) {
+        const long long is = 10LL * out[k].start, ie = 10LL * out[k].end;
+        const bool solid = ie > is;                    // an empty span leaves no edge in the series
+        if (is > period && is < L) {
+            advance(is, solid ? 1.0 : 0.0, 0.0);
+            had_gain = had_gain || solid;
+            const bool g_zero = !had_gain, l_zero = !had_loss;
+            const bool g_tiny = had_gain && g < TINY, l_tiny = had_loss && l < TINY;
+            int keep;
+            if (l_zero) keep = 100.0 < thr;                                   // l == 0: the reference's RSI is 100
+            else if (l_tiny) { if (g_tiny || thr > 99.0) return false; keep = 0; }      // RSI within 1e-200 of 100
+            else if (g_zero) keep = 0.0 < thr;                                // 100 - 100 / (1 + 0)
+            else if (g_tiny) { if (thr < 1.0) return false; keep = 1; }       // RSI within 1e-200 of 0
+            else {
+                const double rsi = 100.0 - (100.0 / (1.0 + g / l));
+                if (!(fabs(rsi - thr) > margin)) return false;
+                keep = rsi < thr;
+            }
+            out[k]._pad[0] = static_cast<unsigned char>(keep);
+        }
+        if (solid && ie > period && ie < L) {
+            advance(ie, 0.0, 1.0);
+            had_loss = true;
+        }
+    }
+    return true;
+}
+
+// One warp per clip: the frame records are staged in shared memory with coalesced loads, the compaction and the squared
+// deviations are lane parallel, the ordered sums and the note state machine run redundantly on every lane (warp-uniform
+// control flow, shared-memory latency), lane 0 writes the events and then runs the per-event passes alone.  (One THREAD
+// per clip, as in round 1, serialised 64 unrelated state machines per block on each other's branches: 6.4 ms.)
+constexpr int FE_STAGE_MAX_FRAMES = 9000;   // 24 B per frame of dynamic shared memory
+
+template <bool STAGED>
+__global__ void __launch_bounds__(32)
+fin_events_kernel(const aegis_fin_params p, const FinFrame* __restrict__ frames, double* __restrict__ compact, int exact_rsi) {
+    extern __shared__ __align__(16) unsigned char fe_smem[];
+    const int clip = blockIdx.x;
+    const int lane = threadIdx.x;
     const int T = p.n_frames;
     const FinFrame* fr = frames + static_cast<long long>(clip) * T;
+    double* c = compact + static_cast<long long>(clip) * T;
+    if (STAGED) {
+        FinFrame* fr_s = reinterpret_cast<FinFrame*>(fe_smem);
+        for (int t = lane; t < T; t += 32) fr_s[t] = fr[t];
+        fr = fr_s;
+        c = reinterpret_cast<double*>(fr_s + T);
+        __syncwarp();
+    }
     aegis_fin_event* out = p.events + static_cast<long long>(clip) * p.max_events;
 
     // ---- threshold (midi_logic_financial.py:77-114,172-176)
     double thr = p.confidence_threshold;
     if (isnan(thr)) {
-        double* c = compact + static_cast<long long>(clip) * T;
         int m = 0;
-        for (int t = 0; t < T; ++t) {
-            const double v = fr[t].combined;
-            if (v > 0) c[m++] = v;
+        for (int t0 = 0; t0 < T; t0 += 32) {          // order-preserving compaction of the positive confidences
+            const int t = t0 + lane;
+            const double v = t < T ? fr[t].combined : 0.0;
+            const bool pos = v > 0;
+            const unsigned mask = __ballot_sync(0xffffffffu, pos);
+            if (pos) c[m + __popc(mask & ((1u << lane) - 1u))] = v;
+            m += __popc(mask);
         }
+        __syncwarp();
         if (m == 0) {
             thr = 0.5;
         } else {
             const double mean = numpy_pairwise_f64(c, m) / static_cast<double>(m);
-            for (int i = 0; i < m; ++i) { const double d = c[i] - mean; c[i] = d * d; }
+            __syncwarp();
+            for (int i = lane; i < m; i += 32) { const double d = c[i] - mean; c[i] = d * d; }
+            __syncwarp();
             const double sd = sqrt(numpy_pairwise_f64(c, m) / static_cast<double>(m));
             thr = fmin(fmax(mean - sd, 0.3), 0.8);
         }
     }
-    if (p.threshold_out != nullptr) p.threshold_out[clip] = thr;
+    if (lane == 0 && p.threshold_out != nullptr) p.threshold_out[clip] = thr;
 
     // ---- phases 2 and 3a: runs of one note, duration filter, sustain merge (:204-328)
     int n_out = 0;
@@ -236,7 +313,7 @@ fin_events_kernel(const aegis_fin_params p, const FinFrame* __restrict__ frames,
                 pending.end = e.end;                                                      // :314-318
                 return;
             }
-            if (n_out < p.max_events) write_fin_event(out + n_out, pending);
+            if (lane == 0 && n_out < p.max_events) write_fin_event(out + n_out, pending);
             ++n_out;
         }
         pending = e;
@@ -274,9 +351,10 @@ fin_events_kernel(const aegis_fin_params p, const FinFrame* __restrict__ frames,
     }
     if (open) close(cur);
     if (have_pending) {
-        if (n_out < p.max_events) write_fin_event(out + n_out, pending);
+        if (lane == 0 && n_out < p.max_events) write_fin_event(out + n_out, pending);
         ++n_out;
     }
+    if (lane != 0) return;   // the passes below touch the clip's few events only
     if (p.key_out != nullptr) p.key_out[clip] = -1;
     if (p.key_confidence_out != nullptr) p.key_confidence_out[clip] = 0.0;
     if (n_out > p.max_events) {   // overflow: report the count, the host raises
@@ -312,20 +390,22 @@ fin_events_kernel(const aegis_fin_params p, const FinFrame* __restrict__ frames,
             }
             g = g / period;
             l = l / period;
-            int nxt = 0;                                     // next event to judge
-            for (long long i = period; i < L; ++i) {
-                if (i > period) {                            // Wilder smoothing with deltas[i - 1] = data[i] - data[i - 1]
-                    const double d = density(i), delta = d - d_prev;
-                    const double gain = delta > 0 ? delta : 0.0, loss = delta < 0 ? -delta : 0.0;
-                    g = (g * (period - 1) + gain) / period;
-                    l = (l * (period - 1) + loss) / period;
-                    d_prev = d;
-                }
-                while (nxt < n_ev && 10LL * out[nxt].start < i) ++nxt;
-                if (nxt < n_ev && 10LL * out[nxt].start == i) {
-                    const double rsi = (l == 0) ? 100.0 : 100.0 - (100.0 / (1.0 + g / l));
-                    out[nxt]._pad[0] = rsi < p.rsi_threshold ? 1 : 0;
-                    ++nxt;
+            if (exact_rsi != 0 || !rsi_verdicts_closed_form(out, n_ev, L, g, l, p.rsi_threshold)) {
+                int nxt = 0;                                 // next event to judge
+                for (long long i = period; i < L; ++i) {
+                    if (i > period) {                        // Wilder smoothing with deltas[i - 1] = data[i] - data[i - 1]
+                        const double d = density(i), delta = d - d_prev;
+                        const double gain = delta > 0 ? delta : 0.0, loss = delta < 0 ? -delta : 0.0;
+                        g = (g * (period - 1) + gain) / period;
+                        l = (l * (period - 1) + loss) / period;
+                        d_prev = d;
+                    }
+                    while (nxt < n_ev && 10LL * out[nxt].start < i) ++nxt;
+                    if (nxt < n_ev && 10LL * out[nxt].start == i) {
+                        const double rsi = (l == 0) ? 100.0 : 100.0 - (100.0 / (1.0 + g / l));
+                        out[nxt]._pad[0] = rsi < p.rsi_threshold ? 1 : 0;
+                        ++nxt;
+                    }
                 }
             }
         }
@@ -472,7 +552,19 @@ extern "C" int aegis_fin_events(const aegis_fin_params* p, void* stream) {
         fin_frames_kernel<<<frame_blocks(p), NF_THREADS, 0, st>>>(*p, s.rms_db, s.frames);
         if (int rc = check_launch("aegis_fin_events(frames)")) return rc;
     }
-    fin_events_kernel<<<(p->n_clips + 63) / 64, 64, 0, st>>>(*p, s.frames, s.compact);
+    // AEGIS_FIN_EXACT_RSI=1 walks every density series step by step (the parity tests compare the two)
+    const char* env = getenv("AEGIS_FIN_EXACT_RSI");
+    const int exact_rsi = (env != nullptr && env[0] == '1') ? 1 : 0;
+    if (p->n_frames <= FE_STAGE_MAX_FRAMES) {
+        const size_t smem = static_cast<size_t>(p->n_frames) * 24 + 16;
+        if (smem > 48 * 1024) {
+            const cudaError_t e = cudaFuncSetAttribute(fin_events_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            AEGIS_REQUIRE(e == cudaSuccess, "aegis_fin_events: %s", cudaGetErrorString(e));
+        }
+        fin_events_kernel<true><<<p->n_clips, 32, smem, st>>>(*p, s.frames, s.compact, exact_rsi);
+    } else {
+        fin_events_kernel<false><<<p->n_clips, 32, 0, st>>>(*p, s.frames, s.compact, exact_rsi);
+    }
     return check_launch("aegis_fin_events(events)");
 }
 

@@ -759,6 +759,36 @@ def test_financial_note_events_batch_equals_oracle(dev, kw):
         assert events > 20
 
 
+def test_financial_rsi_closed_form_equals_the_stepwise_walk(dev, monkeypatch):
+    """K8 decides the RSI ghost-note verdicts from a closed form with an error bound and walks the 10 T-step density
+    series only when a verdict is closer to the threshold than the bound.  AEGIS_FIN_EXACT_RSI=1 forces the walk (the
+    round-1 path, itself pinned to the reference golden above): the event records must be byte-identical, over thresholds
+    that keep everything, drop some and drop most, and on clips with 25 s of silence between notes (the decaying averages
+    reach the subnormal range there)."""
+    T = 1292
+    clips = [_fin_frames(900 + i, T, steady_grid=(i % 3 == 1)) for i in range(24)]
+    for i in (3, 9, 15):   # a long silence in the middle / at the start
+        rake, f0, vf, vp, rms = (a.copy() for a in clips[i])
+        lo, hi = (60, 1150) if i != 9 else (0, 1080)
+        f0[lo:hi], vf[lo:hi], vp[lo:hi] = np.nan, False, 0.05
+        clips[i] = (rake, f0, vf, vp, rms)
+    stack = [torch.from_numpy(np.stack([c[j] for c in clips])).to(dev) for j in range(5)]
+    dropped = []
+    for thr in (70, 55.0, 50.0, 35.5, 20, 100.0, 0.0, 1e-5):
+        monkeypatch.delenv("AEGIS_FIN_EXACT_RSI", raising=False)
+        fast = P.core.note_events_financial(*stack, sr=22050, hop_length=512, rsi_threshold=thr, use_harmonic_filter=False)
+        monkeypatch.setenv("AEGIS_FIN_EXACT_RSI", "1")
+        walk = P.core.note_events_financial(*stack, sr=22050, hop_length=512, rsi_threshold=thr, use_harmonic_filter=False)
+        monkeypatch.delenv("AEGIS_FIN_EXACT_RSI")
+        assert torch.equal(fast["n_events"], walk["n_events"]), thr
+        for c in range(len(clips)):
+            n = int(fast["n_events"][c])
+            assert torch.equal(fast["events"][c, :n], walk["events"][c, :n]), (thr, c)
+        dropped.append(int(fast["n_events"].sum()))
+    assert len(set(dropped)) >= 3 and min(dropped) < max(dropped), dropped   # the thresholds really filter
+    print("events kept per threshold:", dropped)
+
+
 def test_financial_logic_filter_fallback_branch_matches_reference_golden(dev):
     """get_midi_events_financial(use_financial=False) -- the reference function's fallback branch
     (midi_logic_financial.py:178-196 + detect_articulations_financial per note; never taken by the v2 engine): host frame loop,
