@@ -597,29 +597,101 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
     }
 }
 
-// back-trace: one thread per clip (latency bound; all clips walk in parallel).  States the forward pass skipped
-// (dominated: final value -inf, no back-pointer) are never visited.
-__global__ void __launch_bounds__(64)
+// back-trace: one warp per clip.  The walk is a chain of dependent loads from a 2.3 GB array (1024 clips x 1292 frames x
+// 882 states x 2 B): one DRAM round trip per frame when walked naively (1.24 ms).  A predecessor lies within half_width
+// bins of its successor, in either voicing half, so the entries the next BT_DEPTH rows can possibly need form a cone
+// around the current bin: the lanes fetch that cone in one burst of independent loads (one round trip), the walk then
+// runs on shared memory.  A predecessor outside the cone (the log(0 + tiny) transitions are finite, so the forward pass
+// may -- very rarely -- pick one) is read from global memory instead.  States the forward pass skipped (dominated: final
+// value -inf, no back-pointer) are never visited.
+constexpr int BT_DEPTH = 4;
+constexpr int BT_WARPS = 4;
+constexpr int BT_SPAN = 2 * (BT_DEPTH - 1) * VT_MAX_HW + 1;
+__host__ __device__ constexpr int bt_loads_of_row(int k) { return (2 * k * VT_MAX_HW + 1 + 31) / 32; }   // per lane and half
+__host__ __device__ constexpr int bt_loads_total() {
+    int s = 0;
+    for (int k = 0; k < BT_DEPTH; ++k) s += 2 * bt_loads_of_row(k);
+    return s;
+}
+constexpr int BT_LOADS = bt_loads_total();
+
+__global__ void __launch_bounds__(32 * BT_WARPS)
 viterbi_backtrace_kernel(const aegis_viterbi_params p) {
-    const int clip = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ unsigned short cone[BT_WARPS][BT_DEPTH][2][BT_SPAN];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int clip = blockIdx.x * BT_WARPS + warp;
     if (clip >= p.n_clips) return;
-    const int n = p.n_pitch_bins, T = p.n_frames;
+    const int n = p.n_pitch_bins, T = p.n_frames, hw = p.half_width;
     if (T <= 0) return;
     const double* fv = p.final_value + static_cast<long long>(clip) * (2 * n);
-    int st = 0;
-    double best = fv[0];
-    for (int j = 1; j < 2 * n; ++j) {
+    // first maximum of the final values
+    int st = 2 * n;
+    double best = -INFINITY;
+    for (int j = lane; j < 2 * n; j += 32) {
         const double v = fv[j];
-        if (v > best) { best = v; st = j; }
+        if (v > best || st == 2 * n) { best = v; st = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int os = __shfl_xor_sync(0xffffffffu, st, o);
+        if (ov > best || (ov == best && os < st)) { best = ov; st = os; }
     }
     const long long base = static_cast<long long>(clip) * T;
     const unsigned short* bp = p.backptr + base * (2 * n);
-    for (int t = T - 1; t >= 0; --t) {
-        p.states[base + t] = static_cast<unsigned short>(st);
-        const bool voiced = st < n;
-        p.voiced_flag[base + t] = voiced ? 1 : 0;
-        p.f0[base + t] = voiced ? __ldg(p.freqs + st) : p.fill_value;
-        if (t > 0) st = bp[static_cast<long long>(t) * (2 * n) + st];
+    for (int t = T - 1; t >= 0; t -= BT_DEPTH) {
+        const int b0 = st < n ? st : st - n;
+        // row t - k: bins b0 - k hw .. b0 + k hw of both halves (row 0 has no back-pointers).  Every lane first issues
+        // all of its loads, then parks them in shared memory: one round trip, not one per row
+        unsigned short got[BT_LOADS];
+        {
+            int q0 = 0;
+#pragma unroll
+            for (int k = 0; k < BT_DEPTH; ++k) {
+                const unsigned short* row = bp + static_cast<long long>(t - k) * (2 * n) + (b0 - k * hw);
+                const int width = 2 * k * hw + 1;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int q = 0; q < bt_loads_of_row(k); ++q) {
+                        const int o = lane + 32 * q, bin = b0 - k * hw + o;
+                        const bool live = o < width && t - k >= 1 && bin >= 0 && bin < n;
+                        got[q0 + q] = live ? row[h * n + o] : static_cast<unsigned short>(0);
+                    }
+                    q0 += bt_loads_of_row(k);
+                }
+            }
+            q0 = 0;
+#pragma unroll
+            for (int k = 0; k < BT_DEPTH; ++k) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int q = 0; q < bt_loads_of_row(k); ++q)
+                        if (lane + 32 * q < BT_SPAN) cone[warp][k][h][lane + 32 * q] = got[q0 + q];
+                    q0 += bt_loads_of_row(k);
+                }
+            }
+        }
+        __syncwarp();
+        // every lane walks the same chain; lane k keeps the state of frame t - k and writes it
+        int mine = st;
+#pragma unroll
+        for (int k = 0; k < BT_DEPTH; ++k) {
+            if (t - k < 0) break;
+            if (lane == k) mine = st;
+            if (t - k > 0) {
+                const int h = st >= n, o = (st - h * n) - (b0 - k * hw);
+                st = (o >= 0 && o <= 2 * k * hw) ? cone[warp][k][h][o] : bp[static_cast<long long>(t - k) * (2 * n) + st];
+            }
+        }
+        __syncwarp();
+        if (lane < BT_DEPTH && t - lane >= 0) {
+            const bool voiced = mine < n;
+            p.states[base + t - lane] = static_cast<unsigned short>(mine);
+            p.voiced_flag[base + t - lane] = voiced ? 1 : 0;
+            p.f0[base + t - lane] = voiced ? __ldg(p.freqs + mine) : p.fill_value;
+        }
     }
 }
 
@@ -661,6 +733,6 @@ extern "C" int aegis_viterbi(const aegis_viterbi_params* p, void* stream) {
         default: set_error("aegis_viterbi: half_width=%d has no compiled kernel (12, 25, 50)", p->half_width); return 1;
     }
     if (rc) return rc;
-    viterbi_backtrace_kernel<<<(p->n_clips + 63) / 64, 64, 0, st>>>(*p);
+    viterbi_backtrace_kernel<<<(p->n_clips + BT_WARPS - 1) / BT_WARPS, 32 * BT_WARPS, 0, st>>>(*p);
     return check_launch("aegis_viterbi(backtrace)");
 }
