@@ -87,7 +87,15 @@ __device__ __forceinline__ void fft_finish_inplace(int lt, cf* v, const FftTwidd
 // Candidate stage of one frame by one warp (librosa __pyin_helper): troughs of the CMND curve
 // yv[0..L), their probabilities over the beta-weighted thresholds with the Boltzmann prior on the trough rank, parabolic
 // refinement, 10-cent bins; writes the frame's sparse observation (bins ascending, unique) and its voiced probability.
-struct YinTables {   // the prior tables: global pointers (read through the read-only path) or copies in shared memory
+// CMND value d[tau] / (mean of d[1..tau] + tiny) from the float32-rounded cumulative sum s: the mean's division is folded
+// into the numerator, d tau / (s + tau tiny) -- one double division per lag instead of two (tau tiny only matters when
+// s == 0, where it reproduces d / tiny; for any s != 0 the sum is s itself).  Within one ulp of the two-division form.
+__device__ __forceinline__ double cmnd_value(float d, double s_rounded, int tau) {
+    const double tt = static_cast<double>(tau);
+    return (static_cast<double>(d) * tt) / fma(tt, DBL_MIN, s_rounded);
+}
+
+struct YinTables {   // the prior tables: global pointers (read through the read-only path) or copies in shared memory (beta_cumsum: always global)
     const double* thresholds;
     const double* beta_probs;
     const double* beta_cumsum;
@@ -177,7 +185,7 @@ __device__ __forceinline__ void yin_candidates_of_frame(const aegis_yin_params& 
         __syncwarp();
         // 5. every lane turns its troughs' lags into pitch bins (parabolic refinement, log2: the expensive
         //    part, in parallel; tk[] is overwritten with the bin, 0xffff = not a candidate) ...
-        if (lane == 0) tp[best_i] += p.no_trough_prob * tab<SHARED>(tb.beta_cumsum + tq[best_i]);
+        if (lane == 0) tp[best_i] += p.no_trough_prob * __ldg(tb.beta_cumsum + tq[best_i]);   // one read per frame: stays global
         __syncwarp();
         {
             const double scale = 12.0 * p.bins_per_semitone;
@@ -376,8 +384,7 @@ yin_fft_kernel(const aegis_yin_params p, const int pairs_per_clip, const long lo
             for (int tau = lo; tau < hi; ++tau) {
                 run += static_cast<double>(se.d[fr][tau]);
                 if (tau >= minp) {
-                    const double cm = static_cast<double>(static_cast<float>(base + run)) / static_cast<double>(tau);
-                    const double yv = static_cast<double>(se.d[fr][tau]) / (cm + DBL_MIN);
+                    const double yv = cmnd_value(se.d[fr][tau], static_cast<double>(static_cast<float>(base + run)), tau);
                     se.yin[fr][tau - minp] = yv;
                     if (p.cmnd_out != nullptr && t0 + fr < T)
                         p.cmnd_out[(static_cast<long long>(clip) * T + t0 + fr) * L + (tau - minp)] = yv;
@@ -568,8 +575,7 @@ yin_direct_kernel(const aegis_yin_params p, const YinDirectLayout lay, const int
         for (int tau = lo; tau < hi; ++tau) {
             run += static_cast<double>(dbuf[tau]);
             if (tau >= minp) {
-                const double cm = static_cast<double>(static_cast<float>(base + run)) / static_cast<double>(tau);
-                const double yv = static_cast<double>(dbuf[tau]) / (cm + DBL_MIN);
+                const double yv = cmnd_value(dbuf[tau], static_cast<double>(static_cast<float>(base + run)), tau);
                 yin[tau - minp] = yv;
                 if (p.cmnd_out != nullptr) p.cmnd_out[(static_cast<long long>(clip) * T + t) * L + (tau - minp)] = yv;
             }
@@ -591,6 +597,12 @@ constexpr int YS_SPAN_MAX = YD_BLOCKS * 512 + 1 + 16 * 64;                // 16 
 constexpr int YS_PHYS = YS_SPAN_MAX + YS_SPAN_MAX / 16 + 32;
 
 // 4-byte cp.async with zero fill: copies src_bytes (4 or 0) bytes and zero-fills the rest of the 4
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gmem_src, int src_bytes) {
     const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
@@ -686,7 +698,10 @@ yin_blocksum_kernel(const aegis_yin_params p, const int n_groups, const int b_pi
     }
 }
 
-constexpr int YF_WARPS = 8;   // frames per CTA of the per-frame kernel
+#ifndef AEGIS_YF_WARPS
+#define AEGIS_YF_WARPS 7
+#endif
+constexpr int YF_WARPS = AEGIS_YF_WARPS;   // frames per CTA of the per-frame kernel (7: 53 KB of shared memory, four CTAs per SM; 8: 60 KB, three)
 
 struct YinFrameLayout {
     int b_pitch, n_blocks;
@@ -710,22 +725,35 @@ yin_frame_kernel(const aegis_yin_params p, const YinFrameLayout lay, const int g
     const long long g0 = static_cast<long long>(t0) * 512 - p.pad;
     const int n_fr = min(YF_WARPS, T - t0);
     const int m_end = 512 * (n_fr - 1) + 1025 + maxp;
-    for (int m = tid; m < m_end; m += 32 * YF_WARPS) {
+    // everything the CTA reads is requested up front with asynchronous 16- / 8-byte copies (one round trip; the
+    // register-staged loops this replaces took five, 21 % of the kernel's stall samples)
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(yc) & 15) == 0) && ((g0 & 3) == 0);
+    for (int m = tid * 4; m < m_end; m += 4 * 32 * YF_WARPS) {
         const long long gi = g0 + m;
-        xs[m] = (gi >= 0 && gi < N) ? __ldg(yc + gi) : 0.f;
+        if (vec_ok && gi >= 0 && gi + 3 < N) {
+            cp_async16(&xs[m], yc + gi);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xs[m + j] = (gi + j >= 0 && gi + j < N) ? __ldg(yc + gi + j) : 0.f;
+        }
     }
-    {   // block sums of blocks t0 .. t0 + n_fr
+    {   // block sums of blocks t0 .. t0 + n_fr (rows of b_pitch = 16 k floats: 16-byte pieces)
         const float* src = p.block_sums + (static_cast<long long>(clip) * lay.n_blocks + t0) * lay.b_pitch;
         const int cnt = (n_fr + 1) * lay.b_pitch;
-        for (int i = tid; i < cnt; i += 32 * YF_WARPS) Bs[i] = __ldg(src + i);
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            for (int i = tid * 4; i < cnt; i += 4 * 32 * YF_WARPS) cp_async16(&Bs[i], src + i);
+        } else {
+            for (int i = tid; i < cnt; i += 32 * YF_WARPS) Bs[i] = __ldg(src + i);
+        }
     }
-    // the prior tables, copied once per CTA: thresholds | beta_probs | beta_cumsum | boltz_fact | boltz_exp
+    // the prior tables, copied once per CTA: thresholds | beta_probs | boltz_fact | boltz_exp
     double* tabs = reinterpret_cast<double*>(smem_raw + lay.off_tab);
     const int nth = p.n_thresholds, nbz = lay.max_troughs + 1;
-    for (int i = tid; i < nth; i += 32 * YF_WARPS) { tabs[i] = __ldg(p.thresholds + i); tabs[nth + i] = __ldg(p.beta_probs + i); }
-    for (int i = tid; i <= nth; i += 32 * YF_WARPS) tabs[2 * nth + i] = __ldg(p.beta_cumsum + i);
-    for (int i = tid; i < nbz; i += 32 * YF_WARPS) { tabs[3 * nth + 1 + i] = __ldg(p.boltz_fact + i); tabs[3 * nth + 1 + nbz + i] = __ldg(p.boltz_exp + i); }
-    const YinTables tb{tabs, tabs + nth, tabs + 2 * nth, tabs + 3 * nth + 1, tabs + 3 * nth + 1 + nbz};
+    for (int i = tid; i < nth; i += 32 * YF_WARPS) { cp_async8(&tabs[i], p.thresholds + i); cp_async8(&tabs[nth + i], p.beta_probs + i); }
+    for (int i = tid; i < nbz; i += 32 * YF_WARPS) { cp_async8(&tabs[2 * nth + i], p.boltz_fact + i); cp_async8(&tabs[2 * nth + nbz + i], p.boltz_exp + i); }
+    const YinTables tb{tabs, tabs + nth, p.beta_cumsum, tabs + 2 * nth, tabs + 2 * nth + nbz};
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (warp >= n_fr) return;
     unsigned char* wbase = smem_raw + lay.off_warp + warp * lay.warp_bytes;
@@ -775,8 +803,7 @@ yin_frame_kernel(const aegis_yin_params p, const YinFrameLayout lay, const int g
     for (int tau = lo; tau < hi; ++tau) {
         run += static_cast<double>(dbuf[tau]);
         if (tau >= minp) {
-            const double cm = static_cast<double>(static_cast<float>(base + run)) / static_cast<double>(tau);
-            const double yv = static_cast<double>(dbuf[tau]) / (cm + DBL_MIN);
+            const double yv = cmnd_value(dbuf[tau], static_cast<double>(static_cast<float>(base + run)), tau);
             yin[tau - minp] = yv;
             if (p.cmnd_out != nullptr) p.cmnd_out[(static_cast<long long>(clip) * T + t) * L + (tau - minp)] = yv;
         }
@@ -826,12 +853,17 @@ extern "C" int aegis_yin_candidates(const aegis_yin_params* p, void* stream) {
         lay.off_b = ((lay.span * 4 + 15) / 16) * 16;
         lay.max_troughs = L / 2 + 1 < YIN_MAX_TROUGHS ? L / 2 + 1 : YIN_MAX_TROUGHS;
         lay.off_tab = lay.off_b + (((YF_WARPS + 1) * b_pitch * 4 + 15) / 16) * 16;
-        lay.off_warp = lay.off_tab + (((3 * p->n_thresholds + 1 + 2 * (lay.max_troughs + 1)) * 8 + 15) / 16) * 16;
+        lay.off_warp = lay.off_tab + (((2 * p->n_thresholds + 2 * (lay.max_troughs + 1)) * 8 + 15) / 16) * 16;
+        // per warp: the CMND row, then the difference row d[] -- dead once the CMND is written -- sharing its bytes with the
+        // trough lists (first written after that): 56 KB per CTA instead of 65, four CTAs per SM instead of three
         int o = ((L * 8 + 15) / 16) * 16;
-        lay.off_d = o;       o += (((p->max_period + 1) * 4 + 15) / 16) * 16;
-        lay.off_tp = o;      o += ((lay.max_troughs * 8 + 15) / 16) * 16;
-        lay.off_tk = o;      o += ((lay.max_troughs * 2 + 15) / 16) * 16;
-        lay.off_tq = o;      o += ((lay.max_troughs + 15) / 16) * 16;
+        const int d_bytes = (((p->max_period + 1) * 4 + 15) / 16) * 16;
+        lay.off_d = o;
+        lay.off_tp = o;
+        int q = o + ((lay.max_troughs * 8 + 15) / 16) * 16;
+        lay.off_tk = q;      q += ((lay.max_troughs * 2 + 15) / 16) * 16;
+        lay.off_tq = q;      q += ((lay.max_troughs + 15) / 16) * 16;
+        o = (q - o > d_bytes) ? q : o + d_bytes;
         lay.warp_bytes = o;
         lay.total_bytes = lay.off_warp + YF_WARPS * lay.warp_bytes;
         AEGIS_REQUIRE(lay.total_bytes <= 227 * 1024, "aegis_yin_candidates: %d B shared memory needed for max_period=%d", lay.total_bytes, p->max_period);

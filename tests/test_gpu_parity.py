@@ -789,6 +789,34 @@ def test_financial_rsi_closed_form_equals_the_stepwise_walk(dev, monkeypatch):
     print("events kept per threshold:", dropped)
 
 
+def test_logic_filters_on_clips_too_long_for_the_staged_walk(dev):
+    """K7 / K8 stage a clip's frame rows in shared memory when they fit (T <= 20 000 / 9 000 frames); longer clips -- the
+    one-hour recording of cfg4 -- walk the global rows.  Both logic filters on 21 000-frame clips == the restatements."""
+    from oracle import financial_events as FE
+    from spectrogram_midi_b200 import midi_logic as M
+
+    T = 21000
+    clips = [_fin_frames(4000 + i, T, steady_grid=bool(i)) for i in range(2)]
+    stack = [torch.from_numpy(np.stack([c[j] for c in clips])).to(dev) for j in range(5)]
+    res = P.core.note_events_financial(*stack, sr=22050, hop_length=512)
+    for c, (rake, f0, vf, vp, rms) in enumerate(clips):
+        want = FE.get_midi_events_financial(rake, f0, vf, vp, rms, 22050, 512)
+        wi, wc, wk = FE.events_rows(want)
+        gi, gc, gk = FE.events_rows(P.core.fin_events_to_list(res, c))
+        np.testing.assert_array_equal(gi, wi, err_msg=f"v2 clip {c}")
+        np.testing.assert_allclose(gc, wc, rtol=1e-12, atol=0)
+        assert (gk is None) == (wk is None) and (gk is None or gk[:2] == wk[:2])
+        assert len(want) > 50
+        # v1 filter (K7) on continuous pitches: see test_note_events_random_frames_equal_oracle for why not pYIN's grid
+        f0c = np.where(vf, np.nan_to_num(f0) * 2.0 ** (np.random.default_rng(c).uniform(-3, 3, T) / 1200.0), 0.0)
+        got = M.get_midi_events(rake, f0c, vf, vp, rms, 22050, 512, 0.7)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = R.get_midi_events(rake, f0c, vf, vp, rms, 22050, 512, 0.7)
+        assert len(ref) > 50
+        assert _event_rows(got)[0].tolist() == _event_rows(ref)[0].tolist(), f"v1 clip {c}"
+
+
 def test_financial_logic_filter_fallback_branch_matches_reference_golden(dev):
     """get_midi_events_financial(use_financial=False) -- the reference function's fallback branch
     (midi_logic_financial.py:178-196 + detect_articulations_financial per note; never taken by the v2 engine): host frame loop,
