@@ -593,105 +593,143 @@ yin_direct_kernel(const aegis_yin_params p, const YinDirectLayout lay, const int
 // registers per thread, then everything per frame at high occupancy (the energy / CMND / candidate stage is a chain of
 // short dependent steps: it wants warps, not registers).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int YS_SPAN_MAX = YD_BLOCKS * 512 + 1 + 16 * 64;                // 16 blocks + look-ahead of the widest lag range
-constexpr int YS_PHYS = YS_SPAN_MAX + YS_SPAN_MAX / 16 + 32;
+// Lane map of the block-sum kernel: lane = (lag group g = lane & 15, sample half h = lane >> 4).  A lane owns YB_WG = 17
+// consecutive lags (16 groups x 17 = 272 lags per pass; E2 at 22.05 kHz needs 269, at 44.1 kHz 537 = two passes) and walks
+// its half of the block's 512 samples with a 17-entry sliding window in registers: per sample one broadcast load of
+// x[n], one load of the sample entering the window, 17 packed FMAs (the two halves of a register pair are the two blocks
+// of the warp's block pair).  Nothing is reduced across lanes but the two halves (one shuffle per lag).  The halves are
+// 272 / 240 samples, not 256 / 256: 272 = 16 * 17 is a whole number of window rotations and puts the upper half's
+// loads 16 banks from the lower half's (17 g mod 32 covers 16 banks), so neither the broadcast nor the window loads
+// conflict and the samples need no skewed layout.  (The first cut owned 16 samples x 16 lags per lane and reduced over
+// all 32 lanes: 39 % of its instructions were the transpose-reduce and the pipe sat at 60 %.)
+constexpr int YB_WG = 17;
+constexpr int YB_PASS_LAGS = 16 * YB_WG;     // 272
+constexpr int YB_LOWER = 16 * YB_WG;         // 272 samples for h = 0, 240 for h = 1
+constexpr int YB_MAX_PASSES = 4;             // lags <= 1087 >= FFT_N / 2 - 1
+constexpr int YS_SPAN_MAX = YD_BLOCKS * 512 + 1 + YB_MAX_PASSES * YB_PASS_LAGS + 64;
+constexpr int YS_PHYS = ((YS_SPAN_MAX + 3) / 4) * 4;
 
-// 4-byte cp.async with zero fill: copies src_bytes (4 or 0) bytes and zero-fills the rest of the 4
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
 }
+// 4-byte cp.async with zero fill: copies src_bytes (4 or 0) bytes and zero-fills the rest of the 4
 __device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gmem_src, int src_bytes) {
     const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
 
-// block sums of blocks [16 run, 16 run + 16) of a clip -> bsum[clip][block][b_pitch].  Persistent CTAs (two per SM) walk
-// the runs; the samples of the NEXT run are requested with cp.async while this run's sums are being accumulated, so the
-// FMA pipe does not idle behind the fill at the start of every run (ncu: 6 % of the stall samples sat on the fill before).
-__global__ void __launch_bounds__(YD_THREADS, 2)
-yin_blocksum_kernel(const aegis_yin_params p, const int n_groups, const int b_pitch, const int runs_per_clip, const int n_blocks,
+// position of lag tau in a block-sum row: pass-major, then lag-in-group, then group (what a warp stores side by side)
+__host__ __device__ __forceinline__ int blocksum_index(int tau) {
+    const int pass = tau / YB_PASS_LAGS, r = tau - pass * YB_PASS_LAGS, g = r / YB_WG;
+    return pass * YB_PASS_LAGS + 16 * (r - g * YB_WG) + g;
+}
+
+// one rotation of the window = 17 samples.  MASKED: the upper half-warp has run out of its 240 samples at sample `n0 + s`
+template <bool MASKED>
+__device__ __forceinline__ void blocksum_rotation(const float* __restrict__ pa, const float* __restrict__ pr, unsigned long long (&c)[YB_WG],
+                                                  unsigned long long (&R)[YB_WG], const int n0, const bool upper) {
+#pragma unroll
+    for (int s_ = 0; s_ < YB_WG; ++s_) {
+        float a0 = pa[s_], a1 = pa[512 + s_];
+        if (MASKED) {
+            const bool off = upper && (n0 + s_ >= 512 - YB_LOWER);
+            a0 = off ? 0.f : a0;
+            a1 = off ? 0.f : a1;
+        }
+        const unsigned long long a = pack2(a0, a1);
+#pragma unroll
+        for (int j = 0; j < YB_WG; ++j) c[j] = ffma2(a, R[(s_ + j) % YB_WG], c[j]);
+        R[s_] = pack2(pr[YB_WG + s_], pr[512 + YB_WG + s_]);
+    }
+}
+
+// block sums of blocks [16 run, 16 run + 16) of a clip -> bsum[clip][block][b_pitch] (lag tau at blocksum_index(tau)).
+// Persistent CTAs (two per SM) walk the runs; the samples of the NEXT run are requested with cp.async while this run's
+// sums are being accumulated, so the FMA pipe does not idle behind the fill at the start of every run.
+#ifndef AEGIS_YB_MINB
+#define AEGIS_YB_MINB 2
+#endif
+__global__ void __launch_bounds__(YD_THREADS, AEGIS_YB_MINB)
+yin_blocksum_kernel(const aegis_yin_params p, const int n_passes, const int b_pitch, const int runs_per_clip, const int n_blocks,
                     const long long n_runs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* const bufs = reinterpret_cast<float*>(smem_raw);                  // two sample buffers of YS_PHYS floats
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long N = p.n_samples;
-    const int span = YD_BLOCKS * 512 + 1 + 16 * n_groups;
+    const int span = YD_BLOCKS * 512 + 1 + n_passes * YB_PASS_LAGS + 64;
+    const int ys_phys = ((span + 3) / 4) * 4;                                // floats per sample buffer
 
-    auto request = [&](long long run, float* xs) {      // samples of `run` -> xs (skewed), zeros outside the clip
+    auto request = [&](long long run, float* xs) {      // samples of `run` -> xs, zeros outside the clip
         const int clip = static_cast<int>(run / runs_per_clip);
         const int k0 = static_cast<int>(run - static_cast<long long>(clip) * runs_per_clip) * YD_BLOCKS;
         const float* __restrict__ yc = p.y + static_cast<long long>(clip) * p.clip_stride;
         const long long g0 = static_cast<long long>(k0) * 512 - p.pad;       // clip sample of m = 0; block b = m in [512 b + 1, 512 b + 512]
-        for (int m = tid; m < span; m += YD_THREADS) {
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(yc) & 15) == 0) && ((g0 & 3) == 0);
+        for (int m = tid * 4; m < span; m += 4 * YD_THREADS) {
             const long long gi = g0 + m;
-            const bool in = gi >= 0 && gi < N;
-            cp_async4_zfill(&xs[m + (m >> 4)], yc + (in ? gi : 0), in ? 4 : 0);
+            if (vec_ok && gi >= 0 && gi + 3 < N) {
+                cp_async16(&xs[m], yc + gi);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool in = gi + j >= 0 && gi + j < N;
+                    cp_async4_zfill(&xs[m + j], yc + (in ? gi + j : 0), in ? 4 : 0);
+                }
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    const int g = lane & 15;
+    const bool upper = (lane & 16) != 0;
     long long run = blockIdx.x;
     int cur = 0;
     if (run < n_runs) request(run, bufs);
     for (; run < n_runs; run += gridDim.x, cur ^= 1) {
         const long long next = run + gridDim.x;
         if (next < n_runs) {
-            request(next, bufs + (cur ^ 1) * YS_PHYS);
+            request(next, bufs + (cur ^ 1) * ys_phys);
             asm volatile("cp.async.wait_group 1;" ::: "memory");           // this run's samples have landed (the next run's may be in flight)
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const float* xs = bufs + cur * YS_PHYS;
+        const float* xs = bufs + cur * ys_phys;
         const int clip = static_cast<int>(run / runs_per_clip);
         const int k0 = static_cast<int>(run - static_cast<long long>(clip) * runs_per_clip) * YD_BLOCKS;
         if (k0 + 2 * warp < n_blocks) {
-            const float* pa = xs + 544 * (2 * warp) + 17 * lane + 1;             // phys(512 b + 1 + 16 l); block 2w+1 is 544 words further
-            unsigned long long a[16], R[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int o = i + ((1 + i) >> 4);
-                a[i] = pack2(pa[o], pa[544 + o]);
-                R[i] = a[i];
-            }
-            const int kb = k0 + 2 * warp + (lane >> 4);                           // the block this lane stores
-            float* brow = p.block_sums + (static_cast<long long>(clip) * n_blocks + min(kb, n_blocks - 1)) * b_pitch + (lane & 15);
+            const int kb = k0 + 2 * warp + (upper ? 1 : 0);                     // the block this lane stores
+            float* brow = p.block_sums + (static_cast<long long>(clip) * n_blocks + min(kb, n_blocks - 1)) * b_pitch + g;
             const bool store = kb < n_blocks;
-            const bool hi_half = (lane & 16) != 0;
+            const float* base = xs + 512 * (2 * warp) + 1 + (upper ? YB_LOWER : 0);   // first sample of this lane's half; block 2w+1 is 512 further
 #pragma unroll 1
-            for (int g = 0; g < n_groups; ++g) {
-                const float* pw = pa + 17 * g;
-                unsigned long long c[16];
+            for (int pass = 0; pass < n_passes; ++pass) {
+                const int lag0 = pass * YB_PASS_LAGS + YB_WG * g;
+                const float* pa = base;
+                const float* pr = base + lag0;
+                unsigned long long c[YB_WG], R[YB_WG];
 #pragma unroll
-                for (int s_ = 0; s_ < 16; ++s_) {
-                    unsigned long long acc = 0ull;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) acc = ffma2(a[i], R[(s_ + i) & 15], acc);
-                    c[s_] = acc;
-                    const int o = s_ + 17 + (s_ == 15 ? 1 : 0);
-                    R[s_] = pack2(pw[o], pw[544 + o]);
+                for (int j = 0; j < YB_WG; ++j) {
+                    c[j] = 0ull;
+                    R[j] = pack2(pr[j], pr[512 + j]);
                 }
-                float v[16];
+                constexpr int FULL = (512 - YB_LOWER) / YB_WG;                   // rotations both halves run unmasked (14)
+#pragma unroll 1
+                for (int it = 0; it < FULL; ++it, pa += YB_WG, pr += YB_WG) blocksum_rotation<false>(pa, pr, c, R, YB_WG * it, upper);
+#pragma unroll 1
+                for (int it = FULL; it < YB_LOWER / YB_WG; ++it, pa += YB_WG, pr += YB_WG) blocksum_rotation<true>(pa, pr, c, R, YB_WG * it, upper);
+                // the other half's sum: the lower lanes keep block 2w (low words), the upper lanes block 2w+1 (high words)
 #pragma unroll
-                for (int s_ = 0; s_ < 16; ++s_) {
+                for (int j = 0; j < YB_WG; ++j) {
                     float lo, hi;
-                    unpack2(c[s_], lo, hi);
-                    const float mine = hi_half ? hi : lo, other = hi_half ? lo : hi;
-                    v[s_] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+                    unpack2(c[j], lo, hi);
+                    const float keep = upper ? hi : lo, send = upper ? lo : hi;
+                    const float v = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    if (store && lag0 + j <= p.max_period) brow[pass * YB_PASS_LAGS + 16 * j] = v;
                 }
-#pragma unroll
-                for (int w_ = 8; w_ >= 1; w_ >>= 1) {
-                    const bool up = (lane & w_) != 0;
-#pragma unroll
-                    for (int s_ = 0; s_ < w_; ++s_) {
-                        const float keep = up ? v[s_ + w_] : v[s_], send = up ? v[s_] : v[s_ + w_];
-                        v[s_] = keep + __shfl_xor_sync(0xffffffffu, send, w_);
-                    }
-                }
-                if (store) brow[16 * g] = v[0];
             }
         }
         __syncthreads();   // every warp is done with this buffer before the run after next is requested into it
@@ -784,13 +822,20 @@ yin_frame_kernel(const aegis_yin_params p, const YinFrameLayout lay, const int g
     const float* B1 = B0 + lay.b_pitch;
     run = 0.0;
     double dsum = 0.0;
+    // position of lag `lo` in a block-sum row (blocksum_index), stepped along with tau
+    int bj = lo % YB_PASS_LAGS, bi = lo - bj;
+    { const int bg = bj / YB_WG; bj -= bg * YB_WG; bi += bg; }
 #pragma unroll 1
     for (int tau = lo; tau < hi; ++tau) {
         const float u1 = f[FFT_N / 2 + tau], u0 = f[tau];
         run += static_cast<double>(u1 * u1) - static_cast<double>(u0 * u0);
         float e = static_cast<float>(base + run);
         if (fabsf(e) < 1e-6f) e = 0.f;
-        float acf = B0[tau] + B1[tau];
+        float acf = B0[bi + 16 * bj] + B1[bi + 16 * bj];
+        if (++bj == YB_WG) {                       // next group; after the 16th, the next pass
+            bj = 0;
+            bi += ((bi & 15) == 15) ? YB_PASS_LAGS - 15 : 1;
+        }
         if (fabsf(acf) < 1e-6f) acf = 0.f;
         const float dv = (e0f + e) - 2.0f * acf;
         dbuf[tau] = dv;
@@ -829,21 +874,23 @@ extern "C" int aegis_yin_candidates(const aegis_yin_params* p, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (p->hop == 512 && p->block_sums != nullptr) {   // the reference's hop, workspace given: block sums, then the per-frame stage
         const int L = p->max_period - p->min_period + 1;
-        const int n_groups = (p->max_period + 1 + 15) / 16;
-        const int b_pitch = n_groups * 16;
+        const int n_passes = (p->max_period + 1 + YB_PASS_LAGS - 1) / YB_PASS_LAGS;
+        AEGIS_REQUIRE(n_passes <= YB_MAX_PASSES, "aegis_yin_candidates: max_period=%d needs more block-sum passes than compiled", p->max_period);
+        const int b_pitch = n_passes * YB_PASS_LAGS;
         const int n_blocks = p->n_frames + 1;
         const int runs_per_clip = (n_blocks + YD_BLOCKS - 1) / YD_BLOCKS;
         const long long n_runs = static_cast<long long>(runs_per_clip) * p->n_clips;
         {
-            const int smem = 2 * YS_PHYS * static_cast<int>(sizeof(float));
+            const int span = YD_BLOCKS * 512 + 1 + n_passes * YB_PASS_LAGS + 64;
+            const int smem = 2 * (((span + 3) / 4) * 4) * static_cast<int>(sizeof(float));
             cudaError_t e = cudaFuncSetAttribute(yin_blocksum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) {
                 set_error("aegis_yin_candidates: cannot reserve %d B shared memory: %s", smem, cudaGetErrorString(e));
                 return 2;
             }
-            const long long max_grid = 2LL * sm_count();
+            const long long max_grid = static_cast<long long>(AEGIS_YB_MINB) * sm_count();
             const unsigned grid = static_cast<unsigned>(n_runs < max_grid ? n_runs : max_grid);
-            yin_blocksum_kernel<<<grid, YD_THREADS, smem, st>>>(*p, n_groups, b_pitch, runs_per_clip, n_blocks, n_runs);
+            yin_blocksum_kernel<<<grid, YD_THREADS, smem, st>>>(*p, n_passes, b_pitch, runs_per_clip, n_blocks, n_runs);
         }
         if (int rc = check_launch("aegis_yin_candidates(block sums)")) return rc;
         YinFrameLayout lay{};
@@ -918,9 +965,9 @@ extern "C" int aegis_yin_candidates(const aegis_yin_params* p, void* stream) {
     return check_launch("aegis_yin_candidates");
 }
 
-// bytes of the block-sum workspace of aegis_yin_candidates (hop 512): (n_frames + 1) rows of 16 * ceil((max_period + 1) / 16) floats per clip
+// bytes of the block-sum workspace of aegis_yin_candidates (hop 512): (n_frames + 1) rows of 272 * ceil((max_period + 1) / 272) floats per clip
 extern "C" long long aegis_yin_workspace_bytes(int n_clips, int n_frames, int max_period) {
     if (n_clips <= 0 || n_frames <= 0 || max_period < 0) return 0;
-    const long long pitch = 16LL * ((max_period + 1 + 15) / 16);
+    const long long pitch = static_cast<long long>(aegis::YB_PASS_LAGS) * ((max_period + 1 + aegis::YB_PASS_LAGS - 1) / aegis::YB_PASS_LAGS);
     return static_cast<long long>(n_clips) * (n_frames + 1) * pitch * 4;
 }
