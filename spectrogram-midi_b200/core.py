@@ -212,7 +212,8 @@ def yin_candidates(y: torch.Tensor, cfg: tables.PyinConfig, *, center: bool = Tr
                    max_cand: Optional[int] = None, pad: Optional[int] = None, n_frames: Optional[int] = None,
                    want_cmnd: bool = False, split: bool = True, out: Optional[dict] = None) -> dict:
     """Sparse pYIN observations per frame (bins ascending, unique) + voiced probability.  ``split=False`` withholds the
-    block-sum workspace, so hop 512 runs as one fused kernel instead of two (identical results; for tests).  ``out`` may
+    block-sum workspace, so hop 512 runs as one fused kernel instead of two (same results to float32 rounding of the block
+    sums, not bit for bit; for tests).  ``out`` may
     hold preallocated ``cand_bin`` / ``cand_prob`` / ``cand_count`` / ``voiced_prob`` tensors for these clips (slices of
     batch-wide buffers: ``batch.TranscribePipeline`` fills them piece by piece and decodes whole groups)."""
     _check_fft(cfg.frame_length, cfg.hop_length)
@@ -255,7 +256,7 @@ def yin_candidates(y: torch.Tensor, cfg: tables.PyinConfig, *, center: bool = Tr
     P.cand_bin, P.cand_prob, P.cand_count = cand_bin.data_ptr(), cand_prob.data_ptr(), cand_count.data_ptr()
     P.voiced_prob, P.overflow = voiced_prob.data_ptr(), overflow.data_ptr()
     work = None
-    if split and cfg.hop_length == 512 and n_fr > 0:   # block-sum workspace: the two-kernel form of K2 (same results as the fused one)
+    if split and cfg.hop_length == 512 and n_fr > 0:   # block-sum workspace: the two-kernel form of K2
         nbytes = int(nat.load().aegis_yin_workspace_bytes(n_clips, T, cfg.max_period))
         work = torch.empty(((nbytes + 3) // 4,), dtype=torch.float32, device=dev)
         P.block_sums = work.data_ptr()
