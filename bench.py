@@ -418,6 +418,12 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    # Python's cyclic collector stays off while anything is timed (as timeit does): with the corpus plan's ~10^5 small objects
+    # alive, a full collection landing inside a step cost tens of milliseconds (seen as one v2 step in five at 2x)
+    import gc
+
+    gc.collect()
+    gc.disable()
     sampler = ClockSampler(local_rank)
     sampler.start()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -518,9 +524,8 @@ def run_gpu(args):
             for _ in range(3):
                 transcribe_v2()
             barrier()
-            # this pipeline makes several host round trips per step (overflow checks between its kernels), so a host
-            # hiccup shows up as GPU idle time: one step in six took 2-3x the others in back-to-back runs.  Every step is
-            # timed on its own and the MEDIAN is reported (the v1 line above and the headline stay plain K-step means)
+            # every step is timed on its own and the MEDIAN is reported, with the worst step beside it (a full Python garbage
+            # collection inside one step used to double it; the collector is now off while anything is timed)
             per_step = []
             for _ in range(tr_steps + 2):
                 a = ev()
@@ -549,6 +554,7 @@ def run_gpu(args):
               "v2_ms_worst": v2_ms_worst if v2_ms is not None else None}
     del pcm_host
     clocks = sampler.stop()   # sampled every 200 ms from the headline loop to the end of the transcription section
+    gc.enable()
 
     # ---- long clip (BASELINE cfg4) at N > 1: one hour at 44.1 kHz over the ranks, exact and windowed, against one rank alone
     long_clip = None
