@@ -800,13 +800,14 @@ def test_financial_rsi_closed_form_equals_the_stepwise_walk(dev, monkeypatch):
     print("events kept per threshold:", dropped)
 
 
-def test_logic_filters_on_clips_too_long_for_the_staged_walk(dev):
-    """K7 / K8 stage a clip's frame rows in shared memory when they fit (T <= 20 000 / 9 000 frames); longer clips -- the
-    one-hour recording of cfg4 -- walk the global rows.  Both logic filters on 21 000-frame clips == the restatements."""
+@pytest.mark.parametrize("T", [8500, 21000])
+def test_logic_filters_on_long_clips(dev, T):
+    """K7 / K8 stage a clip's frame rows in shared memory when they fit (T <= 20 000 / 9 000 frames: up to 200 KB, opted in
+    per launch); longer clips -- the one-hour recording of cfg4 -- walk the global rows.  Both logic filters on 8 500-frame
+    (staged, large shared-memory carve-out) and 21 000-frame (unstaged) clips == the restatements."""
     from oracle import financial_events as FE
     from spectrogram_midi_b200 import midi_logic as M
 
-    T = 21000
     clips = [_fin_frames(4000 + i, T, steady_grid=bool(i)) for i in range(2)]
     stack = [torch.from_numpy(np.stack([c[j] for c in clips])).to(dev) for j in range(5)]
     res = P.core.note_events_financial(*stack, sr=22050, hop_length=512)
