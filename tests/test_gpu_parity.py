@@ -1146,7 +1146,7 @@ def test_midi_note_events_identical_to_reference(dev, golden):
             n = len(res["f0"])
             agree = (roll(got, n) == roll(want, n)).mean()
             print(f"{name}: events {len(got)} vs {len(want)}, frame-level note agreement {agree:.4f}")
-            assert agree >= 0.97
+            assert agree >= 0.99 and len(got) == len(want)   # round 2: identical on this clip (was 0.97 with the FFT-based K2)
         total += len(ev)
     assert total >= 10
 
