@@ -159,8 +159,7 @@ typedef struct {
     double* cmnd_out;          /* optional [n_clips * n_frames][max_period - min_period + 1] CMND curves, or NULL */
     float* block_sums;         /* optional workspace of aegis_yin_workspace_bytes(...) bytes (hop 512 only): with it the
                                   autocorrelation block sums and the per-frame stage run as two kernels (faster: each at
-                                  its own register budget); NULL = one fused kernel, which sums a block's products in a
-                                  different order (agrees to float32 rounding of the sums, same candidates; not bit for bit) */
+                                  its own register budget); NULL = one fused kernel, bit-identical results */
 } aegis_yin_params;
 
 int aegis_yin_candidates(const aegis_yin_params* p, void* stream);

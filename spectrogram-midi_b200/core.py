@@ -212,8 +212,7 @@ def yin_candidates(y: torch.Tensor, cfg: tables.PyinConfig, *, center: bool = Tr
                    max_cand: Optional[int] = None, pad: Optional[int] = None, n_frames: Optional[int] = None,
                    want_cmnd: bool = False, split: bool = True, out: Optional[dict] = None) -> dict:
     """Sparse pYIN observations per frame (bins ascending, unique) + voiced probability.  ``split=False`` withholds the
-    block-sum workspace, so hop 512 runs as one fused kernel instead of two (same results to float32 rounding of the block
-    sums, not bit for bit; for tests).  ``out`` may
+    block-sum workspace, so hop 512 runs as one fused kernel instead of two (identical results; for tests).  ``out`` may
     hold preallocated ``cand_bin`` / ``cand_prob`` / ``cand_count`` / ``voiced_prob`` tensors for these clips (slices of
     batch-wide buffers: ``batch.TranscribePipeline`` fills them piece by piece and decodes whole groups)."""
     _check_fft(cfg.frame_length, cfg.hop_length)

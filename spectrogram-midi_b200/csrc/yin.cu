@@ -413,12 +413,12 @@ yin_fft_kernel(const aegis_yin_params p, const int pairs_per_clip, const long lo
 constexpr int YD_THREADS = 256;                    // 8 warps = 8 block pairs
 constexpr int YD_BLOCKS = 16;                      // blocks of 512 products per CTA
 constexpr int YD_FRAMES = YD_BLOCKS - 1;           // frame i = block i + block i+1
-constexpr int YD_SPAN = YD_BLOCKS * 512 + 1024;    // samples m = 0 .. 9215 relative to the first frame's first sample
-constexpr int YD_PHYS = YD_SPAN + YD_SPAN / 16 + 32;   // skewed layout phys(m) = m + (m >> 4), + slack for one look-ahead load
+// samples a run of 16 blocks reads with n_passes lag passes: m < 16 * 512 + 1 + 272 n_passes + 64 (the sliding windows look ahead)
 
 struct YinDirectLayout {      // byte offsets into dynamic shared memory (computed on the host from max_period)
-    int n_groups;             // lag groups of 16
-    int b_pitch;              // floats per block row of B (n_groups * 16)
+    int n_passes;             // lag passes of 272
+    int span;                 // samples staged per run
+    int b_pitch;              // floats per block row of B (272 * n_passes; lag tau at blocksum_index(tau))
     int off_b, off_warp;      // B sums; first per-warp scratch area
     int warp_bytes;           // per-warp scratch: yin (double), d (float), tp (double), tk (u16), tq (u8)
     int off_d, off_tp, off_tk, off_tq;   // inside a warp's area
@@ -449,150 +449,6 @@ __device__ __forceinline__ double warp_scan_incl_d(double v, int lane) {
     return v;
 }
 
-__global__ void __launch_bounds__(YD_THREADS, 2)
-yin_direct_kernel(const aegis_yin_params p, const YinDirectLayout lay, const int runs_per_clip) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* xs = reinterpret_cast<float*>(smem_raw);
-    float* Bs = reinterpret_cast<float*>(smem_raw + lay.off_b);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int clip = blockIdx.x / runs_per_clip;
-    const int t0 = (blockIdx.x - clip * runs_per_clip) * YD_FRAMES;
-    const int T = p.n_frames;
-    const long long N = p.n_samples;
-    const int maxp = p.max_period, minp = p.min_period;
-    const int L = maxp - minp + 1;
-    const float* __restrict__ yc = p.y + static_cast<long long>(clip) * p.clip_stride;
-    const long long g0 = static_cast<long long>(t0) * 512 - p.pad;   // clip sample of m = 0
-    const int n_fr = min(YD_FRAMES, T - t0);                         // frames of this run
-    // samples this run reads: m < 512 * (n_fr + 1) + 1 + 16 * 31 + 15 + maxp ... simply fill what the frames span
-    const int m_end = min(YD_SPAN, 512 * (n_fr - 1) + 2048);
-
-    // ---- phase A: samples -> shared, skewed (zeros outside the clip: center padding)
-    for (int m = tid; m < YD_SPAN; m += YD_THREADS) {
-        const long long gi = g0 + m;
-        xs[m + (m >> 4)] = (m < m_end && gi >= 0 && gi < N) ? __ldg(yc + gi) : 0.f;
-    }
-    if (tid < 32) xs[YD_SPAN + YD_SPAN / 16 + tid] = 0.f;
-    __syncthreads();
-
-    // ---- phase B: block sums B[b][tau] = sum_{n in block b} x[n] x[n + tau], block b = samples m = 512 b + 1 .. 512 b + 512.
-    // Warp w: blocks 2w (lo) and 2w+1 (hi).  Lane l: the 16 samples m = 512 b + 1 + 16 l + i.
-    if (2 * warp < n_fr + 1) {
-        const float* pa = xs + 544 * (2 * warp) + 17 * lane + 1;    // phys(512 b + 1 + 16 l) ; block 2w+1 is 544 words further
-        unsigned long long a[16], R[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int o = i + ((1 + i) >> 4);
-            a[i] = pack2(pa[o], pa[544 + o]);
-            R[i] = a[i];                                             // window W[j] = x[.. + j], j = 0 .. 15 (tau = 0)
-        }
-        float* brow = Bs + (2 * warp + (lane >> 4)) * lay.b_pitch + (lane & 15);
-        const bool hi_half = (lane & 16) != 0;
-#pragma unroll 1
-        for (int g = 0; g < lay.n_groups; ++g) {
-            const float* pw = pa + 17 * g;                           // W[16 g + s + 16] sits at pw[s + 17 + (s == 15)]
-            unsigned long long c[16];
-#pragma unroll
-            for (int s_ = 0; s_ < 16; ++s_) {
-                unsigned long long acc = 0ull;                       // (+0.f, +0.f)
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc = ffma2(a[i], R[(s_ + i) & 15], acc);
-                c[s_] = acc;
-                const int o = s_ + 17 + (s_ == 15 ? 1 : 0);
-                R[s_] = pack2(pw[o], pw[544 + o]);
-            }
-            // transpose-reduce: 16 lags x 2 blocks = 32 values over 32 lanes; lane q ends with block (q >> 4), lag 16 g + (q & 15)
-            float v[16];
-#pragma unroll
-            for (int s_ = 0; s_ < 16; ++s_) {
-                float lo, hi;
-                unpack2(c[s_], lo, hi);
-                const float mine = hi_half ? hi : lo, other = hi_half ? lo : hi;
-                v[s_] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
-            }
-#pragma unroll
-            for (int w_ = 8; w_ >= 1; w_ >>= 1) {
-                const bool up = (lane & w_) != 0;
-#pragma unroll
-                for (int s_ = 0; s_ < w_; ++s_) {
-                    const float keep = up ? v[s_ + w_] : v[s_], send = up ? v[s_] : v[s_ + w_];
-                    v[s_] = keep + __shfl_xor_sync(0xffffffffu, send, w_);
-                }
-            }
-            brow[16 * g] = v[0];
-        }
-    }
-    __syncthreads();
-
-    // ---- phases E + C, one warp per frame: energies, difference function, cumulative mean, CMND; then the candidates
-    unsigned char* wbase = smem_raw + lay.off_warp + warp * lay.warp_bytes;
-    double* yin = reinterpret_cast<double*>(wbase);
-    float* dbuf = reinterpret_cast<float*>(wbase + lay.off_d);
-    double* tp = reinterpret_cast<double*>(wbase + lay.off_tp);
-    unsigned short* tk = reinterpret_cast<unsigned short*>(wbase + lay.off_tk);
-    unsigned char* tq = wbase + lay.off_tq;
-    for (int fr = warp; fr < n_fr; fr += YD_THREADS / 32) {
-        const int t = t0 + fr;
-        const float* f = xs;                       // frame sample j = x[m = 512 fr + j]
-        auto fs = [&](int j) -> float { const int m = 512 * fr + j; return f[m + (m >> 4)]; };
-        double acc = 0.0;
-#pragma unroll 4
-        for (int j = 1 + lane; j <= FFT_N / 2; j += 32) { const float v = fs(j); acc += static_cast<double>(v * v); }
-        const double e0 = warp_sum_d(acc);
-        const int chunk = (maxp + 31) / 32;
-        const int lo = 1 + lane * chunk, hi = min(lo + chunk, maxp + 1);
-        double run = 0.0;
-#pragma unroll 1
-        for (int tau = lo; tau < hi; ++tau) {
-            const float u1 = fs(FFT_N / 2 + tau), u0 = fs(tau);
-            run += static_cast<double>(u1 * u1) - static_cast<double>(u0 * u0);
-        }
-        double incl = warp_scan_incl_d(run, lane);
-        double base = e0 + (incl - run);           // e0 + sum of the lower lanes' chunks
-        float e0f = static_cast<float>(e0);
-        if (fabsf(e0f) < 1e-6f) e0f = 0.f;
-        const float* B0 = Bs + fr * lay.b_pitch;
-        const float* B1 = B0 + lay.b_pitch;
-        run = 0.0;
-        double dsum = 0.0;
-#pragma unroll 1
-        for (int tau = lo; tau < hi; ++tau) {
-            const float u1 = fs(FFT_N / 2 + tau), u0 = fs(tau);
-            run += static_cast<double>(u1 * u1) - static_cast<double>(u0 * u0);
-            float e = static_cast<float>(base + run);
-            if (fabsf(e) < 1e-6f) e = 0.f;
-            float acf = B0[tau] + B1[tau];
-            if (fabsf(acf) < 1e-6f) acf = 0.f;
-            const float dv = (e0f + e) - 2.0f * acf;
-            dbuf[tau] = dv;
-            dsum += static_cast<double>(dv);
-        }
-        incl = warp_scan_incl_d(dsum, lane);
-        base = incl - dsum;
-        run = 0.0;
-        __syncwarp();
-#pragma unroll 1
-        for (int tau = lo; tau < hi; ++tau) {
-            run += static_cast<double>(dbuf[tau]);
-            if (tau >= minp) {
-                const double yv = cmnd_value(dbuf[tau], static_cast<double>(static_cast<float>(base + run)), tau);
-                yin[tau - minp] = yv;
-                if (p.cmnd_out != nullptr) p.cmnd_out[(static_cast<long long>(clip) * T + t) * L + (tau - minp)] = yv;
-            }
-        }
-        __syncwarp();
-        const YinTables tb{p.thresholds, p.beta_probs, p.beta_cumsum, p.boltz_fact, p.boltz_exp};
-        yin_candidates_of_frame<false>(p, tb, yin, L, minp, tk, tq, tp, lay.max_troughs, static_cast<long long>(clip) * T + t, lane);
-        __syncwarp();
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------------------------------
-// hop == 512, two kernels (used when the caller provides the block-sum workspace): the FMA-bound block sums at 128
-// registers per thread, then everything per frame at high occupancy (the energy / CMND / candidate stage is a chain of
-// short dependent steps: it wants warps, not registers).
-// ------------------------------------------------------------------------------------------------------------------
 // Lane map of the block-sum kernel: lane = (lag group g = lane & 15, sample half h = lane >> 4).  A lane owns YB_WG = 17
 // consecutive lags (16 groups x 17 = 272 lags per pass; E2 at 22.05 kHz needs 269, at 44.1 kHz 537 = two passes) and walks
 // its half of the block's 512 samples with a 17-entry sliding window in registers: per sample one broadcast load of
@@ -646,6 +502,140 @@ __device__ __forceinline__ void blocksum_rotation(const float* __restrict__ pa, 
     }
 }
 
+__global__ void __launch_bounds__(YD_THREADS, 2)
+yin_direct_kernel(const aegis_yin_params p, const YinDirectLayout lay, const int runs_per_clip) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* xs = reinterpret_cast<float*>(smem_raw);
+    float* Bs = reinterpret_cast<float*>(smem_raw + lay.off_b);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int clip = blockIdx.x / runs_per_clip;
+    const int t0 = (blockIdx.x - clip * runs_per_clip) * YD_FRAMES;
+    const int T = p.n_frames;
+    const long long N = p.n_samples;
+    const int maxp = p.max_period, minp = p.min_period;
+    const int L = maxp - minp + 1;
+    const float* __restrict__ yc = p.y + static_cast<long long>(clip) * p.clip_stride;
+    const long long g0 = static_cast<long long>(t0) * 512 - p.pad;   // clip sample of m = 0
+    const int n_fr = min(YD_FRAMES, T - t0);                         // frames of this run
+    const int m_end = 512 * (n_fr - 1) + 2048;                       // samples the frames of this run span
+
+    // ---- phase A: samples -> shared (zeros outside the clip: center padding; zeros past the run's last frame)
+    for (int m = tid; m < lay.span; m += YD_THREADS) {
+        const long long gi = g0 + m;
+        xs[m] = (m < m_end && gi >= 0 && gi < N) ? __ldg(yc + gi) : 0.f;
+    }
+    __syncthreads();
+
+    // ---- phase B: block sums B[b][tau] = sum_{n in block b} x[n] x[n + tau], block b = samples m = 512 b + 1 .. 512 b + 512,
+    // summed exactly as yin_blocksum_kernel sums them (same lane map, same order: the two forms of K2 give identical bits).
+    // Warp w: blocks 2w (low words) and 2w+1 (high words)
+    if (2 * warp < n_fr + 1) {
+        const int g = lane & 15;
+        const bool upper = (lane & 16) != 0;
+        float* brow = Bs + (2 * warp + (upper ? 1 : 0)) * lay.b_pitch + g;
+        const float* base = xs + 512 * (2 * warp) + 1 + (upper ? YB_LOWER : 0);
+#pragma unroll 1
+        for (int pass = 0; pass < lay.n_passes; ++pass) {
+            const int lag0 = pass * YB_PASS_LAGS + YB_WG * g;
+            const float* pa = base;
+            const float* pr = base + lag0;
+            unsigned long long c[YB_WG], R[YB_WG];
+#pragma unroll
+            for (int j = 0; j < YB_WG; ++j) {
+                c[j] = 0ull;
+                R[j] = pack2(pr[j], pr[512 + j]);
+            }
+            constexpr int FULL = (512 - YB_LOWER) / YB_WG;
+#pragma unroll 1
+            for (int it = 0; it < FULL; ++it, pa += YB_WG, pr += YB_WG) blocksum_rotation<false>(pa, pr, c, R, YB_WG * it, upper);
+#pragma unroll 1
+            for (int it = FULL; it < YB_LOWER / YB_WG; ++it, pa += YB_WG, pr += YB_WG) blocksum_rotation<true>(pa, pr, c, R, YB_WG * it, upper);
+#pragma unroll
+            for (int j = 0; j < YB_WG; ++j) {
+                float lo, hi;
+                unpack2(c[j], lo, hi);
+                const float keep = upper ? hi : lo, send = upper ? lo : hi;
+                brow[pass * YB_PASS_LAGS + 16 * j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phases E + C, one warp per frame: energies, difference function, cumulative mean, CMND; then the candidates
+    unsigned char* wbase = smem_raw + lay.off_warp + warp * lay.warp_bytes;
+    double* yin = reinterpret_cast<double*>(wbase);
+    float* dbuf = reinterpret_cast<float*>(wbase + lay.off_d);
+    double* tp = reinterpret_cast<double*>(wbase + lay.off_tp);
+    unsigned short* tk = reinterpret_cast<unsigned short*>(wbase + lay.off_tk);
+    unsigned char* tq = wbase + lay.off_tq;
+    for (int fr = warp; fr < n_fr; fr += YD_THREADS / 32) {
+        const int t = t0 + fr;
+        const float* f = xs;                       // frame sample j = x[m = 512 fr + j]
+        auto fs = [&](int j) -> float { return f[512 * fr + j]; };
+        double acc = 0.0;
+#pragma unroll 4
+        for (int j = 1 + lane; j <= FFT_N / 2; j += 32) { const float v = fs(j); acc += static_cast<double>(v * v); }
+        const double e0 = warp_sum_d(acc);
+        const int chunk = (maxp + 31) / 32;
+        const int lo = 1 + lane * chunk, hi = min(lo + chunk, maxp + 1);
+        double run = 0.0;
+#pragma unroll 1
+        for (int tau = lo; tau < hi; ++tau) {
+            const float u1 = fs(FFT_N / 2 + tau), u0 = fs(tau);
+            run += static_cast<double>(u1 * u1) - static_cast<double>(u0 * u0);
+        }
+        double incl = warp_scan_incl_d(run, lane);
+        double base = e0 + (incl - run);           // e0 + sum of the lower lanes' chunks
+        float e0f = static_cast<float>(e0);
+        if (fabsf(e0f) < 1e-6f) e0f = 0.f;
+        const float* B0 = Bs + fr * lay.b_pitch;
+        const float* B1 = B0 + lay.b_pitch;
+        run = 0.0;
+        double dsum = 0.0;
+        int bj = lo % YB_PASS_LAGS, bi = lo - bj;   // position of lag `lo` in a block-sum row (blocksum_index), stepped with tau
+        { const int bg = bj / YB_WG; bj -= bg * YB_WG; bi += bg; }
+#pragma unroll 1
+        for (int tau = lo; tau < hi; ++tau) {
+            const float u1 = fs(FFT_N / 2 + tau), u0 = fs(tau);
+            run += static_cast<double>(u1 * u1) - static_cast<double>(u0 * u0);
+            float e = static_cast<float>(base + run);
+            if (fabsf(e) < 1e-6f) e = 0.f;
+            float acf = B0[bi + 16 * bj] + B1[bi + 16 * bj];
+            if (++bj == YB_WG) {
+                bj = 0;
+                bi += ((bi & 15) == 15) ? YB_PASS_LAGS - 15 : 1;
+            }
+            if (fabsf(acf) < 1e-6f) acf = 0.f;
+            const float dv = (e0f + e) - 2.0f * acf;
+            dbuf[tau] = dv;
+            dsum += static_cast<double>(dv);
+        }
+        incl = warp_scan_incl_d(dsum, lane);
+        base = incl - dsum;
+        run = 0.0;
+        __syncwarp();
+#pragma unroll 1
+        for (int tau = lo; tau < hi; ++tau) {
+            run += static_cast<double>(dbuf[tau]);
+            if (tau >= minp) {
+                const double yv = cmnd_value(dbuf[tau], static_cast<double>(static_cast<float>(base + run)), tau);
+                yin[tau - minp] = yv;
+                if (p.cmnd_out != nullptr) p.cmnd_out[(static_cast<long long>(clip) * T + t) * L + (tau - minp)] = yv;
+            }
+        }
+        __syncwarp();
+        const YinTables tb{p.thresholds, p.beta_probs, p.beta_cumsum, p.boltz_fact, p.boltz_exp};
+        yin_candidates_of_frame<false>(p, tb, yin, L, minp, tk, tq, tp, lay.max_troughs, static_cast<long long>(clip) * T + t, lane);
+        __syncwarp();
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// hop == 512, two kernels (used when the caller provides the block-sum workspace): the FMA-bound block sums at 128
+// registers per thread, then everything per frame at high occupancy (the energy / CMND / candidate stage is a chain of
+// short dependent steps: it wants warps, not registers).
+// ------------------------------------------------------------------------------------------------------------------
 // block sums of blocks [16 run, 16 run + 16) of a clip -> bsum[clip][block][b_pitch] (lag tau at blocksum_index(tau)).
 // Persistent CTAs (two per SM) walk the runs; the samples of the NEXT run are requested with cp.async while this run's
 // sums are being accumulated, so the FMA pipe does not idle behind the fill at the start of every run.
@@ -928,9 +918,11 @@ extern "C" int aegis_yin_candidates(const aegis_yin_params* p, void* stream) {
     if (p->hop == 512) {   // no workspace: one kernel does both stages (15 frames per CTA)
         YinDirectLayout lay{};
         const int L = p->max_period - p->min_period + 1;
-        lay.n_groups = (p->max_period + 1 + 15) / 16;
-        lay.b_pitch = lay.n_groups * 16;
-        lay.off_b = ((YD_PHYS * 4 + 15) / 16) * 16;
+        lay.n_passes = (p->max_period + 1 + YB_PASS_LAGS - 1) / YB_PASS_LAGS;
+        AEGIS_REQUIRE(lay.n_passes <= YB_MAX_PASSES, "aegis_yin_candidates: max_period=%d needs more block-sum passes than compiled", p->max_period);
+        lay.span = YD_BLOCKS * 512 + 1 + lay.n_passes * YB_PASS_LAGS + 64;
+        lay.b_pitch = lay.n_passes * YB_PASS_LAGS;
+        lay.off_b = ((lay.span * 4 + 15) / 16) * 16;
         lay.off_warp = lay.off_b + ((YD_BLOCKS * lay.b_pitch * 4 + 15) / 16) * 16;
         lay.max_troughs = L / 2 + 1 < YIN_MAX_TROUGHS ? L / 2 + 1 : YIN_MAX_TROUGHS;
         int o = ((L * 8 + 15) / 16) * 16;

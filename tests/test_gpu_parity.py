@@ -443,12 +443,11 @@ def test_turbo_worker_and_parallel_pitch_tracking(dev):
     np.testing.assert_array_equal(tp, sp)
 
 
-def test_yin_split_kernels_are_batch_invariant_and_agree_with_the_fused_form(dev):
+def test_yin_fused_and_split_kernels_agree_bit_for_bit(dev):
     """K2 at hop 512 has two forms: block sums + per-frame stage as two kernels (with the workspace; the product path) or
-    one fused kernel (without).  A block sum depends only on its own samples and is summed in one fixed order, so a frame
-    gets identical bits in any batch / window it is analysed in.  The two forms sum the 512 float32 products of a block in
-    different orders (17-lag groups over two half-blocks vs 16-sample tiles over 32 lanes): they agree to float32
-    rounding of the block sums, not bit for bit.  Other hops take the FFT kernel."""
+    one fused kernel (without).  A block sum depends only on its own samples and both forms sum it with the same lane map
+    in the same order, so both forms -- and any batch / window a frame is analysed in -- give identical bits.  Other hops
+    take the FFT kernel (not bit-equal)."""
     for sr in (22050, 44100):
         y = np.stack([corpus.random_clip(40 + i, 3.0, sr) for i in range(3)])
         y[2, 20000:] = 0.0
@@ -457,23 +456,16 @@ def test_yin_split_kernels_are_batch_invariant_and_agree_with_the_fused_form(dev
         a = P.core.yin_candidates(yd, cfg, want_cmnd=True)
         b = P.core.yin_candidates(yd, cfg, want_cmnd=True, split=False)
         one = P.core.yin_candidates(yd[1:2], cfg, want_cmnd=True)
+        for k in ("cand_count", "voiced_prob", "cmnd"):
+            assert torch.equal(a[k], b[k]), (sr, k)
+        T = a["n_frames"]
+        cnt = a["cand_count"].view(3, T)
+        m = torch.arange(a["max_cand"], device=dev)[None, None, :] < cnt[:, :, None]
+        for k in ("cand_bin", "cand_prob"):
+            assert torch.equal(a[k].view(3, T, -1)[m], b[k].view(3, T, -1)[m]), (sr, k)
         assert torch.equal(a["cmnd"][1], one["cmnd"][0]) and torch.equal(a["voiced_prob"][1], one["voiced_prob"][0])
-        assert torch.equal(a["cand_count"].view(3, -1)[1], one["cand_count"].view(1, -1)[0])
-        # compared on frames that are not nearly silent: below ~1e-6 both forms zero the sums (as librosa does), and which side
-        # of that cut a sum lands on is rounding noise
-        rms = P.core.stft_features(yd, sr=sr, want_mag=False, want_rms=True)["rms"][:, : a["cmnd"].shape[1]]
-        loud = rms > 1e-2
-        d = (a["cmnd"] - b["cmnd"]).abs()[loud].flatten()
-        same_count = float((a["cand_count"].view(3, -1) == b["cand_count"].view(3, -1))[loud].float().mean())
-        dv = (a["voiced_prob"] - b["voiced_prob"]).abs()[loud].flatten()
-        print(f"sr {sr}: loud frames {int(loud.sum())}; |cmnd split - fused| median {float(d.median()):.2e} p99 {float(torch.quantile(d[:2_000_000], 0.99)):.2e} "
-              f"max {float(d.max()):.2e}; same candidate count {same_count:.4f}; |voiced_prob diff| p99 {float(torch.quantile(dv, 0.99)):.2e}")
-        assert int(loud.sum()) > 100
-        assert float(d.median()) < 2e-6 and float(torch.quantile(d[:2_000_000], 0.99)) < 1e-2
-        assert same_count > 0.98 and float(torch.quantile(dv, 0.99)) < 2e-2
-        # digital silence is exact in both
-        sil = slice(20000 // 512 + 5, None)
-        assert float(a["cmnd"][2, sil].abs().max()) == 0.0 and float(b["cmnd"][2, sil].abs().max()) == 0.0
+        sil = slice(20000 // 512 + 5, None)   # digital silence is exact
+        assert float(a["cmnd"][2, sil].abs().max()) == 0.0
 
 
 def test_pyin_batch_equals_single_and_handles_silence(dev):
