@@ -254,8 +254,14 @@ class TranscribePipeline:
         with torch.cuda.device(self.dev):
             n_sm = int(nat.load().aegis_device_sm_count())
         self.chunk = max(1, min(n_sm if chunk_clips is None else chunk_clips, n_clips))
-        # a group = up to two full waves of Viterbi chains (4 per SM each): the decoder's time per wave is nearly flat in the
-        # number of chains, so fewer, fuller launches win (measured, tools/pipeline_trace.py: 592 clips 17.4 ms, 432 clips 15.8 ms)
+        # a group = the clips of one decoder launch.  Full waves of Viterbi chains (4 per SM) use the SMs best, and one launch
+        # for everything (two waves for 1024 clips) is fastest when the step is COMPUTE-bound: 25.9 ms against 14.9 + 13.4 ms
+        # for 592 + 432 clips (tools/pipeline_trace.py).  When the step is COPY-bound (several ranks behind one host link: a
+        # piece lands every 7 ms and keeps the SMs busy for 3) the first wave's decode fits into the idle time under the
+        # remaining copies and only the last group's decode is left after the last piece.  group_clips=None decides from
+        # the first run's event times (copy per piece against kernels per piece) and keeps the choice.
+        self.n_sm = n_sm
+        self.auto_group = group_clips is None
         self.group = max(self.chunk, min(8 * n_sm if group_clips is None else group_clips, n_clips))
         self.T = T = core.frame_count(n_samples, hop_length)
         self.cfg = tables.pyin_config(float(sr), int(hop_length), float(fmin), float(fmax))
@@ -266,7 +272,7 @@ class TranscribePipeline:
         self.inbuf = torch.empty(self.in_shape, dtype=in_dtype, device=dev)
         self.copy_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, copy_streams))]
         self.pieces = list(range(0, n_clips, self.chunk))
-        self.landed = [torch.cuda.Event() for _ in self.pieces]
+        self.landed = [torch.cuda.Event(enable_timing=True) for _ in self.pieces]
         # batch-wide device buffers filled piece by piece
         self.obs = {"cand_bin": torch.empty((n_clips * T, mc), dtype=torch.int16, device=dev),
                     "cand_prob": torch.empty((n_clips * T, mc), dtype=torch.float64, device=dev),
@@ -341,17 +347,32 @@ class TranscribePipeline:
                 self.inbuf[c0 : c0 + self.chunk].copy_(y_host[c0 : c0 + self.chunk], non_blocking=True)
                 self.landed[i].record(cs)
         g0 = 0
+        probe = None
         for i, c0 in enumerate(self.pieces):
             c1 = min(self.n_clips, c0 + self.chunk)
             main.wait_event(self.landed[i])
             mark(f"piece {i} landed")
+            if self.auto_group and i == len(self.pieces) // 2:   # time one piece's kernels (first run only)
+                probe = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                probe[0].record(main)
             self._piece(c0, c1)
+            if probe is not None and i == len(self.pieces) // 2:
+                probe[1].record(main)
             mark(f"piece {i} K9+K1+K4+K2 done")
             if c1 - g0 >= self.group or c1 == self.n_clips:
                 self._group(g0, c1)
                 mark(f"group [{g0},{c1}) K3+K7+D2H issued/done")
                 g0 = c1
         main.synchronize()
+        if self.auto_group:
+            self.auto_group = False
+            if probe is not None and len(self.pieces) >= 4 and self.n_clips > 4 * self.n_sm:
+                k = len(self.pieces) // 2
+                copy_ms = self.landed[k].elapsed_time(self.landed[k + 1])       # one piece on the bus
+                kern_ms = probe[0].elapsed_time(probe[1])                       # one piece through K9 + K1 + K4 + K2
+                if copy_ms > 1.5 * kern_ms:
+                    self.group = max(self.chunk, (4 * self.n_sm // self.chunk) * self.chunk)   # copy-bound: decode wave by wave
+                self.group_decision = {"copy_ms_per_piece": copy_ms, "kernel_ms_per_piece": kern_ms, "group_clips": self.group}
         if trace is not None:
             trace[:] = [(label, start.elapsed_time(e)) for label, e in marks]
         return self.out

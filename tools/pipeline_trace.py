@@ -16,7 +16,7 @@ pipe = batch.TranscribePipeline(n_clips, int(dur * sr), sr=sr, device=dev, **kw)
 for _ in range(2): pipe.run(pcm)
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(3): pipe.run(pcm)
-torch.cuda.synchronize(); print(f"chunk {pipe.chunk} group {pipe.group}: {(time.perf_counter() - t0) / 3 * 1e3:.1f} ms per run")
+torch.cuda.synchronize(); print(f"chunk {pipe.chunk} group {pipe.group}: {(time.perf_counter() - t0) / 3 * 1e3:.1f} ms per run", getattr(pipe, "group_decision", None))
 pipe.trace = []
 pipe.run(pcm)
 for label, ms in pipe.trace: print(f"{ms:8.2f} ms  {label}")
