@@ -210,28 +210,43 @@ __device__ __forceinline__ void yin_candidates_of_frame(const aegis_yin_params& 
             }
         }
         __syncwarp();
-        //    ... and lane 0 emits them in ascending-bin order (= descending lag); equal bins: the larger lag wins
-        if (lane == 0) {
+        //    ... and they are emitted in ascending-bin order (= descending lag; bins never increase with the lag, so equal
+        //    bins are neighbours among the candidates): the larger lag wins.  32 troughs per round, lane l takes trough
+        //    hi - l; a candidate is kept unless the previous candidate in emission order has the same bin.
+        {
             unsigned short* ob = p.cand_bin + fidx * p.max_cand;
             double* op = p.cand_prob + fidx * p.max_cand;
             int last_bin = -1;
             bool over = false;
-            for (int i = nt - 1; i >= 0; --i) {
-                const int bin = tk[i];
-                if (bin == 0xffff) continue;
-                if (bin == last_bin) continue;        // overwritten by the later (larger-lag) write
-                last_bin = bin;
-                if (count < p.max_cand) {
-                    ob[count] = static_cast<unsigned short>(bin);
-                    const double pr = tp[i];
-                    op[count] = pr;
-                    vsum += pr;
-                    ++count;
-                } else {
-                    over = true;
+            for (int hi = nt - 1; hi >= 0; hi -= 32) {
+                const int i = hi - lane;
+                const int bin = i >= 0 ? tk[i] : 0xffff;
+                const bool valid = bin != 0xffff;
+                const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                const unsigned below = vm & ((1u << lane) - 1u);
+                const int prev = __shfl_sync(0xffffffffu, bin, below ? 31 - __clz(below) : 0);
+                const bool keep = valid && bin != (below ? prev : last_bin);
+                const unsigned km = __ballot_sync(0xffffffffu, keep);
+                const int pos = count + __popc(km & ((1u << lane) - 1u));
+                if (keep) {
+                    if (pos < p.max_cand) {
+                        ob[pos] = static_cast<unsigned short>(bin);
+                        op[pos] = tp[i];
+                    } else {
+                        over = true;
+                    }
                 }
+                count += __popc(km);
+                if (vm) last_bin = __shfl_sync(0xffffffffu, bin, 31 - __clz(vm));
             }
-            if (over) atomicExch(p.overflow, 1);
+            if (__any_sync(0xffffffffu, over)) {
+                if (lane == 0) atomicExch(p.overflow, 1);
+                count = p.max_cand;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                for (int c = 0; c < count; ++c) vsum += op[c];   // in emission order, as the oracle's row sum
+            }
         }
     }
     if (lane == 0) {
