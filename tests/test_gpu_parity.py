@@ -973,6 +973,22 @@ def test_pcm_ingest_and_load(dev, tmp_path):
         P.core.resample_poly(torch.zeros((1, 8), device=dev), 44100.5, 22050)
 
 
+def test_host_pipeline_chunking_does_not_change_results(dev):
+    """HostPipeline cuts its last chunk into a half and two quarters (so that little work is left once the last byte has
+    landed): 70 one-second clips in chunks of 16 (4 full chunks, then 3 + 2 + 1 clips... and 6 = 3 + 1 + 2) == one chunk
+    for everything == the device-level calls on the whole batch."""
+    sr, n_clips, n = 22050, 80, 22050
+    clips = corpus.clip_batch(n_clips, 1.0, sr, first_seed=900)
+    y = torch.from_numpy(clips).pin_memory()
+    whole = {k: v.clone() for k, v in P.batch.HostPipeline(n_clips, n, sr=sr, device=dev, chunk_clips=n_clips).run(y).items()}
+    for chunk in (16, 24):   # 5 pieces of 16 (the last tapered 8 + 4 + 4); 24, 24, 24, then 8 -> no taper below 16
+        got = P.batch.HostPipeline(n_clips, n, sr=sr, device=dev, chunk_clips=chunk).run(y)
+        for k in whole:
+            assert torch.equal(got[k], whole[k]), (chunk, k)
+    feat = P.core.stft_features(_dev(clips, dev), sr=sr, want_mag=False, want_rms=True)
+    assert torch.equal(whole["rms"], feat["rms"].cpu())
+
+
 def test_host_pipeline_pcm_ingest(dev):
     """HostPipeline fed with int16 PCM (same rate, and stereo 44.1 kHz) == HostPipeline fed with the float32 audio
     that numpy / scipy make of that PCM: the ingest kernel sits in front of an unchanged path."""
