@@ -234,6 +234,101 @@ onset_flux4_kernel(const aegis_melpost_params p, int groups_per_clip, int blocks
     }
 }
 
+// Rake mask only (no dB image stored, no onset envelope: the transcription step).  Same arithmetic per cell as
+// mel_post_kernel -- column maximum first, then one hardware log2 per cell, the broadband count against max - 20 dB, the
+// run-length gate over the flags of a 256-column CTA with 32-column halos -- but a thread owns FOUR consecutive columns
+// and reads them with one 16-byte load per mel row (the one-column kernel's warp request per row is 128 bytes).
+constexpr int MR_THREADS = MP_THREADS / 4;   // 64 threads = 256 columns, of which 2 x 32 are halo
+
+__global__ void __launch_bounds__(MR_THREADS)
+mel_rake4_kernel(const aegis_melpost_params p) {
+    __shared__ unsigned char flag[MP_THREADS];
+    const int clip = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int T = p.n_frames;
+    const int t0 = blockIdx.x * MP_OWN - MP_HALO + 4 * tid;          // first of this thread's four columns (a multiple of 4)
+    const bool any_in = t0 >= 0 && t0 < T;                           // t0 < 0: all four columns lie before the clip
+    const bool own = 4 * tid >= MP_HALO && 4 * tid < MP_HALO + MP_OWN;
+    const float* __restrict__ mel = p.mel + static_cast<long long>(clip) * p.mel_clip_stride;
+    const float amin = 1e-10f;
+    const float max_db = db10(fmaxf(amin, __ldg(p.mel_max + clip)));
+    const float ref_db = p.ref_power ? db10(fmaxf(amin, __ldg(p.ref_power + clip))) : max_db;
+    const float db_floor = (max_db - ref_db) - 80.0f;
+    constexpr int MB = 4;
+    float4 cmax = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (any_in) {
+        for (int m0 = 0; m0 < p.n_mels; m0 += MB) {
+            float4 raw[MB];
+#pragma unroll
+            for (int i = 0; i < MB; ++i)
+                raw[i] = (m0 + i < p.n_mels) ? __ldg(reinterpret_cast<const float4*>(mel + static_cast<long long>(m0 + i) * p.mel_row_stride + t0))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < MB; ++i) {
+                cmax.x = fmaxf(cmax.x, raw[i].x); cmax.y = fmaxf(cmax.y, raw[i].y);
+                cmax.z = fmaxf(cmax.z, raw[i].z); cmax.w = fmaxf(cmax.w, raw[i].w);
+            }
+        }
+    }
+    float col_max_db[4], thr[4];
+    int active[4] = {0, 0, 0, 0};
+    {
+        const float cm[4] = {cmax.x, cmax.y, cmax.z, cmax.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            col_max_db[j] = (any_in && t0 + j < T) ? fmaxf(db10(fmaxf(amin, cm[j])) - ref_db, db_floor) : -80.0f;
+            thr[j] = col_max_db[j] - 20.0f;
+        }
+    }
+    if (any_in) {
+        for (int m0 = 0; m0 < p.n_mels; m0 += MB) {
+            float4 raw[MB];
+#pragma unroll
+            for (int i = 0; i < MB; ++i)
+                raw[i] = (m0 + i < p.n_mels) ? __ldg(reinterpret_cast<const float4*>(mel + static_cast<long long>(m0 + i) * p.mel_row_stride + t0))
+                                             : make_float4(amin, amin, amin, amin);
+#pragma unroll
+            for (int i = 0; i < MB; ++i) {
+                if (m0 + i < p.n_mels) {
+                    const float v[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float db = fmaxf(db10(fmaxf(amin, v[j])) - ref_db, db_floor);
+                        active[j] += (db > thr[j]) ? 1 : 0;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        bool is_rake = false;
+        if (any_in && t0 + j < T && !(col_max_db[j] < -60.0f))
+            is_rake = (static_cast<double>(active[j]) / static_cast<double>(p.n_mels)) > p.rake_ratio;
+        flag[4 * tid + j] = is_rake ? 1 : 0;
+    }
+    __syncthreads();
+    if (own) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int t = t0 + j, c = 4 * tid + j;
+            if (t >= T) break;
+            bool keep = false;
+            if (flag[c]) {
+                const int maxf = p.rake_max_frames;
+                int left = 0;   // rake columns directly before t
+                while (left <= maxf && c - left - 1 >= 0 && t - left - 1 >= 0 && flag[c - left - 1]) ++left;
+                int right = 0;  // rake columns directly after t
+                while (right <= maxf && c + right + 1 < MP_THREADS && t + right + 1 < T && flag[c + right + 1]) ++right;
+                const int len = left + right + 1;
+                const bool closed = (t + right + 1) < T;  // a run still open at the last column is never emitted
+                keep = closed && left <= maxf && right <= maxf && len >= p.rake_min_frames && len <= maxf;
+            }
+            p.rake_mask[static_cast<long long>(clip) * T + t] = keep ? 1 : 0;
+        }
+    }
+}
+
 // candidate test of librosa.util.peak_pick on the normalised envelope, one thread per frame
 __global__ void __launch_bounds__(256)
 peak_candidates_kernel(const aegis_peaks_params p) {
@@ -319,6 +414,13 @@ extern "C" int aegis_mel_post(const aegis_melpost_params* p, void* stream) {
         AEGIS_REQUIRE(static_cast<long long>(blocks_per_clip) * p->n_clips < (1LL << 31), "aegis_mel_post: too many blocks for one launch");
         onset_flux4_kernel<<<static_cast<unsigned>(blocks_per_clip) * p->n_clips, OF_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*p, groups, blocks_per_clip);
         return check_launch("aegis_mel_post(onset flux)");
+    }
+    const bool rows16 = (p->mel_row_stride % 4) == 0 && (p->mel_clip_stride % 4) == 0 && (reinterpret_cast<uintptr_t>(p->mel) % 16) == 0 &&
+                        p->mel_row_stride >= ((p->n_frames + 3) / 4) * 4;
+    if (p->rake_mask != nullptr && p->s_db == nullptr && p->onset_env == nullptr && !p->input_is_db && rows16) {   // rake mask alone
+        dim3 grid4((p->n_frames + MP_OWN - 1) / MP_OWN, p->n_clips);
+        mel_rake4_kernel<<<grid4, MR_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*p);
+        return check_launch("aegis_mel_post(rake mask)");
     }
     const int own_n = p->rake_mask != nullptr ? MP_OWN : MP_THREADS;
     dim3 grid((p->n_frames + own_n - 1) / own_n, p->n_clips);

@@ -648,6 +648,36 @@ def test_note_events_batch_from_states(dev):
         assert _event_rows(got)[0].tolist() == _event_rows(ref)[0].tolist()
 
 
+def test_rake_mask_fast_path_equals_general_kernel(dev):
+    """The rake-mask-only kernel (four columns per thread, 16-byte loads; what the transcription step runs) and the general
+    mel_post kernel (one column per thread, used whenever the dB image or the onset envelope is wanted too) give identical
+    masks: synthetic mel images with broadband bursts of every length around the 20 ms .. 150 ms gate, placed across the
+    192-column CTA borders and at both ends of the clip, for frame counts that end anywhere inside a group of four."""
+    rng = np.random.default_rng(3)
+    total = 0
+    for T in (97, 386, 771, 1292, 1293, 1294, 1295):
+        pitch = (T + 3) // 4 * 4
+        buf = torch.zeros((5, 128, pitch), dtype=torch.float32, device=dev)
+        mel = rng.random((5, 128, T)).astype(np.float32) * 1e-4
+        mel[:, :20, :] += 0.5 * rng.random((5, 20, T)).astype(np.float32)          # a narrow-band "note": never a rake column
+        starts = list(rng.integers(0, T, size=40)) + [0, 1, T - 8, T - 3, 185, 190, 191, 192, 380]
+        for c in range(5):
+            for t0 in starts:
+                ln = int(rng.integers(1, 12))
+                mel[c, :, max(0, t0): max(0, t0) + ln] = (0.3 + 0.7 * rng.random((128, 1))).astype(np.float32)[:, : 1]   # broadband burst
+        buf[:, :, :T] = torch.from_numpy(mel).to(dev)
+        view = buf[:, :, :T]                       # rows padded to a multiple of four floats: the fast path's precondition
+        mx = view.amax(dim=(1, 2)).contiguous()
+        fast = P.core.mel_post(view, mx, sr=22050, want_sdb=False, want_rake=True)
+        slow = P.core.mel_post(view, mx, sr=22050, want_sdb=True, want_rake=True)
+        assert torch.equal(fast["rake_mask"], slow["rake_mask"]), T
+        tight = P.core.mel_post(torch.from_numpy(mel).to(dev), mx, sr=22050, want_sdb=False, want_rake=True)   # unpadded rows: general kernel
+        if T % 4:
+            assert torch.equal(tight["rake_mask"], slow["rake_mask"]), T
+        total += int(fast["rake_mask"].sum())
+    assert total > 50     # bursts that survive the run-length gate (overlapping bursts merge into runs that are too long)
+
+
 def test_onset_fast_path_equals_general_kernel(dev):
     """The onset-only kernel (four columns per thread, 16-byte loads) and the general mel_post kernel (one column per
     thread, used whenever the dB image or the rake mask is wanted) give bit-identical envelopes, extrema and peaks,
