@@ -87,6 +87,7 @@ struct VitSmem {
     unsigned short cand_bin[3][32];
     double cand_lp[3][32];                         // log(prob + tiny) of the listed candidates
     double lt_max;                                 // largest finite log transition of the whole table
+    int run_t;                                     // first frame a collapse run (warp 0 alone) left unprocessed
 };
 
 // table entry for (source row, same|switch, offset 0 <= o < W), any row
@@ -434,8 +435,147 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
         if (lane == 0) s.seg_hi[nxt][v][win] = 0xFFF00000u;
     };
 
+    // COLLAPSE RUN.  After a collapsed frame the whole decoder state is the (<= 32) candidate states of that frame; while
+    // the following frames collapse too, a frame is: for every candidate of frame t the strict first-index maximum over the
+    // candidates of frame t-1 (the arithmetic of viterbi_task_sparse, destination = the candidate's own bin), the collapse
+    // test on the same numbers, one back-pointer per candidate.  One WARP does that alone, lane = candidate, without the
+    // shared-memory images of V, without task counter and without CTA barrier, while the other warps wait; it stops at the
+    // first frame that does not collapse (or is the last one, or has no / too many candidates), rebuilds the images the
+    // general frame code expects (V[t-1] with chunk maxima and window bounds, the observation of frame t, the candidate
+    // lists of t-1 and t) and returns that frame's index.  Every collapse decision satisfies the bound of the file header
+    // (with max V[t-1] itself in place of its high-word bound), so the decoded path is unchanged.
+    auto collapse_run = [&](const int t0) -> int {
+        constexpr unsigned FULL = 0xffffffffu;
+        const int mc = p.max_cand;
+        int t = t0;
+        int Kp = s.cand_n[(t + 2) % 3];
+        int pb = 0;
+        double pv = NEG_INF;
+        if (lane < Kp) {
+            pb = s.cand_bin[(t + 2) % 3][lane];
+            pv = s.V[t & 1][0][VT_HALO + pb];
+        }
+        int K = s.cand_n[t % 3];
+        int cb = 0;
+        double clp = NEG_INF;
+        if (lane < min(K, 32)) {
+            cb = s.cand_bin[t % 3][lane];
+            clp = s.cand_lp[t % 3][lane];
+        }
+        double lpu = s.lp_u[t & 1];
+        bool dense = !(lpu > LOGTINY + 10.0);
+        // observations of the next two frames travel in registers (one DRAM round trip is longer than a frame of the run)
+        int ak = 0, abin = 0, bk = 0, bbin = 0;
+        double aprob = 0.0, avp = 0.0, bprob = 0.0, bvp = 0.0;
+        auto fetch = [&](const int f, int& k, int& bin, double& prob, double& vp) {
+            k = 0; bin = 0; prob = 0.0; vp = 0.0;
+            if (f < T) {
+                k = __ldg(ccnt + f);
+                vp = __ldg(vprob + f);
+                if (lane < mc) {
+                    bin = __ldg(cbin + static_cast<long long>(f) * mc + lane);
+                    prob = __ldg(cprob + static_cast<long long>(f) * mc + lane);
+                }
+            }
+        };
+        fetch(t + 1, ak, abin, aprob, avp);
+        fetch(t + 2, bk, bbin, bprob, bvp);
+        const double lt2 = 2.0 * s.lt_max;
+        while (dense && K >= 1 && K <= 32 && t < T - 1) {
+            double best = NEG_INF, inb = NEG_INF;
+            int arg = 0;
+#pragma unroll 1
+            for (int k = 0; k < Kp; ++k) {   // ascending bins, strict >: the first index wins a tie
+                const double x = __shfl_sync(FULL, pv, k);
+                const int c = __shfl_sync(FULL, pb, k);
+                const int o = cb - c + hw;
+                const bool in = static_cast<unsigned>(o) < static_cast<unsigned>(W);
+                const double tv = in ? lt_entry<W>(s, p, c, 0, o) : LOGTINY;
+                const double v = x + tv;
+                if (v > best) { best = v; arg = c; }
+                if (in && v > inb) inb = v;
+            }
+            const double lbmax = warp_max_d(lane < K ? clp + inb : NEG_INF);   // a real in-band candidate of a candidate state
+            const double vmax = warp_max_d(pv);
+            if (!(lbmax + LOGTINY > lpu + vmax + lt2 + 1e-6)) break;
+            const bool has = lane < K && clp > LOGTINY;
+            if (has) bp_out[static_cast<long long>(t) * (2 * n) + cb] = static_cast<unsigned short>(arg);
+            if (lane < K) {
+                s.prev[0][cb] = static_cast<unsigned short>(arg);
+                if (t == t0) s.obs_lp[t & 1][cb] = LOGTINY;   // the only frame of the run whose observation was scattered
+            }
+            Kp = K; pb = cb; pv = has ? clp + best : NEG_INF;
+            ++t;
+            K = min(ak, mc);
+            cb = lane < K ? abin : 0;
+            {
+                const double l = log(aprob + DBL_MIN);
+                clp = lane < K ? l : NEG_INF;
+            }
+            dense = avp == 1.0;   // <=> log((1 - vp) / n + tiny) <= log(tiny) + 10 for vp in [0, 1]
+            lpu = LOGTINY;
+            ak = bk; abin = bbin; aprob = bprob; avp = bvp;
+            fetch(t + 2, bk, bbin, bprob, bvp);
+        }
+        if (t == t0) return t0;
+        // ---- hand frame t to the general code: V[t-1] = the candidates of frame t-1, everything else -inf
+        const int cur = t & 1;
+        for (int w = 0; w < n_win; ++w) {
+            publish_empty(cur, 0, w);
+            publish_empty(cur, 1, w);
+        }
+        __syncwarp();
+        if (lane < Kp) {
+            s.V[cur][0][VT_HALO + pb] = pv;
+            s.cand_bin[(t + 2) % 3][lane] = static_cast<unsigned short>(pb);
+        }
+        unsigned pm = __reduce_or_sync(FULL, lane < Kp ? 1u << (pb >> 5) : 0u);
+        __syncwarp();
+        for (; pm; pm &= pm - 1) {
+            const int w = __ffs(pm) - 1, d = 32 * w + lane;
+            publish(cur, 0, w, d < n ? s.V[cur][0][VT_HALO + d] : NEG_INF);
+        }
+        const int Kt = min(__ldg(ccnt + t), mc);
+        unsigned wm = 0u;
+        for (int i = lane; i < Kt; i += 32) {
+            const int bin = __ldg(cbin + static_cast<long long>(t) * mc + i);
+            const double v = log(__ldg(cprob + static_cast<long long>(t) * mc + i) + DBL_MIN);
+            s.obs_lp[cur][bin] = v;
+            wm |= 1u << (bin >> 5);
+            if (i < 32) { s.cand_bin[t % 3][i] = static_cast<unsigned short>(bin); s.cand_lp[t % 3][i] = v; }
+        }
+        wm = __reduce_or_sync(FULL, wm);
+        if (lane == 0) {
+            s.cand_n[(t + 2) % 3] = Kp;
+            s.cand_n[t % 3] = Kt;
+            s.cand_windows[t % 3] = wm;
+            s.cand_windows[(t + 1) % 3] = 0u;
+            s.lp_u[cur] = log((1.0 - __ldg(vprob + t)) / static_cast<double>(n) + DBL_MIN);
+            s.next_task[0] = 0;
+            s.next_task[1] = 0;
+        }
+        return t;
+    };
+
     bool prev_collapsed = false;   // frame t-1 collapsed: V[t-1] holds nothing but its candidate states (warp-uniform, same in every warp)
+    bool just_ran = false;         // the previous iteration was a collapse run: frame t is the one it could not take
     for (int t = 0; t < T; ++t) {
+#ifndef VT_NO_RUN   // A/B builds only
+        if (prev_collapsed && !just_ran && t < T - 1) {
+            if (warp == 0) {
+                const int t1 = collapse_run(t);
+                if (lane == 0) s.run_t = t1;
+            }
+            __syncthreads();
+            const int t1 = s.run_t;
+            if (t1 != t) {
+                t = t1 - 1;
+                just_ran = true;
+                continue;
+            }
+        }
+        just_ran = false;
+#endif
         const int cur = t & 1, nxt = cur ^ 1;
         int ncnt = 0, nbin = 0;   // prefetch the next frame's sparse observation
         double nprob = 0.0;
