@@ -38,6 +38,10 @@
 //      without a candidate can win or tie anywhere in frame t+1, nor be the final state: the frame computes the voiced
 //      destinations of the windows that hold candidates and nothing else (all other values -inf, no back-pointers).
 //      The bounds use only V[t-1] and the candidate lists of frames t-1 and t, so every warp takes the same decision.
+//   5. COLLAPSE RUN: after a collapsed frame the decoder state is just that frame's (<= 32) candidate states.  While the
+//      following frames collapse too, ONE warp decodes them alone on the candidate lists (lane = candidate): no V images,
+//      no task queue, no CTA barrier; the other warps wait once.  The run ends at the first frame that does not collapse;
+//      the warp then rebuilds what the general frame code expects (see `collapse_run` in the kernel).
 // Rows of the transition table that differ in the last ulp (librosa's pairwise row sums) are kept as
 // "variants": the few interior ones in shared memory (padded with -inf so that no lane needs a range
 // check), the truncated edge rows in global memory (a source row is warp-uniform inside a chunk, the
@@ -53,7 +57,17 @@
 
 namespace aegis {
 
-constexpr int VT_MAX_BINS = 512;
+#ifndef VT_RUN_UNROLL
+#define VT_RUN_UNROLL 4      // sources of a collapse-run frame evaluated together (1, 2 or 4: 32 is a multiple)
+#endif
+#ifndef VT_RUN_PRECHECK
+#define VT_RUN_PRECHECK 0   // A/B timed: the test costs every frame more than the failed attempts it saves
+#endif
+
+#ifndef VT_MAX_BINS_DEF
+#define VT_MAX_BINS_DEF 512
+#endif
+constexpr int VT_MAX_BINS = VT_MAX_BINS_DEF;
 constexpr int VT_HALO = 64;            // V halo: sources outside [0, n) read -inf; needs half_width + 7 <= 64
 constexpr int VT_MAX_HW = 50;
 constexpr int VT_MAX_W = 2 * VT_MAX_HW + 1;
@@ -449,10 +463,12 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
         const int mc = p.max_cand;
         int t = t0;
         int Kp = s.cand_n[(t + 2) % 3];
-        int pb = 0;
+        // previous frame, lane = candidate: value, and bin | table offset of its row << 16 (one shuffle brings both)
+        int pq = s.rowoff[VT_HALO] << 16;
         double pv = NEG_INF;
         if (lane < Kp) {
-            pb = s.cand_bin[(t + 2) % 3][lane];
+            const int pb = s.cand_bin[(t + 2) % 3][lane];
+            pq = pb | (s.rowoff[VT_HALO + pb] << 16);
             pv = s.V[t & 1][0][VT_HALO + pb];
         }
         int K = s.cand_n[t % 3];
@@ -481,19 +497,37 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
         fetch(t + 1, ak, abin, aprob, avp);
         fetch(t + 2, bk, bbin, bprob, bvp);
         const double lt2 = 2.0 * s.lt_max;
+        // one source: candidate k of frame t-1 against this lane's destination (lanes >= Kp hold -inf: they never win)
+        auto source = [&](const int k, double& v, int& c, bool& in) {
+            const double x = __shfl_sync(FULL, pv, k);
+            const int q = __shfl_sync(FULL, pq, k);
+            c = q & 0xFFFF;
+            const unsigned off = static_cast<unsigned>(q) >> 16;
+            const int o = cb - c + hw;
+            in = static_cast<unsigned>(o) < static_cast<unsigned>(W);
+            double tv = LOGTINY;
+            if (in) {
+                if (!(off & VT_EDGE_BIT)) tv = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(&s.lt[0][0][VT_LT_PAD + o]) + off);
+                else tv = __ldg(p.lt_variants + (off & 0x7FFFu) + o);
+            }
+            v = x + tv;
+        };
         while (dense && K >= 1 && K <= 32 && t < T - 1) {
+            const int cro = s.rowoff[VT_HALO + cb];   // needed when this frame has become the previous one
             double best = NEG_INF, inb = NEG_INF;
             int arg = 0;
 #pragma unroll 1
-            for (int k = 0; k < Kp; ++k) {   // ascending bins, strict >: the first index wins a tie
-                const double x = __shfl_sync(FULL, pv, k);
-                const int c = __shfl_sync(FULL, pb, k);
-                const int o = cb - c + hw;
-                const bool in = static_cast<unsigned>(o) < static_cast<unsigned>(W);
-                const double tv = in ? lt_entry<W>(s, p, c, 0, o) : LOGTINY;
-                const double v = x + tv;
-                if (v > best) { best = v; arg = c; }
-                if (in && v > inb) inb = v;
+            for (int k = 0; k < Kp; k += VT_RUN_UNROLL) {   // ascending bins, strict >: the first index wins a tie; VT_RUN_UNROLL sources in flight
+                double v[VT_RUN_UNROLL];
+                int c[VT_RUN_UNROLL];
+                bool in[VT_RUN_UNROLL];
+#pragma unroll
+                for (int j = 0; j < VT_RUN_UNROLL; ++j) source(k + j, v[j], c[j], in[j]);
+#pragma unroll
+                for (int j = 0; j < VT_RUN_UNROLL; ++j) {
+                    if (v[j] > best) { best = v[j]; arg = c[j]; }
+                    if (in[j] && v[j] > inb) inb = v[j];
+                }
             }
             const double lbmax = warp_max_d(lane < K ? clp + inb : NEG_INF);   // a real in-band candidate of a candidate state
             const double vmax = warp_max_d(pv);
@@ -504,7 +538,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
                 s.prev[0][cb] = static_cast<unsigned short>(arg);
                 if (t == t0) s.obs_lp[t & 1][cb] = LOGTINY;   // the only frame of the run whose observation was scattered
             }
-            Kp = K; pb = cb; pv = has ? clp + best : NEG_INF;
+            Kp = K; pq = cb | (cro << 16); pv = has ? clp + best : NEG_INF;
             ++t;
             K = min(ak, mc);
             cb = lane < K ? abin : 0;
@@ -517,6 +551,7 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
             ak = bk; abin = bbin; aprob = bprob; avp = bvp;
             fetch(t + 2, bk, bbin, bprob, bvp);
         }
+        const int pb = pq & 0xFFFF;
         if (t == t0) return t0;
         // ---- hand frame t to the general code: V[t-1] = the candidates of frame t-1, everything else -inf
         const int cur = t & 1;
@@ -561,7 +596,12 @@ viterbi_forward_kernel(const aegis_viterbi_params p) {
     bool just_ran = false;         // the previous iteration was a collapse run: frame t is the one it could not take
     for (int t = 0; t < T; ++t) {
 #ifndef VT_NO_RUN   // A/B builds only
+        // (a frame with voiced_prob < 1 or without / with too many candidates cannot collapse: no attempt, no barrier)
+#if VT_RUN_PRECHECK
+        if (prev_collapsed && !just_ran && t < T - 1 && !(s.lp_u[t & 1] > LOGTINY + 10.0) && s.cand_n[t % 3] >= 1 && s.cand_n[t % 3] <= 32) {
+#else
         if (prev_collapsed && !just_ran && t < T - 1) {
+#endif
             if (warp == 0) {
                 const int t1 = collapse_run(t);
                 if (lane == 0) s.run_t = t1;
@@ -843,6 +883,10 @@ static int launch_forward(const aegis_viterbi_params* p, cudaStream_t st) {
     // warps per CTA (tasks are pulled dynamically, so any count works): A/B timed through AEGIS_VT_WARPS
     static const int forced = []() { const char* e = getenv("AEGIS_VT_WARPS"); return e ? atoi(e) : 0; }();
     nw = forced ? forced : (n_win <= 14 ? 7 : 8);
+#ifdef VT_FIVE   // A/B builds only (needs VT_MAX_BINS_DEF <= 448 for five CTAs per SM)
+    if (nw == 5) kern = viterbi_forward_kernel<HW, 5, 5>;
+    else
+#endif
     if (nw == 6) kern = viterbi_forward_kernel<HW, 6, 4>;
     else if (nw == 7) kern = viterbi_forward_kernel<HW, 7, 4>;     // 441 bins (E2..C6): 7 warps, four clips per SM
     else { kern = viterbi_forward_kernel<HW, 8, 4>; nw = 8; }      // up to 512 bins

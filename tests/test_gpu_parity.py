@@ -292,6 +292,75 @@ def test_viterbi_adversarial_observations(dev):
         np.testing.assert_array_equal(dec["states"][0].cpu().numpy().astype(np.uint16), ref, err_msg=f"trial {trial}")
 
 
+def test_viterbi_collapse_runs_equal_dense_decoder(dev):
+    """Long stretches of voiced_prob == 1 frames (K3 decodes them in its one-warp collapse run) with everything that can end,
+    interrupt or stress a run: slowly drifting note candidates with octave partners, far jumps (out-of-band transitions),
+    equal candidate masses (ties), a candidate whose mass is exactly zero, frames with 33..40 candidates in the middle of a
+    run and as its first frame, single voiced_prob < 1 frames, silence, a run that reaches the last frame, runs at the edge
+    bins.  The decoded states must equal the dense float64 decoder's (oracle) exactly."""
+    sr = 22050
+    cfg = tables.pyin_config(float(sr), 512, E2, C6)
+    n = cfg.n_pitch_bins
+    assert cfg.max_troughs >= 40
+    trans, _ = L.pyin_transition(n, 10, sr, 512)
+    p_init = np.zeros(2 * n)
+    p_init[n:] = 1 / n
+    rng = np.random.default_rng(23)
+    for trial in range(4):
+        T = 260
+        obs = np.zeros((2 * n, T))
+        centre = [int(rng.integers(60, n - 60)), 3, n - 4, int(rng.integers(0, n))][trial]
+        t = 0
+        while t < T:
+            kind = rng.random()
+            if kind < 0.70:      # a run of exact voiced_prob == 1 frames
+                ln = int(rng.integers(2, 60))
+                for u in range(t, min(T, t + ln)):
+                    centre = int(np.clip(centre + rng.integers(-2, 3), 0, n - 1))
+                    if rng.random() < 0.04:
+                        centre = int(rng.integers(0, n))          # far jump inside the run
+                    k = int(rng.integers(1, 5))
+                    if rng.random() < 0.03:
+                        k = int(rng.integers(33, 41))              # more candidates than a run can hold
+                    bins = {centre}
+                    while len(bins) < k:
+                        bins.add(int(np.clip(centre + rng.choice([-120, -70, -12, -1, 1, 12, 70, 120]) + rng.integers(-3, 4), 0, n - 1)) if k < 8 else int(rng.integers(0, n)))
+                    bins = sorted(bins)
+                    if rng.random() < 0.3:
+                        pr = np.full(len(bins), 1.0 / len(bins))   # ties between candidates
+                        if len(bins) in (2, 4, 8):                  # masses that sum to exactly 1
+                            pass
+                        else:
+                            pr = rng.dirichlet(np.ones(len(bins)))
+                    else:
+                        pr = rng.dirichlet(np.ones(len(bins)))
+                    obs[bins, u] = pr
+                    if len(bins) > 1 and rng.random() < 0.05:
+                        obs[bins[0], u] = 0.0                      # drops out of the sparse list: the frame is no longer exactly 1
+                t += ln
+            elif kind < 0.85:    # one or two frames with voiced_prob < 1
+                for u in range(t, min(T, t + int(rng.integers(1, 3)))):
+                    k = int(rng.integers(0, 4))
+                    bins = rng.choice(n, size=k, replace=False)
+                    obs[bins, u] = rng.random(k) * 0.3 / max(1, k)
+                t += 2
+            else:                # silence
+                t += int(rng.integers(1, 6))
+        if trial == 1:
+            obs[:n, T - 5:] = 0.0
+            obs[3, T - 5:] = 1.0                                    # the run reaches the last frame
+        vp = np.clip(obs[:n].sum(axis=0, keepdims=True), 0, 1)
+        snap = np.abs(vp - 1.0) < 1e-12
+        vp[snap] = 1.0                                             # what K2 hands over when the masses sum to one
+        obs[n:, :] = (1 - vp) / n
+        assert (vp == 1.0).mean() > 0.4
+        ref = L.viterbi(obs, trans, p_init)
+        sp = _sparse_from_dense(obs, n, cfg.max_troughs, dev)
+        sp["voiced_prob"] = torch.from_numpy(vp).to(dev)
+        dec = P.core.viterbi_decode(sp, cfg, 1)
+        np.testing.assert_array_equal(dec["states"][0].cpu().numpy().astype(np.uint16), ref, err_msg=f"trial {trial}")
+
+
 def _dense_obs(obs, n):
     T = obs["n_frames"]
     cb = obs["cand_bin"].cpu().numpy().astype(np.int64)
